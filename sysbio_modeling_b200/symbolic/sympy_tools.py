@@ -1,0 +1,603 @@
+"""Symbolic front-end: model file / RHS callable -> SymPy -> {Python RHS, CUDA device functions}.
+
+Role on the hot path: the reference turns a ``#*!``-delimited model
+file into SymPy expressions, derives the forward-sensitivity equations
+``dS_ij/dt = df_i/dp_j + sum_k df_i/dy_k S_kj`` and writes Python source that numba compiles
+(reference ``symbolic/sympy_tools.py:130-146, 162-216, 272-397``).  This module keeps that front
+end (same section markers, same ``yout[N + i*P_free + j]`` layout for the Python emitter, which
+feeds the CPU oracle) and adds the CUDA emitter the B200 kernels are built from.
+
+The CUDA emitter does NOT print the expanded sensitivity equations.  It prints three pieces that
+the integrator kernels combine per lane (see ``csrc/kernels/sbm_ode_kernels.cuh``):
+
+* ``sbm_f``      - the RHS f(t, y, p);
+* ``sbm_fJG``    - f plus the structural non-zeros of J = df/dy and G = df/dp_free, CSE'd together;
+* ``sbm_col``    - one column of the augmented RHS: ``f`` for the state column, else
+                   ``J*s + G[:, j]`` for sensitivity column j, with the lane-dependent pick of
+                   ``G[:, j]`` done by integer selects (ALU pipe, not the FP64 pipe);
+* ``sbm_jac_dense`` / ``sbm_dfdt`` - dense state Jacobian and time derivative for the Rosenbrock kernel.
+
+Nothing here is copied from the reference; the model-file grammar and output layouts are kept so
+that reference users can reuse their model files.
+"""
+from __future__ import annotations
+
+import hashlib
+import inspect
+import io
+import textwrap
+from collections import OrderedDict
+from dataclasses import dataclass, field
+
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+from sympy.printing.pycode import PythonCodePrinter
+
+CATEGORIES = OrderedDict([
+    ('Parameters', False), ('Variables', False), ('Conservation Laws', True),
+    ('Rate Laws', True), ('Differential Equations', True), ('Imports', False),
+])
+
+T_SYM = sp.Symbol('t', real=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# Parsing
+# ----------------------------------------------------------------------------------------------
+def _model_text(model):
+    """Accept a path, an open file, a text blob or a python function (reference :285-297)."""
+    if hasattr(model, 'py_func'):          # numba dispatcher
+        model = model.py_func
+    if inspect.isfunction(model):
+        return inspect.getsource(model)
+    if isinstance(model, str):
+        if '#*!' in model:
+            return model
+        with open(model, 'r') as fh:
+            return fh.read()
+    if hasattr(model, 'read'):
+        text = model.read()
+        return text
+    raise TypeError('model must be a path, file handle, source text or function')
+
+
+def _chunk(text, category):
+    start = text.find('#*! %s Start' % category)
+    end = text.find('#*! %s End' % category)
+    if start < 0 or end < 0:
+        return []
+    return text[start:end].split('\n')[1:]
+
+
+def _clean(line):
+    line = line.split('#')[0]
+    return line.replace(' ', '').replace('\t', '').strip()
+
+
+def parse_model_file(model):
+    """Parse a ``#*!``-delimited model description into ordered dicts of SymPy objects.
+
+    Same section names as the reference (``sympy_tools.py:300-311``).  Returns a dict with keys
+    'Parameters', 'Variables' (name -> Symbol, in file order), 'Conservation Laws', 'Rate Laws',
+    'Differential Equations' (name -> expression) and 'Imports' (raw lines).
+    Unlike the reference, every declared name is bound to a plain Symbol before the right-hand
+    sides are parsed, so species called ``S``, ``E``, ``N``... do not collide with SymPy globals.
+    """
+    text = _model_text(model)
+    names = OrderedDict()
+    parsed = {}
+    for category in ('Parameters', 'Variables'):
+        d = OrderedDict()
+        for raw in _chunk(text, category):
+            line = _clean(raw)
+            if not line or '=' not in line:
+                continue
+            lhs = line[:line.find('=')]
+            d[lhs] = sp.Symbol(lhs, real=True)
+            names[lhs] = d[lhs]
+        parsed[category] = d
+
+    # left-hand sides of laws are names too (they get substituted away)
+    law_lines = {}
+    for category in ('Conservation Laws', 'Rate Laws', 'Differential Equations'):
+        rows = []
+        for raw in _chunk(text, category):
+            line = _clean(raw)
+            if not line or '=' not in line:
+                continue
+            lhs, rhs = line[:line.find('=')], line[line.find('=') + 1:]
+            rows.append((lhs, rhs))
+            if category != 'Differential Equations' and lhs not in names:
+                names[lhs] = sp.Symbol(lhs, real=True)
+        law_lines[category] = rows
+
+    symtab = dict(names)
+    symtab['t'] = T_SYM
+    for category, rows in law_lines.items():
+        d = OrderedDict()
+        for lhs, rhs in rows:
+            d[lhs] = sp.sympify(rhs, locals=symtab)
+        parsed[category] = d
+    parsed['Imports'] = [l for l in _chunk(text, 'Imports') if l.strip()]
+    return parsed
+
+
+# ----------------------------------------------------------------------------------------------
+# Symbolic model container
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class SymbolicModel:
+    """f(t, y, p) with its structural derivatives.
+
+    ``J[(i, k)] = df_i/dy_k`` and ``G[(i, j)] = df_i/dp_free[j]`` hold non-zero entries only.
+    ``free`` lists the non-fixed parameters in ``param_order`` order - this is the column order of
+    the reference's sensitivity block (``sympy_tools.py:135-145``: variable-major, free-param-minor).
+    """
+    name: str
+    variables: list
+    var_syms: list
+    param_order: list
+    param_syms: list
+    f: list
+    fixed: list = field(default_factory=list)
+    J: dict = field(default_factory=dict)
+    G: dict = field(default_factory=dict)
+    dfdt: list = field(default_factory=list)
+
+    def __post_init__(self):
+        self.fixed = [p for p in self.param_order if p in set(self.fixed)]
+        self.free = [p for p in self.param_order if p not in set(self.fixed)]
+        self.free_idx = [self.param_order.index(p) for p in self.free]
+        self._derive()
+
+    @property
+    def n_vars(self):
+        return len(self.variables)
+
+    @property
+    def n_params(self):
+        return len(self.param_order)
+
+    @property
+    def n_free(self):
+        return len(self.free)
+
+    @property
+    def autonomous(self):
+        return all(d == 0 for d in self.dfdt)
+
+    def _derive(self):
+        self.J, self.G = {}, {}
+        for i, fi in enumerate(self.f):
+            for k, yk in enumerate(self.var_syms):
+                d = sp.diff(fi, yk)
+                if d != 0:
+                    self.J[(i, k)] = d
+            for j, m in enumerate(self.free_idx):
+                d = sp.diff(fi, self.param_syms[m])
+                if d != 0:
+                    self.G[(i, j)] = d
+        self.dfdt = [sp.diff(fi, T_SYM) for fi in self.f]
+
+    def with_fixed(self, fixed_params):
+        fixed_params = list(fixed_params or [])
+        for p in fixed_params:
+            if p not in self.param_order:
+                raise KeyError('%s not in model parameters' % p)
+        return SymbolicModel(self.name, self.variables, self.var_syms, self.param_order,
+                             self.param_syms, self.f, fixed_params)
+
+    def sens_symbols(self):
+        """Symbols ``sens_<var>_<par>`` in the reference's augmented-state order."""
+        return [[sp.Symbol('sens_%s_%s' % (v.lstrip('_'), p), real=True) for p in self.free]
+                for v in self.variables]
+
+    def sensitivity_equations(self):
+        """Expanded dS_ij/dt, row-major (i, j) - reference ``_derive_sensitivity_equations``."""
+        S = self.sens_symbols()
+        out = []
+        for i in range(self.n_vars):
+            for j in range(self.n_free):
+                e = self.G.get((i, j), sp.Integer(0))
+                for k in range(self.n_vars):
+                    if (i, k) in self.J:
+                        e = e + self.J[(i, k)] * S[k][j]
+                out.append(e)
+        return out
+
+    def fingerprint(self):
+        h = hashlib.sha256()
+        h.update(repr((self.variables, self.param_order, self.fixed,
+                       [sp.srepr(e) for e in self.f])).encode())
+        return h.hexdigest()[:16]
+
+
+def _state_symbol_for(eq_name, variables):
+    """Map a ``d_x`` left-hand side to the declared state it differentiates (``x`` or ``_x``)."""
+    base = eq_name[2:] if eq_name.startswith('d_') else eq_name
+    for cand in (base, '_' + base):
+        if cand in variables:
+            return cand
+    raise KeyError('differential equation %s does not match any declared variable' % eq_name)
+
+
+def symbolic_model_from_dict(model_dict, name='Model', fixed_params=None, simplify=False):
+    """Expand rate and conservation laws into the ODEs (reference :351-353) and build the model."""
+    params = model_dict['Parameters']
+    variables = model_dict['Variables']
+    rate_laws = model_dict.get('Rate Laws') or {}
+    cons_laws = model_dict.get('Conservation Laws') or {}
+    eqns = model_dict['Differential Equations']
+
+    def expand(e):
+        # laws may refer to each other: substitute to a fixed point
+        for _ in range(8):
+            new = e
+            if rate_laws:
+                new = new.subs({sp.Symbol(k, real=True): v for k, v in rate_laws.items()})
+            if cons_laws:
+                new = new.subs({sp.Symbol(k, real=True): v for k, v in cons_laws.items()})
+            if new == e:
+                break
+            e = new
+        return sp.simplify(e) if simplify else e
+
+    by_var = {}
+    for lhs, rhs in eqns.items():
+        by_var[_state_symbol_for(lhs, variables)] = expand(rhs)
+    missing = [v for v in variables if v not in by_var]
+    if missing:
+        raise KeyError('no differential equation for variables: %s' % ', '.join(missing))
+    var_names = list(variables.keys())
+    return SymbolicModel(name, var_names, [variables[v] for v in var_names],
+                         list(params.keys()), list(params.values()),
+                         [by_var[v] for v in var_names], list(fixed_params or []))
+
+
+def symbolic_model_from_file(model, name='Model', fixed_params=None, simplify=False):
+    return symbolic_model_from_dict(parse_model_file(model), name, fixed_params, simplify)
+
+
+def trace_rhs_callable(model, n_vars, param_order, name='Model', fixed_params=None):
+    """Recover f symbolically from a reference-ABI callable ``model(y, t, yout, p)``.
+
+    The reference's ``OdeModel`` is handed plain Python functions (``ode_model.py:27-29``; RHS ABI
+    ``void f(y, t, yout, p)``, :50-51).  Calling such a function on SymPy symbols executes its
+    arithmetic symbolically, which is how ``OdeModel(backend='cuda')`` stays a drop-in for models
+    that exist only as generated Python (e.g. reference ``tests/test_utils/jittable_model.py``).
+    """
+    if hasattr(model, 'py_func'):
+        model = model.py_func
+    ys = [sp.Symbol('y%d' % i, real=True) for i in range(n_vars)]
+    ps = [sp.Symbol(str(p), real=True) for p in param_order]
+    yout = [sp.Integer(0)] * n_vars
+    model(ys, T_SYM, yout, ps)
+    return SymbolicModel(name, ['y%d' % i for i in range(n_vars)], ys, [str(p) for p in param_order],
+                         ps, [sp.sympify(e) for e in yout], list(fixed_params or []))
+
+
+# ----------------------------------------------------------------------------------------------
+# Reference-shaped API (dict in / dict out)
+# ----------------------------------------------------------------------------------------------
+def process_model_dict(model_dict, fixed_params=None, calculate_model_sensitivities=True,
+                       simplify_subexpressions=False, calculate_model_jacobian=False):
+    """Reference-shaped driver (``sympy_tools.py:325-397``): fills 'Sensitivity Equations',
+    'Model Jacobian Equations' and 'Subexpressions' and stores the SymbolicModel under 'Symbolic'."""
+    sm = symbolic_model_from_dict(model_dict, fixed_params=fixed_params)
+    model_dict['Symbolic'] = sm
+    if fixed_params:
+        for p in fixed_params:
+            model_dict['Parameters'][p] = 'fixed'
+    sens = None
+    if calculate_model_sensitivities:
+        sens = OrderedDict()
+        eqs = sm.sensitivity_equations()
+        q = 0
+        for v in sm.variables:
+            for p in sm.free:
+                sens['d_sens_%s_%s' % (v.lstrip('_'), p)] = eqs[q]
+                q += 1
+    model_dict['Sensitivity Equations'] = sens
+    jac = None
+    if calculate_model_jacobian:
+        jac = OrderedDict()
+        for i, vi in enumerate(sm.variables):
+            for k, vk in enumerate(sm.variables):
+                jac['d_%s_d_%s' % (vi, vk)] = sm.J.get((i, k), sp.Integer(0))
+    model_dict['Model Jacobian Equations'] = jac
+    sub = None
+    if simplify_subexpressions:
+        exprs = list(sm.f) + (list(sens.values()) if sens else [])
+        rep, red = sp.cse(exprs, optimizations='basic')
+        sub = OrderedDict(rep)
+        model_dict['Reduced Equations'] = red
+    model_dict['Subexpressions'] = sub
+    return model_dict
+
+
+# ----------------------------------------------------------------------------------------------
+# Operation counting (the ALGORITHMIC flop model of DESIGN.md)
+# ----------------------------------------------------------------------------------------------
+def count_flops(exprs):
+    """1 per add/sub/mul/div; integer power k costs k-1 multiplies (+1 divide if negative);
+    real pow / exp / log / other functions cost 1 each.  An FMA therefore counts 2."""
+    total = 0
+    for e in exprs:
+        for node in sp.preorder_traversal(e):
+            if isinstance(node, sp.Add) or isinstance(node, sp.Mul):
+                n = len(node.args)
+                # a leading -1 coefficient is a sign flip folded into the add/sub, not a multiply
+                if isinstance(node, sp.Mul) and node.args[0] == -1:
+                    n -= 1
+                total += max(n - 1, 0)
+            elif isinstance(node, sp.Pow):
+                ex = node.exp
+                if ex.is_Integer:
+                    k = abs(int(ex))
+                    total += max(k - 1, 0) + (1 if ex < 0 else 0)
+                else:
+                    total += 1
+            elif isinstance(node, sp.Function):
+                total += 1
+    return total
+
+
+# ----------------------------------------------------------------------------------------------
+# Printers
+# ----------------------------------------------------------------------------------------------
+class sbm_rcp(sp.Function):
+    """Explicit reciprocal node: lets CSE share 1/x between x**-1, x**-2, ... (one divide each)."""
+    nargs = 1
+
+    def fdiff(self, argindex=1):
+        return -sbm_rcp(self.args[0]) ** 2
+
+
+def _share_reciprocals(e):
+    """Rewrite x**-k as sbm_rcp(x)**k so that the emitted code divides once per denominator."""
+    return e.replace(lambda n: n.is_Pow and n.exp.is_Integer and n.exp < 0,
+                     lambda n: sbm_rcp(n.base) ** (-n.exp))
+
+
+class _CudaPrinter(C99CodePrinter):
+    """C printer that expands small integer powers into multiplies and reciprocals."""
+
+    def _print_sbm_rcp(self, expr):
+        return '(1.0/(%s))' % self._print(expr.args[0])
+
+    def _print_Pow(self, expr):
+        base, ex = expr.base, expr.exp
+        if ex.is_Integer and 1 <= abs(int(ex)) <= 8:
+            b = self.parenthesize(base, 1000)
+            prod = '*'.join([b] * abs(int(ex)))
+            if ex > 0:
+                return '(%s)' % prod
+            return '(1.0/(%s))' % prod
+        if ex == sp.Rational(1, 2):
+            return 'sqrt(%s)' % self._print(base)
+        if ex == -sp.Rational(1, 2):
+            return 'rsqrt(%s)' % self._print(base)
+        return 'pow(%s, %s)' % (self._print(base), self._print(ex))
+
+    def _print_Integer(self, expr):
+        return '%d.0' % int(expr)
+
+    def _print_Rational(self, expr):
+        return '(%d.0/%d.0)' % (expr.p, expr.q)
+
+
+class _PyPrinter(PythonCodePrinter):
+    def _print_Pow(self, expr, rational=False):
+        base, ex = expr.base, expr.exp
+        if ex.is_Integer and 1 <= abs(int(ex)) <= 4:
+            b = self.parenthesize(base, 1000)
+            prod = '*'.join([b] * abs(int(ex)))
+            return '(%s)' % prod if ex > 0 else '(1.0/(%s))' % prod
+        return '(%s)**(%s)' % (self.parenthesize(base, 1000), self._print(ex))
+
+
+_PY_FUNCS = {'math.exp': 'exp', 'math.log': 'log', 'math.sqrt': 'sqrt', 'math.sin': 'sin',
+             'math.cos': 'cos', 'math.tanh': 'tanh'}
+
+
+def _py(expr):
+    s = _PyPrinter({'fully_qualified_modules': True}).doprint(expr)
+    for k, v in _PY_FUNCS.items():
+        s = s.replace(k, v)
+    return s
+
+
+# ----------------------------------------------------------------------------------------------
+# Python emitter (reference ABI; feeds the CPU oracle and the reference arm of bench.py)
+# ----------------------------------------------------------------------------------------------
+def emit_python(sm, sensitivities=True, cse=True, fcn_name=None):
+    """Source of ``model(y, t, yout, p)`` or ``sens_model(y, t, yout, p)`` in the reference's
+    generated-file format (``sympy_tools.py:38-127,185-195``): ``yout[0:N] = f`` and
+    ``yout[N + i*P_free + j] = dS_ij/dt``.  Pure arithmetic, so ``numba.jit`` accepts it
+    (``ode_model.py:50-51``)."""
+    fcn_name = fcn_name or ('sens_model' if sensitivities else 'model')
+    exprs = list(sm.f)
+    S = sm.sens_symbols()
+    if sensitivities:
+        exprs += sm.sensitivity_equations()
+    if cse:
+        rep, red = sp.cse(exprs, symbols=sp.numbered_symbols('x_'), optimizations='basic')
+    else:
+        rep, red = [], exprs
+    pad = '    '
+    L = ['from math import exp, log, sqrt, sin, cos, tanh', '',
+         'ordered_params = [%s]' % ', '.join("'%s'" % p for p in sm.param_order),
+         'n_vars = %d' % sm.n_vars,
+         'free_params = [%s]' % ', '.join("'%s'" % p for p in sm.free), '', '',
+         'def %s(y, t, yout, p):' % fcn_name]
+    for m, ps in enumerate(sm.param_syms):
+        L.append(pad + '%s = p[%d]' % (ps, m))
+    for i, ys in enumerate(sm.var_syms):
+        L.append(pad + '%s = y[%d]' % (ys, i))
+    if sensitivities:
+        for i in range(sm.n_vars):
+            for j in range(sm.n_free):
+                L.append(pad + '%s = y[%d]' % (S[i][j], sm.n_vars + i * sm.n_free + j))
+    for lhs, rhs in rep:
+        L.append(pad + '%s = %s' % (lhs, _py(rhs)))
+    for q, e in enumerate(red):
+        L.append(pad + 'yout[%d] = %s' % (q, _py(e)))
+    return '\n'.join(L) + '\n'
+
+
+def make_ode_model(sm, sensitivities=False, cse=True, output_fh=None):
+    """Exec the emitted Python and return the callable (reference ``make_ode_model`` :162-216)."""
+    src = emit_python(sm, sensitivities=sensitivities, cse=cse)
+    if output_fh is not None:
+        output_fh.write(src)
+    ns = {}
+    exec(compile(src, '<sbm generated %s>' % sm.name, 'exec'), ns)
+    fn = ns['sens_model' if sensitivities else 'model']
+    fn.n_vars = sm.n_vars
+    fn.ordered_params = list(sm.param_order)
+    fn.state_variables = list(sm.variables)
+    fn.source = src
+    return fn
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA emitter
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class CudaModelSource:
+    source: str
+    n_vars: int
+    n_params: int
+    n_free: int
+    free_idx: list
+    nnz_J: int
+    nnz_G: int
+    flops_f: int          # one evaluation of f
+    flops_fJG: int        # f + J + G non-zeros, CSE'd, evaluated once
+    flops_col: int        # one sensitivity column: J*s + G[:, j]
+    flops_sens_rhs: int   # ALGORITHMIC cost of one augmented RHS evaluation (non-redundant)
+    flops_jac_dense: int
+    autonomous: bool
+    fingerprint: str
+
+
+def _emit_block(lines, rep, outs, printer, pad='    '):
+    for lhs, rhs in rep:
+        lines.append(pad + 'const double %s = %s;' % (lhs, printer.doprint(rhs)))
+    for target, e in outs:
+        lines.append(pad + '%s = %s;' % (target, printer.doprint(e)))
+
+
+def emit_cuda(sm):
+    """Emit the device functions the integrator kernels are compiled against (NVRTC, sm_100a)."""
+    pr = _CudaPrinter()
+    N, NP, NF = sm.n_vars, sm.n_params, sm.n_free
+    jkeys = sorted(sm.J.keys())
+    gkeys = sorted(sm.G.keys())
+
+    # substitute array accesses for the named symbols
+    ysub = {s: sp.Symbol('y[%d]' % i, real=True) for i, s in enumerate(sm.var_syms)}
+    psub = {s: sp.Symbol('p[%d]' % m, real=True) for m, s in enumerate(sm.param_syms)}
+    sub = {}
+    sub.update(ysub)
+    sub.update(psub)
+
+    def X(e):
+        return _share_reciprocals(sp.sympify(e).xreplace(sub))
+
+    f_x = [X(e) for e in sm.f]
+    J_x = [X(sm.J[k]) for k in jkeys]
+    G_x = [X(sm.G[k]) for k in gkeys]
+
+    L = []
+    L.append('// ---- generated by sysbio_modeling_b200.symbolic.emit_cuda: model "%s" ----' % sm.name)
+    L.append('// states : %s' % ', '.join(sm.variables))
+    L.append('// params : %s' % ', '.join(sm.param_order))
+    L.append('// free   : %s' % ', '.join(sm.free))
+    L.append('#define SBM_N %d' % N)
+    L.append('#define SBM_NP %d' % NP)
+    L.append('#define SBM_NF %d' % NF)
+    L.append('#define SBM_NJ %d' % max(len(jkeys), 1))
+    L.append('#define SBM_NG %d' % max(len(gkeys), 1))
+    L.append('#define SBM_AUTONOMOUS %d' % (1 if sm.autonomous else 0))
+    L.append('')
+
+    # --- f only
+    rep, red = sp.cse(f_x, symbols=sp.numbered_symbols('a_'), optimizations='basic')
+    flops_f = count_flops([r for _, r in rep] + list(red))
+    L.append('__device__ __forceinline__ void sbm_f(const double t, const double* __restrict__ y,')
+    L.append('        const double* __restrict__ p, double* __restrict__ f)')
+    L.append('{')
+    _emit_block(L, rep, [('f[%d]' % i, e) for i, e in enumerate(red)], pr)
+    L.append('}')
+    L.append('')
+
+    # --- f + J + G non-zeros
+    allx = f_x + J_x + G_x
+    rep, red = sp.cse(allx, symbols=sp.numbered_symbols('b_'), optimizations='basic')
+    flops_fJG = count_flops([r for _, r in rep] + list(red))
+    outs = [('f[%d]' % i, red[i]) for i in range(N)]
+    outs += [('Jv[%d]' % q, red[N + q]) for q in range(len(jkeys))]
+    outs += [('Gv[%d]' % q, red[N + len(jkeys) + q]) for q in range(len(gkeys))]
+    L.append('// Jv[q] = df_i/dy_k for (i,k) in: %s' % ' '.join('%d:(%d,%d)' % (q, i, k)
+                                                             for q, (i, k) in enumerate(jkeys)))
+    L.append('// Gv[q] = df_i/dp_free[j] for (i,j) in: %s' % ' '.join('%d:(%d,%d)' % (q, i, j)
+                                                                   for q, (i, j) in enumerate(gkeys)))
+    L.append('__device__ __forceinline__ void sbm_fJG(const double t, const double* __restrict__ y,')
+    L.append('        const double* __restrict__ p, double* __restrict__ f,')
+    L.append('        double* __restrict__ Jv, double* __restrict__ Gv)')
+    L.append('{')
+    _emit_block(L, rep, outs, pr)
+    L.append('}')
+    L.append('')
+
+    # --- one column of the augmented RHS
+    # cid == 0 : the state column (out = f);  cid == j+1 : sensitivity w.r.t. free parameter j
+    L.append('__device__ __forceinline__ void sbm_col(const double* __restrict__ f,')
+    L.append('        const double* __restrict__ Jv, const double* __restrict__ Gv,')
+    L.append('        const double* __restrict__ s, const int cid, double* __restrict__ out)')
+    L.append('{')
+    flops_col = 0
+    for i in range(N):
+        terms = ['Jv[%d]*s[%d]' % (q, k) for q, (ii, k) in enumerate(jkeys) if ii == i]
+        gsel = [(q, j) for q, (ii, j) in enumerate(gkeys) if ii == i]
+        L.append('    {')
+        L.append('        double g = 0.0;')
+        for q, j in gsel:
+            L.append('        g = (cid == %d) ? Gv[%d] : g;' % (j + 1, q))
+        acc = 'g'
+        for tm in terms:
+            acc = 'fma(%s, %s, %s)' % (tm.split('*')[0], tm.split('*')[1], acc)
+        flops_col += 2 * len(terms)
+        L.append('        const double d = %s;' % acc)
+        L.append('        out[%d] = (cid == 0) ? f[%d] : d;' % (i, i))
+        L.append('    }')
+    L.append('}')
+    L.append('')
+
+    # --- dense Jacobian (row-major Jd[i*N+k]) and df/dt for the Rosenbrock kernel
+    rep, red = sp.cse(J_x, symbols=sp.numbered_symbols('c_'), optimizations='basic')
+    flops_jd = count_flops([r for _, r in rep] + list(red))
+    L.append('__device__ __forceinline__ void sbm_jac_dense(const double t, const double* __restrict__ y,')
+    L.append('        const double* __restrict__ p, double* __restrict__ Jd)')
+    L.append('{')
+    L.append('    #pragma unroll')
+    L.append('    for (int q = 0; q < SBM_N*SBM_N; ++q) Jd[q] = 0.0;')
+    _emit_block(L, rep, [('Jd[%d]' % (i * N + k), red[q]) for q, (i, k) in enumerate(jkeys)], pr)
+    L.append('}')
+    L.append('')
+    dfdt_x = [X(e) for e in sm.dfdt]
+    rep, red = sp.cse(dfdt_x, symbols=sp.numbered_symbols('d_'), optimizations='basic')
+    L.append('__device__ __forceinline__ void sbm_dfdt(const double t, const double* __restrict__ y,')
+    L.append('        const double* __restrict__ p, double* __restrict__ ft)')
+    L.append('{')
+    _emit_block(L, rep, [('ft[%d]' % i, e) for i, e in enumerate(red)], pr)
+    L.append('}')
+    L.append('')
+
+    src = '\n'.join(L)
+    flops_sens = flops_fJG + NF * flops_col + len(gkeys)
+    return CudaModelSource(source=src, n_vars=N, n_params=NP, n_free=NF, free_idx=list(sm.free_idx),
+                           nnz_J=len(jkeys), nnz_G=len(gkeys), flops_f=flops_f, flops_fJG=flops_fJG,
+                           flops_col=flops_col, flops_sens_rhs=flops_sens, flops_jac_dense=flops_jd,
+                           autonomous=sm.autonomous, fingerprint=sm.fingerprint())
