@@ -1,0 +1,670 @@
+// =================================================================================================
+// sbm_ode_kernels.cuh - batched FP64 ODE(+forward sensitivity) integrators for NVIDIA B200 (sm_100a)
+//
+// This text is compiled at run time by NVRTC, AFTER the model-specific device functions emitted by
+// sysbio_modeling_b200.symbolic.emit_cuda (sbm_f, sbm_fJG, sbm_col, sbm_jac_dense, sbm_dfdt and the
+// SBM_N / SBM_NP / SBM_NF / SBM_NJ / SBM_NG macros) and sbm_kernel_args.h.  It replaces, for every
+// (experiment, parameter set) pair at once, what the reference does one experiment at a time:
+//   OdeModel.simulate / OdeModel.calc_jacobian   (reference model/ode_model.py:83-169, SciPy LSODA)
+//   the mapping functions                         (reference project/utils.py:10-89)
+//   the log-parameter chain rule + column scatter (reference project/base_project.py:343-363, 443-488)
+//
+// Work decomposition ("group" = G lanes of one warp, G in {1,2,4,8,16,32}):
+//   * the augmented system  [y | S_1 ... S_NF]  (S_j = dy/dp_j, N doubles each) is split by COLUMN:
+//     lane l of the group owns columns l, l+G, ... (C slots); column 0 is the state y itself.
+//     Column dynamics are independent given y:  dS_j/dt = J(y) S_j + df/dp_j, so a stage needs one
+//     broadcast of the stage value of y (shuffles from the group leader) and nothing else.
+//   * every stage vector lives in registers (8*C*N doubles per lane); nothing but the final
+//     observable rows ever goes to HBM - full trajectories never exist.
+//   * all lanes of a group share t, h and the accept/reject decision (error norm by xor-shuffle
+//     butterfly), so there is no divergence inside a group; groups in one warp may diverge.
+//   * output: the integrator steps exactly onto each snapped measurement time (no dense output) and
+//     forms the observable (sum over a state bit-mask) and its log-parameter derivative row in
+//     place; lanes write consecutive project columns -> coalesced row segments of the Jacobian.
+// =================================================================================================
+
+#ifndef SBM_BLOCK_SENS
+#define SBM_BLOCK_SENS 128
+#endif
+#ifndef SBM_BLOCK_PLAIN
+#define SBM_BLOCK_PLAIN 128
+#endif
+
+#define SBM_NPP (SBM_NP | 1)      /* odd stride: conflict-free shared-memory parameter rows */
+
+#ifndef SBM_HAS_FREE_IDX
+#error "model source must define sbm_free_idx"
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Dormand-Prince 5(4) coefficients
+// ---------------------------------------------------------------------------------------------
+#define DP_C2 (1.0/5.0)
+#define DP_C3 (3.0/10.0)
+#define DP_C4 (4.0/5.0)
+#define DP_C5 (8.0/9.0)
+#define DP_A21 (1.0/5.0)
+#define DP_A31 (3.0/40.0)
+#define DP_A32 (9.0/40.0)
+#define DP_A41 (44.0/45.0)
+#define DP_A42 (-56.0/15.0)
+#define DP_A43 (32.0/9.0)
+#define DP_A51 (19372.0/6561.0)
+#define DP_A52 (-25360.0/2187.0)
+#define DP_A53 (64448.0/6561.0)
+#define DP_A54 (-212.0/729.0)
+#define DP_A61 (9017.0/3168.0)
+#define DP_A62 (-355.0/33.0)
+#define DP_A63 (46732.0/5247.0)
+#define DP_A64 (49.0/176.0)
+#define DP_A65 (-5103.0/18656.0)
+#define DP_A71 (35.0/384.0)
+#define DP_A73 (500.0/1113.0)
+#define DP_A74 (125.0/192.0)
+#define DP_A75 (-2187.0/6784.0)
+#define DP_A76 (11.0/84.0)
+#define DP_E1 (71.0/57600.0)
+#define DP_E3 (-71.0/16695.0)
+#define DP_E4 (71.0/1920.0)
+#define DP_E5 (-17253.0/339200.0)
+#define DP_E6 (22.0/525.0)
+#define DP_E7 (-1.0/40.0)
+
+// ---------------------------------------------------------------------------------------------
+// group helpers
+// ---------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ double sbm_group_sum(double v, unsigned gmask)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
+}
+
+template <int G>
+__device__ __forceinline__ int sbm_group_or(int v, unsigned gmask)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(gmask, v, o);
+    return v;
+}
+
+// One evaluation of the (column-split) augmented right-hand side.
+//   x[c][:]  this lane's columns;  cid[c] their ids (0 = state column);  out[c][:] = d/dt of them.
+template <int G, int C, int SENS>
+__device__ __forceinline__ void sbm_rhs(const double t, const double (&x)[C][SBM_N],
+                                        const double* __restrict__ p, const int (&cid)[C],
+                                        const unsigned gmask, const int leader,
+                                        double (&out)[C][SBM_N])
+{
+    double Y[SBM_N];
+#pragma unroll
+    for (int i = 0; i < SBM_N; ++i)
+        Y[i] = (G == 1) ? x[0][i] : __shfl_sync(gmask, x[0][i], leader);
+    if (!SENS) {
+        sbm_f(t, Y, p, out[0]);
+    } else {
+        double f[SBM_N], Jv[SBM_NJ], Gv[SBM_NG];
+        sbm_fJG(t, Y, p, f, Jv, Gv);
+#pragma unroll
+        for (int c = 0; c < C; ++c) sbm_col(f, Jv, Gv, x[c], cid[c], out[c]);
+    }
+}
+
+// Weighted RMS norm pieces (Hairer's sk = atol + rtol*max(|y|,|ynew|)); padded columns hold zeros
+// and add nothing.
+template <int C>
+__device__ __forceinline__ double sbm_sq_scaled(const double (&v)[C][SBM_N], const double (&a)[C][SBM_N],
+                                                const double (&b)[C][SBM_N], const double rtol,
+                                                const double atol)
+{
+    double sq = 0.0;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int i = 0; i < SBM_N; ++i) {
+            const double sk = atol + rtol * fmax(fabs(a[c][i]), fabs(b[c][i]));
+            const double q = v[c][i] / sk;
+            sq = fma(q, q, sq);
+        }
+    return sq;
+}
+
+// Observable rows for one output time: value (state column) and d/dtheta row (sensitivity columns).
+template <int G, int C, int SENS>
+__device__ __forceinline__ void sbm_emit_rows(const SbmSolveArgs& a, const long long b, const int kt,
+                                              const double (&x)[C][SBM_N], const int (&cid)[C],
+                                              const int (&pcol)[C], const double (&pscale)[C],
+                                              const bool poison)
+{
+    const int r0 = a.orow_off[kt], r1 = a.orow_off[kt + 1];
+    for (int r = r0; r < r1; ++r) {
+        const unsigned long long mask = a.row_mask[r];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < SBM_N; ++i) acc += ((mask >> i) & 1ull) ? x[c][i] : 0.0;
+            if (poison) acc = __longlong_as_double(0x7ff8000000000000ll);
+            if (cid[c] == 0) {
+                a.sims[b * a.n_rows + a.row_sim[r]] = acc;
+            } else if (SENS && a.jac != nullptr && pcol[c] >= 0) {
+                // chain rule to log-parameters: d/dtheta_c = d/dp * exp(theta_c) = d/dp * p
+                double* dst = a.jac + ((b * a.n_rows + a.row_jac[r]) * (long long)a.n_proj + pcol[c]);
+                const double v = acc * pscale[c];
+                if (a.jac_atomic) atomicAdd(dst, v); else *dst = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adaptive Dormand-Prince 5(4), FSAL, PI step controller (Hairer's DOPRI5 constants)
+// ---------------------------------------------------------------------------------------------
+template <int G, int C, int SENS, int BLOCK>
+__device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
+{
+    constexpr int N = SBM_N;
+    constexpr int NCOL = SENS ? (SBM_NF + 1) : 1;
+    static_assert(G * C >= NCOL, "group too small for the augmented system");
+    constexpr int GPB = BLOCK / G;                 // groups (trajectories) per block
+    __shared__ double sp[GPB * SBM_NPP];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int lig = (G == 1) ? 0 : (lane & (G - 1));
+    const int leader = lane - lig;
+    const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << leader);
+    const long long traj = ((long long)blockIdx.x * BLOCK + tid) / G;
+    if (traj >= a.B * (long long)a.E) return;      // whole groups leave together
+    const int e = (int)(traj % a.E);
+    const long long b = traj / a.E;
+
+    // ---- model parameters: p_m = exp(theta[col]) or the experiment's fixed value (base_project.py:343-363)
+    double* p = sp + (tid / G) * SBM_NPP;
+    for (int m = lig; m < SBM_NP; m += G) {
+        const int c = a.pmap[e * SBM_NP + m];
+        p[m] = (c >= 0) ? exp(a.theta[b * a.theta_sb + c * a.theta_sp]) : a.pfix[e * SBM_NP + m];
+    }
+    __syncwarp(gmask);
+
+    int cid[C], pcol[C];
+    double pscale[C];
+    double x[C][N];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        cid[c] = lig + G * c;
+        pcol[c] = -1;
+        pscale[c] = 0.0;
+        if (SENS && cid[c] >= 1 && cid[c] <= SBM_NF) {
+            const int m = sbm_free_idx[cid[c] - 1];
+            if (a.jac_raw) { pcol[c] = cid[c] - 1; pscale[c] = 1.0; }
+            else { pcol[c] = a.pmap[e * SBM_NP + m]; pscale[c] = p[m]; }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[c][i] = (cid[c] == 0) ? a.y0[e * N + i] : 0.0;
+    }
+
+    const double rtol = a.rtol, atol = a.atol;
+    const double inv_naug = 1.0 / (double)(N * NCOL);
+    const int kt0 = a.tout_off[e], kt1 = a.tout_off[e + 1];
+    const double tend = (kt1 > kt0) ? a.tout[kt1 - 1] : 0.0;
+
+    double k1[C][N], k2[C][N], k3[C][N], k4[C][N], k5[C][N], k6[C][N], w[C][N];
+    unsigned nstep = 0, nrej = 0, nrhs = 0;
+    int status = SBM_OK;
+    double t = 0.0;
+
+    sbm_rhs<G, C, SENS>(t, x, p, cid, gmask, leader, k1);
+    nrhs++;
+
+    // ---- initial step size (Hairer, Norsett, Wanner II.4) ----
+    double h;
+    {
+        const double d0 = sqrt(sbm_group_sum<G>(sbm_sq_scaled<C>(x, x, x, rtol, atol), gmask) * inv_naug);
+        const double d1 = sqrt(sbm_group_sum<G>(sbm_sq_scaled<C>(k1, x, x, rtol, atol), gmask) * inv_naug);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, tend);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int i = 0; i < N; ++i) w[c][i] = fma(h0, k1[c][i], x[c][i]);
+        sbm_rhs<G, C, SENS>(t + h0, w, p, cid, gmask, leader, k2);
+        nrhs++;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int i = 0; i < N; ++i) k2[c][i] -= k1[c][i];
+        const double d2 = sqrt(sbm_group_sum<G>(sbm_sq_scaled<C>(k2, x, x, rtol, atol), gmask) * inv_naug) / h0;
+        const double dm = fmax(d1, d2);
+        const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
+        h = fmin(fmin(100.0 * h0, h1), tend);
+        if (a.h0 > 0.0) h = fmin(a.h0, tend);
+    }
+
+    float facold = 1e-4f;
+    bool poison = false, last_rejected = false;
+
+    for (int kt = kt0; kt < kt1; ++kt) {
+        const double tk = a.tout[kt];
+        while (status == SBM_OK && t < tk) {
+            // clip onto the output time; remember the unclipped proposal
+            const double hprop = h;
+            bool clipped = false;
+            if (t + 1.01 * h >= tk) { h = tk - t; clipped = true; }
+            if (nstep >= (unsigned)a.max_steps) { status = SBM_ERR_MAXSTEPS; break; }
+            if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) { status = SBM_ERR_UNDERFLOW; break; }
+            nstep++;
+
+            // stage 2
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int i = 0; i < N; ++i) w[c][i] = fma(h * DP_A21, k1[c][i], x[c][i]);
+            sbm_rhs<G, C, SENS>(t + DP_C2 * h, w, p, cid, gmask, leader, k2);
+            // stage 3
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    w[c][i] = fma(h * DP_A32, k2[c][i], fma(h * DP_A31, k1[c][i], x[c][i]));
+            sbm_rhs<G, C, SENS>(t + DP_C3 * h, w, p, cid, gmask, leader, k3);
+            // stage 4
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    w[c][i] = fma(h * DP_A43, k3[c][i], fma(h * DP_A42, k2[c][i], fma(h * DP_A41, k1[c][i], x[c][i])));
+            sbm_rhs<G, C, SENS>(t + DP_C4 * h, w, p, cid, gmask, leader, k4);
+            // stage 5
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    w[c][i] = fma(h * DP_A54, k4[c][i], fma(h * DP_A53, k3[c][i],
+                              fma(h * DP_A52, k2[c][i], fma(h * DP_A51, k1[c][i], x[c][i]))));
+            sbm_rhs<G, C, SENS>(t + DP_C5 * h, w, p, cid, gmask, leader, k5);
+            // stage 6
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    w[c][i] = fma(h * DP_A65, k5[c][i], fma(h * DP_A64, k4[c][i], fma(h * DP_A63, k3[c][i],
+                              fma(h * DP_A62, k2[c][i], fma(h * DP_A61, k1[c][i], x[c][i])))));
+            sbm_rhs<G, C, SENS>(t + h, w, p, cid, gmask, leader, k6);
+            // 5th-order solution (k2 is dead from here on: it receives k7)
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    w[c][i] = fma(h * DP_A76, k6[c][i], fma(h * DP_A75, k5[c][i], fma(h * DP_A74, k4[c][i],
+                              fma(h * DP_A73, k3[c][i], fma(h * DP_A71, k1[c][i], x[c][i])))));
+            sbm_rhs<G, C, SENS>(t + h, w, p, cid, gmask, leader, k2);
+            nrhs += 6;
+
+            // embedded error estimate, scaled RMS over the whole augmented state
+            double sq = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double er = h * fma(DP_E7, k2[c][i], fma(DP_E6, k6[c][i], fma(DP_E5, k5[c][i],
+                                      fma(DP_E4, k4[c][i], fma(DP_E3, k3[c][i], DP_E1 * k1[c][i])))));
+                    const double sk = atol + rtol * fmax(fabs(x[c][i]), fabs(w[c][i]));
+                    const double q = er / sk;
+                    sq = fma(q, q, sq);
+                }
+            const double err = sqrt(sbm_group_sum<G>(sq, gmask) * inv_naug);
+
+            if (err <= 1.0) {
+                // accept; PI controller (DOPRI5: beta = 0.04, safe = 0.9, fac in [0.2, 10])
+                const float ferr = fmaxf((float)err, 1e-30f);
+                float fac = __powf(ferr, 0.2f - 0.04f * 0.75f) / __powf(facold, 0.04f);
+                fac = fmaxf(0.1f, fminf(5.0f, fac / 0.9f));
+                facold = fmaxf(ferr, 1e-4f);
+                t = clipped ? tk : t + h;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) { x[c][i] = w[c][i]; k1[c][i] = k2[c][i]; }
+                double hnew = h / (double)fac;
+                if (last_rejected) hnew = fmin(hnew, h);
+                if (clipped) hnew = fmax(hnew, hprop);   // a clipped step must not shrink the cruise step
+                h = hnew;
+                last_rejected = false;
+            } else {
+                nrej++;
+                last_rejected = true;
+                if (err == err && err < 1e300) {
+                    const float ferr = (float)fmin(err, 1e30);
+                    h = h / (double)fminf(5.0f, __powf(ferr, 0.2f - 0.04f * 0.75f) / 0.9f);
+                } else {
+                    h *= 0.1;                            // NaN/Inf in the trial state: retreat hard
+                    if (h < 1e-300) { status = SBM_ERR_NONFINITE; break; }
+                }
+            }
+        }
+        if (status != SBM_OK) poison = true;
+        sbm_emit_rows<G, C, SENS>(a, b, kt, x, cid, pcol, pscale, poison);
+    }
+
+    if (lig == 0) {
+        a.status[traj] = status;
+        atomicAdd(a.counters + SBM_CNT_STEPS, (unsigned long long)nstep);
+        atomicAdd(a.counters + SBM_CNT_REJECT, (unsigned long long)nrej);
+        atomicAdd(a.counters + SBM_CNT_RHS, (unsigned long long)nrhs);
+        atomicAdd(a.counters + SBM_CNT_TRAJ, 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rosenbrock RODAS4 (Hairer & Wanner, stiff; L-stable, order 4(3)), one thread per trajectory,
+// dense LU with partial pivoting held in registers.  States only (no sensitivity columns).
+// ---------------------------------------------------------------------------------------------
+#define RO_GAMMA 0.25
+#define RO_C2 0.386
+#define RO_C3 0.21
+#define RO_C4 0.63
+#define RO_D1 0.25
+#define RO_D2 (-0.1043)
+#define RO_D3 0.1035
+#define RO_D4 (-0.03620000000000023)
+#define RO_A21 1.544
+#define RO_A31 0.9466785280815826
+#define RO_A32 0.2557011698983284
+#define RO_A41 3.314825187068521
+#define RO_A42 2.896124015972201
+#define RO_A43 0.9986419139977817
+#define RO_A51 1.221224509226641
+#define RO_A52 6.019134481288629
+#define RO_A53 12.53708332932087
+#define RO_A54 (-0.6878860361058950)
+#define RO_C21 (-5.6688)
+#define RO_C31 (-2.430093356833875)
+#define RO_C32 (-0.2063599157091915)
+#define RO_C41 (-0.1073529058151375)
+#define RO_C42 (-9.594562251023355)
+#define RO_C43 (-20.47028614809616)
+#define RO_C51 7.496443313967647
+#define RO_C52 (-10.24680431464352)
+#define RO_C53 (-33.99990352819905)
+#define RO_C54 11.70890893206160
+#define RO_C61 8.083246795921522
+#define RO_C62 (-7.981132988064893)
+#define RO_C63 (-31.52159432874371)
+#define RO_C64 16.31930543123136
+#define RO_C65 (-6.058818238834054)
+
+// in-register LU, partial pivoting by predicated row swaps (all indices compile-time after unrolling)
+__device__ __forceinline__ bool sbm_lu_factor(double (&A)[SBM_N * SBM_N], int (&piv)[SBM_N])
+{
+    constexpr int N = SBM_N;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        int r = k;
+        double best = fabs(A[k * N + k]);
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const double v = fabs(A[i * N + k]);
+            if (v > best) { best = v; r = i; }
+        }
+        piv[k] = r;
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            if (r == i) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) { const double tmp = A[k * N + j]; A[k * N + j] = A[i * N + j]; A[i * N + j] = tmp; }
+            }
+        }
+        if (!(best > 0.0)) ok = false;
+        const double inv = 1.0 / A[k * N + k];
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const double l = A[i * N + k] * inv;
+            A[i * N + k] = l;
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) A[i * N + j] = fma(-l, A[k * N + j], A[i * N + j]);
+        }
+        A[k * N + k] = inv;          // store the reciprocal pivot
+    }
+    return ok;
+}
+
+__device__ __forceinline__ void sbm_lu_solve(const double (&A)[SBM_N * SBM_N], const int (&piv)[SBM_N],
+                                             double (&b)[SBM_N])
+{
+    constexpr int N = SBM_N;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int i = k + 1; i < N; ++i)
+            if (piv[k] == i) { const double tmp = b[k]; b[k] = b[i]; b[i] = tmp; }
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) b[i] = fma(-A[i * N + k], b[k], b[i]);
+    }
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+        double s = b[k];
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) s = fma(-A[k * N + j], b[j], s);
+        b[k] = s * A[k * N + k];
+    }
+}
+
+template <int BLOCK>
+__device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
+{
+    constexpr int N = SBM_N;
+    __shared__ double sp[BLOCK * SBM_NPP];
+    const int tid = threadIdx.x;
+    const long long traj = (long long)blockIdx.x * BLOCK + tid;
+    if (traj >= a.B * (long long)a.E) return;
+    const int e = (int)(traj % a.E);
+    const long long b = traj / a.E;
+
+    double* p = sp + tid * SBM_NPP;
+    for (int m = 0; m < SBM_NP; ++m) {
+        const int c = a.pmap[e * SBM_NP + m];
+        p[m] = (c >= 0) ? exp(a.theta[b * a.theta_sb + c * a.theta_sp]) : a.pfix[e * SBM_NP + m];
+    }
+
+    const int cid[1] = {0};
+    const int pcol[1] = {-1};
+    const double pscale[1] = {0.0};
+    double y[1][N], yn[1][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[0][i] = a.y0[e * N + i];
+
+    const double rtol = a.rtol, atol = a.atol;
+    const int kt0 = a.tout_off[e], kt1 = a.tout_off[e + 1];
+    const double tend = (kt1 > kt0) ? a.tout[kt1 - 1] : 0.0;
+    unsigned nstep = 0, nrej = 0, nrhs = 0, nlu = 0;
+    int status = SBM_OK;
+    double t = 0.0;
+
+    double f0[N], fs[N], ft[N];
+    double k1[N], k2[N], k3[N], k4[N], k5[N], k6[N];
+    double A[N * N];
+    int piv[N];
+
+    // initial step from the local rate of change (order-4 variant of Hairer's rule)
+    double h;
+    {
+        sbm_f(t, y[0], p, f0);
+        nrhs++;
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sk = atol + rtol * fabs(y[0][i]);
+            d0 = fma(y[0][i] / sk, y[0][i] / sk, d0);
+            d1 = fma(f0[i] / sk, f0[i] / sk, d1);
+        }
+        d0 = sqrt(d0 / N); d1 = sqrt(d1 / N);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, tend);
+#pragma unroll
+        for (int i = 0; i < N; ++i) yn[0][i] = fma(h0, f0[i], y[0][i]);
+        sbm_f(t + h0, yn[0], p, fs);
+        nrhs++;
+        double d2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sk = atol + rtol * fabs(y[0][i]);
+            const double q = (fs[i] - f0[i]) / sk;
+            d2 = fma(q, q, d2);
+        }
+        d2 = sqrt(d2 / N) / h0;
+        const double dm = fmax(d1, d2);
+        const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.25);
+        h = fmin(fmin(100.0 * h0, h1), tend);
+        if (a.h0 > 0.0) h = fmin(a.h0, tend);
+    }
+
+    bool last_rejected = false, first = true, poison = false;
+    double hacc = h, erracc = 1e-2;
+    unsigned naccept = 0;
+
+    for (int kt = kt0; kt < kt1; ++kt) {
+        const double tk = a.tout[kt];
+        while (status == SBM_OK && t < tk) {
+            const double hprop = h;
+            bool clipped = false;
+            if (t + 1.01 * h >= tk) { h = tk - t; clipped = true; }
+            if (nstep >= (unsigned)a.max_steps) { status = SBM_ERR_MAXSTEPS; break; }
+            if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) { status = SBM_ERR_UNDERFLOW; break; }
+            nstep++;
+
+            // E = I/(h*gamma) - J, factored once per step
+            sbm_f(t, y[0], p, f0);
+            sbm_jac_dense(t, y[0], p, A);
+#if !SBM_AUTONOMOUS
+            sbm_dfdt(t, y[0], p, ft);
+#else
+#pragma unroll
+            for (int i = 0; i < N; ++i) ft[i] = 0.0;
+#endif
+            const double fac = 1.0 / (h * RO_GAMMA);
+#pragma unroll
+            for (int q = 0; q < N * N; ++q) A[q] = -A[q];
+#pragma unroll
+            for (int i = 0; i < N; ++i) A[i * N + i] += fac;
+            const bool lu_ok = sbm_lu_factor(A, piv);
+            nlu++;
+            const double hi = 1.0 / h;
+
+            // stage 1
+#pragma unroll
+            for (int i = 0; i < N; ++i) k1[i] = fma(h * RO_D1, ft[i], f0[i]);
+            sbm_lu_solve(A, piv, k1);
+            // stage 2
+#pragma unroll
+            for (int i = 0; i < N; ++i) yn[0][i] = fma(RO_A21, k1[i], y[0][i]);
+            sbm_f(t + RO_C2 * h, yn[0], p, fs);
+#pragma unroll
+            for (int i = 0; i < N; ++i) k2[i] = fma(h * RO_D2, ft[i], fma(hi * RO_C21, k1[i], fs[i]));
+            sbm_lu_solve(A, piv, k2);
+            // stage 3
+#pragma unroll
+            for (int i = 0; i < N; ++i) yn[0][i] = fma(RO_A32, k2[i], fma(RO_A31, k1[i], y[0][i]));
+            sbm_f(t + RO_C3 * h, yn[0], p, fs);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                k3[i] = fma(h * RO_D3, ft[i], fma(hi * RO_C32, k2[i], fma(hi * RO_C31, k1[i], fs[i])));
+            sbm_lu_solve(A, piv, k3);
+            // stage 4
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                yn[0][i] = fma(RO_A43, k3[i], fma(RO_A42, k2[i], fma(RO_A41, k1[i], y[0][i])));
+            sbm_f(t + RO_C4 * h, yn[0], p, fs);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                k4[i] = fma(h * RO_D4, ft[i], fma(hi * RO_C43, k3[i], fma(hi * RO_C42, k2[i],
+                        fma(hi * RO_C41, k1[i], fs[i]))));
+            sbm_lu_solve(A, piv, k4);
+            // stage 5
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                yn[0][i] = fma(RO_A54, k4[i], fma(RO_A53, k3[i], fma(RO_A52, k2[i], fma(RO_A51, k1[i], y[0][i]))));
+            sbm_f(t + h, yn[0], p, fs);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                k5[i] = fma(hi * RO_C54, k4[i], fma(hi * RO_C53, k3[i], fma(hi * RO_C52, k2[i],
+                        fma(hi * RO_C51, k1[i], fs[i]))));
+            sbm_lu_solve(A, piv, k5);
+            // stage 6 (embedded 3rd-order solution is yn + k5)
+#pragma unroll
+            for (int i = 0; i < N; ++i) yn[0][i] += k5[i];
+            sbm_f(t + h, yn[0], p, fs);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                k6[i] = fma(hi * RO_C65, k5[i], fma(hi * RO_C64, k4[i], fma(hi * RO_C63, k3[i],
+                        fma(hi * RO_C62, k2[i], fma(hi * RO_C61, k1[i], fs[i])))));
+            sbm_lu_solve(A, piv, k6);
+#pragma unroll
+            for (int i = 0; i < N; ++i) yn[0][i] += k6[i];
+            nrhs += 7;
+
+            double sq = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double sk = atol + rtol * fmax(fabs(y[0][i]), fabs(yn[0][i]));
+                const double q = k6[i] / sk;
+                sq = fma(q, q, sq);
+            }
+            const double err = sqrt(sq / N);
+
+            if (lu_ok && err <= 1.0) {
+                // accept; Gustafsson predictive controller as in Hairer's RODAS
+                double facr = fmax(1.0 / 6.0, fmin(5.0, pow(fmax(err, 1e-300), 0.25) / 0.9));
+                if (naccept >= 1) {
+                    double facgus = (hacc / h) * pow(err * err / erracc, 0.25) / 0.9;
+                    facgus = fmax(1.0 / 6.0, fmin(5.0, facgus));
+                    facr = fmax(facr, facgus);
+                }
+                hacc = h;
+                erracc = fmax(1e-2, err);
+                naccept++;
+                t = clipped ? tk : t + h;
+#pragma unroll
+                for (int i = 0; i < N; ++i) y[0][i] = yn[0][i];
+                double hnew = h / facr;
+                if (last_rejected) hnew = fmin(hnew, h);
+                if (clipped) hnew = fmax(hnew, hprop);
+                h = hnew;
+                last_rejected = false;
+                first = false;
+            } else {
+                nrej++;
+                if (lu_ok && err == err && err < 1e300) {
+                    const double facr = fmax(1.0 / 6.0, fmin(5.0, pow(err, 0.25) / 0.9));
+                    h = first ? 0.1 * h : h / facr;
+                } else {
+                    h *= 0.5;
+                    if (h < 1e-300) { status = SBM_ERR_NONFINITE; break; }
+                }
+                last_rejected = true;
+            }
+        }
+        if (status != SBM_OK) poison = true;
+        sbm_emit_rows<1, 1, 0>(a, b, kt, y, cid, pcol, pscale, poison);
+    }
+
+    a.status[traj] = status;
+    atomicAdd(a.counters + SBM_CNT_STEPS, (unsigned long long)nstep);
+    atomicAdd(a.counters + SBM_CNT_REJECT, (unsigned long long)nrej);
+    atomicAdd(a.counters + SBM_CNT_RHS, (unsigned long long)nrhs);
+    atomicAdd(a.counters + SBM_CNT_LU, (unsigned long long)nlu);
+    atomicAdd(a.counters + SBM_CNT_TRAJ, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel entry points are instantiated by the host (sbm_api.cu appends SBM_DEFINE_* lines)
+// ---------------------------------------------------------------------------------------------
+#define SBM_DEFINE_DP5(NAME, G, C, SENS, BLOCK)                                             \
+    extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \
+    { sbm_dp5_impl<G, C, SENS, BLOCK>(a); }
+
+#define SBM_DEFINE_RODAS4(NAME, BLOCK)                                                      \
+    extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \
+    { sbm_rodas4_impl<BLOCK>(a); }

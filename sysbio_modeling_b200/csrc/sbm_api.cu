@@ -1,0 +1,532 @@
+// sbm_api.cu - host side of libsbm_b200.so (C ABI declared in include/sbm_b200.h).
+//
+//  * compiles the emitted model device functions + the embedded integrator templates with NVRTC for
+//    sm_100a, caches the cubin on disk, loads it through the driver API (libcuda is dlopen'ed so the
+//    library itself loads on a machine without a GPU - compute calls then fail loudly);
+//  * owns the device copy of the flat project plan;
+//  * launches the integrators and the statically compiled loss-epilogue kernels (sbm_epilogue.cuh).
+//
+// No CPU fallback exists anywhere in this file.
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <nvrtc.h>
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <fstream>
+#include <sstream>
+#include <mutex>
+
+#include "../../include/sbm_b200.h"
+#include "sbm_kernel_args.h"
+#include "sbm_epilogue.cuh"
+
+// generated at build time from sbm_kernel_args.h + kernels/sbm_ode_kernels.cuh
+extern const char* sbm_embedded_args_header;
+extern const char* sbm_embedded_kernels;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+extern "C" const char* sbm_last_error(void) { return g_err.c_str(); }
+extern "C" int sbm_version(void) { return 100; }
+
+#define RT(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(SBM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// driver API through dlopen
+// ------------------------------------------------------------------------------------------------
+struct Driver {
+    void* lib = nullptr;
+    CUresult (*cuInit_)(unsigned) = nullptr;
+    CUresult (*cuModuleLoadData_)(CUmodule*, const void*) = nullptr;
+    CUresult (*cuModuleUnload_)(CUmodule) = nullptr;
+    CUresult (*cuModuleGetFunction_)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*cuFuncGetAttribute_)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*cuLaunchKernel_)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                                unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*cuGetErrorString_)(CUresult, const char**) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+static Driver& driver()
+{
+    static Driver d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        d.lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!d.lib) { d.why = "libcuda.so.1 not found (no NVIDIA driver on this machine)"; return; }
+#define LOAD(field, sym)                                                                           \
+        *(void**)(&d.field) = dlsym(d.lib, sym);                                                   \
+        if (!d.field) { d.why = std::string("missing driver symbol ") + sym; return; }
+        LOAD(cuInit_, "cuInit")
+        LOAD(cuModuleLoadData_, "cuModuleLoadData")
+        LOAD(cuModuleUnload_, "cuModuleUnload")
+        LOAD(cuModuleGetFunction_, "cuModuleGetFunction")
+        LOAD(cuFuncGetAttribute_, "cuFuncGetAttribute")
+        LOAD(cuLaunchKernel_, "cuLaunchKernel")
+        LOAD(cuGetErrorString_, "cuGetErrorString")
+#undef LOAD
+        d.ok = true;
+    });
+    return d;
+}
+
+static std::string cu_err(CUresult r)
+{
+    const char* s = nullptr;
+    if (driver().cuGetErrorString_) driver().cuGetErrorString_(r, &s);
+    return s ? s : "unknown CUDA driver error";
+}
+
+#define DRV(call)                                                                                  \
+    do {                                                                                           \
+        CUresult r__ = (call);                                                                     \
+        if (r__ != CUDA_SUCCESS) return fail(SBM_E_CUDA, std::string(#call) + ": " + cu_err(r__)); \
+    } while (0)
+
+extern "C" int sbm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int require_device()
+{
+    if (!driver().ok) return fail(SBM_E_CUDA, "CUDA driver unavailable: " + driver().why);
+    if (sbm_device_count() <= 0) return fail(SBM_E_CUDA, "no CUDA device visible (this engine has no CPU fallback)");
+    RT(cudaFree(0));   // make sure the primary context exists and is current
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------
+struct KernelSlot {
+    CUfunction fn = nullptr;
+    int regs = -1, local = -1, smem = -1;
+};
+
+struct sbm_model {
+    sbm_model_desc_t desc{};
+    std::string arch;
+    int G = 1, C = 1, block = 128;
+    std::string source;          // full NVRTC translation unit (kept for diagnostics)
+    std::string log;
+    std::vector<char> cubin;
+    bool from_cache = false;
+    bool loaded = false;
+    CUmodule mod = nullptr;
+    KernelSlot dp5_plain, dp5_sens, rodas4;
+    std::mutex mu;
+};
+
+static unsigned long long fnv1a(const std::string& s, unsigned long long seed)
+{
+    unsigned long long h = 1469598103934665603ull ^ seed;
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
+
+static void pick_group(int N, int ncol, int& G, int& C)
+{
+    // smallest group whose per-lane state (8 stage vectors of C*N doubles) stays in registers
+    const int budget = 12;   // C*N doubles per stage vector  ->  <= 96 doubles of stage storage
+    for (int g = 1; g <= 32; g *= 2) {
+        int c = (ncol + g - 1) / g;
+        if (c * N <= budget) { G = g; C = c; return; }
+    }
+    G = 32;
+    C = (ncol + 31) / 32;
+}
+
+extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* desc, sbm_model** out)
+{
+    if (!model_src || !desc || !out) return fail(SBM_E_INVALID, "sbm_model_compile: null argument");
+    if (desc->n_vars < 1 || desc->n_vars > 64) return fail(SBM_E_INVALID, "n_vars must be in [1, 64]");
+    if (desc->n_params < 0 || desc->n_free < 0 || desc->n_free > desc->n_params)
+        return fail(SBM_E_INVALID, "bad parameter counts");
+    sbm_model* m = new sbm_model();
+    m->desc = *desc;
+    m->arch = desc->arch ? desc->arch : "sm_100a";
+    m->block = desc->block_threads > 0 ? desc->block_threads : 128;
+    if (desc->group_lanes > 0 && desc->cols_per_lane > 0) {
+        m->G = desc->group_lanes;
+        m->C = desc->cols_per_lane;
+    } else {
+        pick_group(desc->n_vars, desc->n_free + 1, m->G, m->C);
+    }
+    if (m->G < 1 || m->G > 32 || (m->G & (m->G - 1)) || m->G * m->C < desc->n_free + 1 || (m->block % 32)) {
+        delete m;
+        return fail(SBM_E_INVALID, "invalid group_lanes / cols_per_lane / block_threads");
+    }
+
+    std::ostringstream src;
+    src << sbm_embedded_args_header << "\n" << model_src << "\n" << sbm_embedded_kernels << "\n";
+    src << "SBM_DEFINE_DP5(sbm_dp5_plain, 1, 1, 0, " << m->block << ")\n";
+    src << "SBM_DEFINE_DP5(sbm_dp5_sens, " << m->G << ", " << m->C << ", 1, " << m->block << ")\n";
+    src << "SBM_DEFINE_RODAS4(sbm_rodas4_plain, " << m->block << ")\n";
+    m->source = src.str();
+
+    const std::string archopt = "--gpu-architecture=" + m->arch;
+    std::vector<const char*> opts = {archopt.c_str(), "--std=c++17", "-lineinfo", "--fmad=true",
+                                     "--ptxas-options=-v", "-DSBM_NVRTC=1"};
+    std::string key_material = m->source;
+    for (auto o : opts) { key_material += o; key_material += "\n"; }
+    char key[64];
+    snprintf(key, sizeof key, "%016llx%016llx", fnv1a(key_material, 0), fnv1a(key_material, 0x9e3779b97f4a7c15ull));
+
+    std::string cache_path;
+    if (desc->cache_dir && desc->cache_dir[0]) {
+        mkdir(desc->cache_dir, 0755);
+        cache_path = std::string(desc->cache_dir) + "/sbm_" + key + ".cubin";
+        std::ifstream f(cache_path, std::ios::binary);
+        if (f) {
+            m->cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+            if (!m->cubin.empty()) {
+                m->from_cache = true;
+                std::ifstream lf(cache_path + ".log");
+                if (lf) m->log.assign(std::istreambuf_iterator<char>(lf), std::istreambuf_iterator<char>());
+            }
+        }
+    }
+
+    if (m->cubin.empty()) {
+        nvrtcProgram prog;
+        nvrtcResult r = nvrtcCreateProgram(&prog, m->source.c_str(), "sbm_model.cu", 0, nullptr, nullptr);
+        if (r != NVRTC_SUCCESS) { delete m; return fail(SBM_E_NVRTC, std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r)); }
+        r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+        size_t logsz = 0;
+        nvrtcGetProgramLogSize(prog, &logsz);
+        if (logsz > 1) { m->log.resize(logsz); nvrtcGetProgramLog(prog, &m->log[0]); }
+        if (r != NVRTC_SUCCESS) {
+            std::string msg = std::string("NVRTC compile failed: ") + nvrtcGetErrorString(r) + "\n" + m->log;
+            nvrtcDestroyProgram(&prog);
+            delete m;
+            return fail(SBM_E_NVRTC, msg);
+        }
+        size_t sz = 0;
+        r = nvrtcGetCUBINSize(prog, &sz);
+        if (r != NVRTC_SUCCESS || sz == 0) { nvrtcDestroyProgram(&prog); delete m; return fail(SBM_E_NVRTC, "no cubin produced"); }
+        m->cubin.resize(sz);
+        nvrtcGetCUBIN(prog, m->cubin.data());
+        nvrtcDestroyProgram(&prog);
+        if (!cache_path.empty()) {
+            std::string tmp = cache_path + ".tmp" + std::to_string((long)getpid());
+            { std::ofstream f(tmp, std::ios::binary); f.write(m->cubin.data(), (std::streamsize)m->cubin.size()); }
+            rename(tmp.c_str(), cache_path.c_str());
+            std::ofstream lf(cache_path + ".log");
+            lf << m->log;
+        }
+    }
+    *out = m;
+    return 0;
+}
+
+static int slot_load(sbm_model* m, KernelSlot& s, const char* name)
+{
+    Driver& d = driver();
+    DRV(d.cuModuleGetFunction_(&s.fn, m->mod, name));
+    d.cuFuncGetAttribute_(&s.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, s.fn);
+    d.cuFuncGetAttribute_(&s.local, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, s.fn);
+    d.cuFuncGetAttribute_(&s.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, s.fn);
+    return 0;
+}
+
+static int ensure_loaded(sbm_model* m)
+{
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (m->loaded) return 0;
+    int rc = require_device();
+    if (rc) return rc;
+    DRV(driver().cuModuleLoadData_(&m->mod, m->cubin.data()));
+    if ((rc = slot_load(m, m->dp5_plain, "sbm_dp5_plain"))) return rc;
+    if ((rc = slot_load(m, m->dp5_sens, "sbm_dp5_sens"))) return rc;
+    if ((rc = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return rc;
+    m->loaded = true;
+    return 0;
+}
+
+extern "C" int sbm_model_info(sbm_model* m, sbm_model_info_t* o)
+{
+    if (!m || !o) return fail(SBM_E_INVALID, "sbm_model_info: null argument");
+    if (driver().ok && sbm_device_count() > 0) {
+        int rc = ensure_loaded(m);
+        if (rc) return rc;
+    }
+    o->n_vars = m->desc.n_vars; o->n_params = m->desc.n_params; o->n_free = m->desc.n_free;
+    o->group_lanes = m->G; o->cols_per_lane = m->C; o->block_threads = m->block;
+    o->regs_dp5_plain = m->dp5_plain.regs; o->regs_dp5_sens = m->dp5_sens.regs; o->regs_rodas4 = m->rodas4.regs;
+    o->local_dp5_plain = m->dp5_plain.local; o->local_dp5_sens = m->dp5_sens.local; o->local_rodas4 = m->rodas4.local;
+    o->smem_dp5_plain = m->dp5_plain.smem; o->smem_dp5_sens = m->dp5_sens.smem; o->smem_rodas4 = m->rodas4.smem;
+    o->cubin_bytes = (int)m->cubin.size();
+    o->from_cache = m->from_cache ? 1 : 0;
+    return 0;
+}
+
+extern "C" const char* sbm_model_log(const sbm_model* m) { return m ? m->log.c_str() : ""; }
+
+extern "C" void sbm_model_destroy(sbm_model* m)
+{
+    if (!m) return;
+    if (m->loaded && m->mod) driver().cuModuleUnload_(m->mod);
+    delete m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n)
+    {
+        if (n <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        if (cudaMalloc(&p, n) != cudaSuccess) { cudaGetLastError(); return SBM_E_NOMEM; }
+        bytes = n;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct sbm_plan {
+    sbm_model* model = nullptr;
+    sbm_plan_desc_t d{};
+    // device copies
+    int *pmap = nullptr, *tout_off = nullptr, *orow_off = nullptr, *row_sim = nullptr, *row_jac = nullptr;
+    int *row_group = nullptr, *row_kind = nullptr, *row_aux = nullptr, *grp_off = nullptr, *grp_rows = nullptr;
+    double *pfix = nullptr, *y0 = nullptr, *tout = nullptr, *data = nullptr, *sigma = nullptr;
+    unsigned long long* row_mask = nullptr;
+    std::vector<void*> owned;
+    // grow-only workspaces of the *_host entry points
+    DevBuf w_theta, w_sims, w_jac, w_resid, w_ssr, w_sf, w_sfgrad, w_grad, w_status, w_counters;
+};
+
+template <typename T>
+static int upload(sbm_plan* p, T*& dst, const T* src, size_t n)
+{
+    dst = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(T);
+    void* q = nullptr;
+    if (cudaMalloc(&q, bytes) != cudaSuccess) { cudaGetLastError(); return fail(SBM_E_NOMEM, "cudaMalloc failed for plan table"); }
+    p->owned.push_back(q);
+    if (n && src) RT(cudaMemcpy(q, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    dst = (T*)q;
+    return 0;
+}
+
+extern "C" void sbm_plan_destroy(sbm_plan* p)
+{
+    if (!p) return;
+    for (void* q : p->owned) cudaFree(q);
+    p->w_theta.release(); p->w_sims.release(); p->w_jac.release(); p->w_resid.release(); p->w_ssr.release();
+    p->w_sf.release(); p->w_sfgrad.release(); p->w_grad.release(); p->w_status.release(); p->w_counters.release();
+    delete p;
+}
+
+extern "C" int sbm_plan_create(sbm_model* m, const sbm_plan_desc_t* d, sbm_plan** out)
+{
+    if (!d || !out) return fail(SBM_E_INVALID, "sbm_plan_create: null argument");
+    if ((m && d->E < 1) || d->n_rows < 0 || d->n_proj < 0) return fail(SBM_E_INVALID, "sbm_plan_create: bad sizes");
+    // m == NULL gives a loss-only plan (row tables for sbm_loss, no integrator tables)
+    int rc = m ? ensure_loaded(m) : require_device();
+    if (rc) return rc;
+    sbm_plan* p = new sbm_plan();
+    p->model = m;
+    p->d = *d;
+#define UP(field, n) if ((rc = upload(p, p->field, d->field, (size_t)(n)))) { sbm_plan_destroy(p); return rc; }
+    if (m) {
+        const size_t NP = (size_t)m->desc.n_params, N = (size_t)m->desc.n_vars;
+        UP(pmap, d->E * NP) UP(pfix, d->E * NP) UP(y0, d->E * N)
+        UP(tout_off, d->E + 1) UP(tout, d->n_tout) UP(orow_off, d->n_tout + 1)
+        UP(row_sim, d->n_orow) UP(row_jac, d->n_orow) UP(row_mask, d->n_orow)
+    }
+    UP(data, d->n_rows) UP(sigma, d->n_rows) UP(row_group, d->n_rows) UP(row_kind, d->n_rows) UP(row_aux, d->n_rows)
+    UP(grp_off, d->n_groups + 1)
+    {
+        // grp_off is a host array: read its last entry for the size of grp_rows
+        int n_gr = d->n_groups > 0 ? d->grp_off[d->n_groups] : 0;
+        UP(grp_rows, n_gr)
+    }
+#undef UP
+    *out = p;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve
+// ------------------------------------------------------------------------------------------------
+extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
+                         const double* theta, long long theta_sb, long long theta_sp,
+                         double* sims, double* jac, int* status, unsigned long long* counters, void* stream)
+{
+    if (!p || !o || !theta || !sims || !status || !counters) return fail(SBM_E_INVALID, "sbm_solve: null argument");
+    if (B <= 0) return fail(SBM_E_INVALID, "sbm_solve: B must be positive");
+    sbm_model* m = p->model;
+    if (!m) return fail(SBM_E_INVALID, "sbm_solve: this is a loss-only plan (created without a model)");
+    int rc = ensure_loaded(m);
+    if (rc) return rc;
+    if (o->solver == SBM_SOLVER_RODAS4 && jac) return fail(SBM_E_INVALID, "RODAS4 kernel integrates states only (no sensitivities)");
+    if (o->solver != SBM_SOLVER_DP5 && o->solver != SBM_SOLVER_RODAS4) return fail(SBM_E_INVALID, "unknown solver");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    SbmSolveArgs a;
+    memset(&a, 0, sizeof a);
+    a.pmap = p->pmap; a.pfix = p->pfix; a.y0 = p->y0; a.tout_off = p->tout_off; a.tout = p->tout;
+    a.orow_off = p->orow_off; a.row_sim = p->row_sim; a.row_jac = p->row_jac; a.row_mask = p->row_mask;
+    a.theta = theta; a.theta_sb = theta_sb; a.theta_sp = theta_sp;
+    a.sims = sims; a.jac = jac; a.status = status; a.counters = counters;
+    a.B = B; a.E = p->d.E; a.n_rows = p->d.n_rows; a.n_proj = p->d.n_proj;
+    a.max_steps = o->max_steps > 0 ? o->max_steps : 500000;
+    a.jac_atomic = p->d.jac_atomic;
+    a.jac_raw = o->jac_raw;
+    if (o->jac_raw && jac && p->d.n_proj != m->desc.n_free) return fail(SBM_E_INVALID, "jac_raw needs a plan with n_proj == n_free");
+    a.rtol = o->rtol; a.atol = o->atol; a.h0 = o->h0;
+
+    if (jac) RT(cudaMemsetAsync(jac, 0, (size_t)B * p->d.n_rows * p->d.n_proj * sizeof(double), st));
+
+    const long long ntraj = B * p->d.E;
+    KernelSlot* ks;
+    long long threads;
+    if (o->solver == SBM_SOLVER_RODAS4) { ks = &m->rodas4; threads = ntraj; }
+    else if (jac) { ks = &m->dp5_sens; threads = ntraj * m->G; }
+    else { ks = &m->dp5_plain; threads = ntraj; }
+    const long long blocks = (threads + m->block - 1) / m->block;
+    if (blocks > 2147483647ll) return fail(SBM_E_INVALID, "batch too large for one launch");
+    void* params[] = {&a};
+    DRV(driver().cuLaunchKernel_(ks->fn, (unsigned)blocks, 1, 1, (unsigned)m->block, 1, 1, 0, (CUstream)st, params, nullptr));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss epilogue
+// ------------------------------------------------------------------------------------------------
+extern "C" int sbm_loss(sbm_plan* p, int loss_kind, int flags, long long B,
+                        const double* theta, long long theta_sb, long long theta_sp,
+                        double* sims, double* jac, double* resid, double* ssr, double* sf, double* sfgrad,
+                        double* grad, void* stream)
+{
+    if (!p || !theta || !sims || !resid || !ssr) return fail(SBM_E_INVALID, "sbm_loss: null argument");
+    if (p->d.n_groups > 0 && !sf) return fail(SBM_E_INVALID, "sbm_loss: sf buffer required when scale-factor groups exist");
+    if (jac && p->d.n_groups > 0 && !sfgrad) return fail(SBM_E_INVALID, "sbm_loss: sfgrad workspace required with jac");
+    if (loss_kind < 0 || loss_kind > 2) return fail(SBM_E_INVALID, "sbm_loss: unknown loss");
+    if (B <= 0) return fail(SBM_E_INVALID, "sbm_loss: B must be positive");
+    int rc = require_device();
+    if (rc) return rc;
+    SbmLossArgs a;
+    memset(&a, 0, sizeof a);
+    a.data = p->data; a.sigma = p->sigma; a.row_group = p->row_group; a.row_kind = p->row_kind; a.row_aux = p->row_aux;
+    a.grp_off = p->grp_off; a.grp_rows = p->grp_rows;
+    a.theta = theta; a.theta_sb = theta_sb; a.theta_sp = theta_sp;
+    a.sims = sims; a.jac = jac; a.resid = resid; a.ssr = ssr; a.sf = sf; a.sfgrad = sfgrad; a.grad = grad;
+    a.B = B; a.n_rows = p->d.n_rows; a.n_proj = p->d.n_proj; a.n_groups = p->d.n_groups;
+    a.loss_kind = loss_kind; a.flags = flags;
+    sbm_launch_loss(a, (cudaStream_t)stream);
+    RT(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused host-buffer entry points
+// ------------------------------------------------------------------------------------------------
+static int host_eval(sbm_plan* p, const sbm_solver_opts_t* o, int loss_kind, int flags, long long B, bool with_jac,
+                     const double* theta_host, double* jac_host, double* model_jac_host, double* resid_host,
+                     double* ssr_host, double* grad_host, double* sf_host, double* sims_host, int* status_host,
+                     unsigned long long* counters_host, void* stream)
+{
+    if (!p || !o || !theta_host) return fail(SBM_E_INVALID, "null argument");
+    if (B <= 0) return fail(SBM_E_INVALID, "B must be positive");
+    int rc = require_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t R = (size_t)p->d.n_rows, P = (size_t)p->d.n_proj, Gn = (size_t)p->d.n_groups, E = (size_t)p->d.E;
+    const size_t nB = (size_t)B;
+    if (p->w_theta.ensure(nB * P * 8) || p->w_sims.ensure(nB * R * 8) || p->w_resid.ensure(nB * R * 8) ||
+        p->w_ssr.ensure(nB * 8) || p->w_sf.ensure((nB * Gn + 1) * 8) || p->w_status.ensure(nB * E * 4) ||
+        p->w_counters.ensure(SBM_N_COUNTERS * 8))
+        return fail(SBM_E_NOMEM, "device workspace allocation failed");
+    if (with_jac && (p->w_jac.ensure(nB * R * P * 8) || p->w_sfgrad.ensure((nB * Gn * P + 1) * 8) || p->w_grad.ensure(nB * P * 8)))
+        return fail(SBM_E_NOMEM, "device workspace allocation failed (Jacobian)");
+    double* d_theta = (double*)p->w_theta.p;
+    double* d_sims = (double*)p->w_sims.p;
+    double* d_jac = with_jac ? (double*)p->w_jac.p : nullptr;
+    RT(cudaMemcpyAsync(d_theta, theta_host, nB * P * 8, cudaMemcpyHostToDevice, st));
+    RT(cudaMemsetAsync(p->w_counters.p, 0, SBM_N_COUNTERS * 8, st));
+    RT(cudaMemsetAsync(d_sims, 0, nB * R * 8, st));
+    rc = sbm_solve(p, o, B, d_theta, (long long)P, 1, d_sims, d_jac, (int*)p->w_status.p,
+                   (unsigned long long*)p->w_counters.p, stream);
+    if (rc) return rc;
+    if (with_jac && model_jac_host) RT(cudaMemcpyAsync(model_jac_host, d_jac, nB * R * P * 8, cudaMemcpyDeviceToHost, st));
+    rc = sbm_loss(p, loss_kind, flags, B, d_theta, (long long)P, 1, d_sims, d_jac, (double*)p->w_resid.p,
+                  (double*)p->w_ssr.p, (double*)p->w_sf.p, with_jac ? (double*)p->w_sfgrad.p : nullptr,
+                  with_jac ? (double*)p->w_grad.p : nullptr, stream);
+    if (rc) return rc;
+    if (resid_host) RT(cudaMemcpyAsync(resid_host, p->w_resid.p, nB * R * 8, cudaMemcpyDeviceToHost, st));
+    if (ssr_host) RT(cudaMemcpyAsync(ssr_host, p->w_ssr.p, nB * 8, cudaMemcpyDeviceToHost, st));
+    if (sf_host && Gn) RT(cudaMemcpyAsync(sf_host, p->w_sf.p, nB * Gn * 8, cudaMemcpyDeviceToHost, st));
+    if (sims_host) RT(cudaMemcpyAsync(sims_host, d_sims, nB * R * 8, cudaMemcpyDeviceToHost, st));
+    if (status_host) RT(cudaMemcpyAsync(status_host, p->w_status.p, nB * E * 4, cudaMemcpyDeviceToHost, st));
+    if (counters_host) RT(cudaMemcpyAsync(counters_host, p->w_counters.p, SBM_N_COUNTERS * 8, cudaMemcpyDeviceToHost, st));
+    if (with_jac) {
+        if (jac_host) RT(cudaMemcpyAsync(jac_host, d_jac, nB * R * P * 8, cudaMemcpyDeviceToHost, st));
+        if (grad_host) RT(cudaMemcpyAsync(grad_host, p->w_grad.p, nB * P * 8, cudaMemcpyDeviceToHost, st));
+    }
+    RT(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int sbm_residuals_host(sbm_plan* p, const sbm_solver_opts_t* opts, int loss_kind, long long B,
+                                  const double* theta_host, double* resid_host, double* ssr_host, double* sf_host,
+                                  double* sims_host, int* status_host, unsigned long long* counters_host, void* stream)
+{
+    return host_eval(p, opts, loss_kind, 0, B, false, theta_host, nullptr, nullptr, resid_host, ssr_host, nullptr, sf_host,
+                     sims_host, status_host, counters_host, stream);
+}
+
+extern "C" int sbm_jacobian_host(sbm_plan* p, const sbm_solver_opts_t* opts, int loss_kind, int flags, long long B,
+                                 const double* theta_host, double* jac_host, double* model_jac_host, double* resid_host,
+                                 double* ssr_host, double* grad_host, double* sf_host, double* sims_host, int* status_host,
+                                 unsigned long long* counters_host, void* stream)
+{
+    return host_eval(p, opts, loss_kind, flags, B, true, theta_host, jac_host, model_jac_host, resid_host, ssr_host, grad_host,
+                     sf_host, sims_host, status_host, counters_host, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 roofline denominator
+// ------------------------------------------------------------------------------------------------
+extern "C" int sbm_fp64_peak(int iters, double* tflops_out, double* ms_out)
+{
+    int rc = require_device();
+    if (rc) return rc;
+    if (iters <= 0) iters = 4096;
+    double tf = 0.0, ms = 0.0;
+    cudaError_t e = sbm_run_fp64_peak(iters, &tf, &ms);
+    if (e != cudaSuccess) return fail(SBM_E_CUDA, std::string("fp64 peak kernel: ") + cudaGetErrorString(e));
+    if (tflops_out) *tflops_out = tf;
+    if (ms_out) *ms_out = ms;
+    return 0;
+}

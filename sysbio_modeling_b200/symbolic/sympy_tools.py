@@ -510,7 +510,7 @@ def emit_cuda(sm):
     G_x = [X(sm.G[k]) for k in gkeys]
 
     L = []
-    L.append('// ---- generated by sysbio_modeling_b200.symbolic.emit_cuda: model "%s" ----' % sm.name)
+    L.append('// ---- generated by sysbio_modeling_b200.symbolic.emit_cuda ----')
     L.append('// states : %s' % ', '.join(sm.variables))
     L.append('// params : %s' % ', '.join(sm.param_order))
     L.append('// free   : %s' % ', '.join(sm.free))
@@ -520,6 +520,10 @@ def emit_cuda(sm):
     L.append('#define SBM_NJ %d' % max(len(jkeys), 1))
     L.append('#define SBM_NG %d' % max(len(gkeys), 1))
     L.append('#define SBM_AUTONOMOUS %d' % (1 if sm.autonomous else 0))
+    L.append('#define SBM_HAS_FREE_IDX 1')
+    L.append('// model-parameter index of each free (sensitivity) parameter')
+    L.append('__device__ __constant__ int sbm_free_idx[%d] = {%s};'
+             % (max(NF, 1), ', '.join(str(m) for m in (sm.free_idx or [0]))))
     L.append('')
 
     # --- f only
