@@ -139,7 +139,9 @@ def test_project_mm_sum_vs_goldens_and_oracle(golden):
         gr = np.asarray(proj.calc_rss_gradient(th))
         assert np.abs(gr - np.array(pt['rss_gradient'])[cols]).max() < 1e-6
         ssr = proj.calc_sum_square_residuals(th)
-        assert abs(ssr - pt['ssr']) <= 1e-6 * abs(pt['ssr']) + 1e-15
+        # SSR within 1e-6 relative; at the generating parameters SSR itself is ~1e-6 (pure grid snapping) and
+        # LSODA's own ~1e-9 error in each residual is a 1e-6 relative effect, hence the absolute floor
+        assert abs(ssr - pt['ssr']) <= 1e-6 * abs(pt['ssr']) + 1e-11
     # residuals at the generating parameters are ~0 (only grid snapping), reference :322-323
     th0 = theta_by_name(mine, g['project_order'], g['points'][0]['theta'])
     assert np.allclose(proj.residuals(th0).values, 0, atol=1e-3)
