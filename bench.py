@@ -50,11 +50,12 @@ def make_thetas(nominal, B, seed):
     return np.log(nominal)[None, :] + 0.25 * rng.standard_normal((B, len(nominal)))
 
 
-def build_project(tol, data=None):
+def build_project(tol, data=None, shape=(0, 0, -1)):
     import sysbio_modeling_b200 as sb
     from sysbio_modeling_b200 import model_files
     mod = model_files.module('mapk_kholodenko')
-    om = sb.OdeModel.from_model_file(model_files.path('mapk_kholodenko'), model_name='mapk')
+    om = sb.OdeModel.from_model_file(model_files.path('mapk_kholodenko'), model_name='mapk', group_lanes=shape[0],
+                                     cols_per_lane=shape[1], stage_smem=shape[2])
     if data is None:
         data = {k: np.ones_like(T_OBS) for k in OBS}
     meas = [sb.TimecourseMeasurement(k, data[k], T_OBS, 0.05 * np.abs(data[k]) + 1e-3) for k in OBS]
@@ -69,7 +70,18 @@ def build_project(tol, data=None):
 _W = {}
 
 
+def _single_thread_env():
+    # LSODA's BDF mode factors dense 184x184 Jacobians through LAPACK; one BLAS thread per worker process
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMEXPR_NUM_THREADS'):
+        os.environ[k] = '1'
+
+
 def _cpu_init(tol):
+    try:
+        from threadpoolctl import threadpool_limits
+        _W['tp'] = threadpool_limits(1)
+    except Exception:
+        pass
     import sbm_oracle
     from sysbio_modeling_b200.symbolic import make_ode_model
     sm, nominal, y0 = mapk_model_info()
@@ -100,6 +112,7 @@ def cpu_reference_rate(thetas, tol, cores=None):
     """Solves/s of the reference CPU path on `cores` host processes over the given parameter sets."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
+    _single_thread_env()
     ctx = mp.get_context('spawn')
     with ctx.Pool(cores, initializer=_cpu_init, initargs=(tol,)) as pool:
         pool.map(_cpu_solve, [thetas[0]] * cores)           # make sure every worker is warm
@@ -161,6 +174,7 @@ def run_reference(args):
     per_step = args.cpu_sample if args.cpu_sample > 0 else max(2 * cores, 32)
     thetas = make_thetas(nominal, per_step * (args.steps + args.warmup), 4)
     import multiprocessing as mp
+    _single_thread_env()
     ctx = mp.get_context('spawn')
     with ctx.Pool(cores, initializer=_cpu_init, initargs=(args.tol,)) as pool:
         pool.map(_cpu_solve, [thetas[0]] * cores)
@@ -206,6 +220,7 @@ def main():
     ap.add_argument('--tol', type=float, default=1e-10, help='rtol = atol (reference: 1e-10)')
     ap.add_argument('--cpu-sample', type=int, default=0, help='parameter sets in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--shape', default='0,0,-1', help='group_lanes,cols_per_lane,stage_smem of the sensitivity kernel (0,0,-1 = auto)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = max(args.warmup, 1)
@@ -228,13 +243,14 @@ def main():
     sm, nominal, y0 = mapk_model_info()
     B = args.batch
     # synthetic data: the model at the nominal parameters with 5 % noise (seeded)
-    proj0 = build_project(args.tol)
+    shape = tuple(int(x) for x in args.shape.split(','))
+    proj0 = build_project(args.tol, shape=shape)
     sims = proj0.residuals_batch(np.log(nominal)[None, :])['sims'][0]
     rng = np.random.default_rng(40)
     labels = [l[1] for l in proj0._labels]
     data = {k: np.array([sims[i] for i, l in enumerate(labels) if l == k]) * (1 + 0.05 * rng.standard_normal(20))
             for k in OBS}
-    proj = build_project(args.tol, data)
+    proj = build_project(args.tol, data, shape)
     t = proj.plan_tables
     info = proj._model.compiled.info()
     cuda_src = proj._model.compiled.cuda
@@ -341,6 +357,8 @@ def main():
             'gpu_launches': 2 * args.steps,
             'kernels': {'sbm_dp5_sens_ms': solve_ms, 'sbm_loss_kernel_ms': float(np.mean(ms_step)) - solve_ms,
                         'group_lanes': info['group_lanes'], 'cols_per_lane': info['cols_per_lane'],
+                        'stage_smem': info['stage_smem'], 'block_threads': info['block_threads'],
+                        'dyn_smem_bytes': info['dyn_smem_bytes'],
                         'regs': info['regs_dp5_sens'], 'local_bytes': info['local_dp5_sens']},
             'counters_per_step': cnt, 'failed_trajectories': status_bad,
             'roofline': {'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',

@@ -61,14 +61,15 @@ typedef struct sbm_model_desc_t {
     int         n_free;          /* sensitivity columns (non-fixed parameters)          */
     int         group_lanes;     /* lanes per trajectory for the sensitivity kernel, 0 = auto */
     int         cols_per_lane;   /* columns per lane, 0 = auto                          */
-    int         block_threads;   /* CTA size, 0 = default (128)                         */
+    int         block_threads;   /* CTA size of the sensitivity kernel, 0 = auto        */
+    int         stage_smem;      /* Runge-Kutta stage vectors: 0 registers, 1 shared memory, -1 auto */
     const char* arch;            /* NULL -> "sm_100a"                                   */
     const char* cache_dir;       /* NULL -> no on-disk cubin cache                      */
 } sbm_model_desc_t;
 
 typedef struct sbm_model_info_t {
     int n_vars, n_params, n_free;
-    int group_lanes, cols_per_lane, block_threads;
+    int group_lanes, cols_per_lane, block_threads, stage_smem, dyn_smem_bytes;
     int regs_dp5_plain, regs_dp5_sens, regs_rodas4;          /* registers per thread (after module load; -1 before) */
     int local_dp5_plain, local_dp5_sens, local_rodas4;       /* local-memory (spill) bytes per thread               */
     int smem_dp5_plain, smem_dp5_sens, smem_rodas4;          /* static shared memory bytes per CTA                  */

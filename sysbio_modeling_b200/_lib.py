@@ -26,12 +26,13 @@ class SbmError(RuntimeError):
 class ModelDesc(ctypes.Structure):
     _fields_ = [('n_vars', ctypes.c_int), ('n_params', ctypes.c_int), ('n_free', ctypes.c_int),
                 ('group_lanes', ctypes.c_int), ('cols_per_lane', ctypes.c_int), ('block_threads', ctypes.c_int),
-                ('arch', ctypes.c_char_p), ('cache_dir', ctypes.c_char_p)]
+                ('stage_smem', ctypes.c_int), ('arch', ctypes.c_char_p), ('cache_dir', ctypes.c_char_p)]
 
 
 class ModelInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
-        'n_vars', 'n_params', 'n_free', 'group_lanes', 'cols_per_lane', 'block_threads',
+        'n_vars', 'n_params', 'n_free', 'group_lanes', 'cols_per_lane', 'block_threads', 'stage_smem',
+        'dyn_smem_bytes',
         'regs_dp5_plain', 'regs_dp5_sens', 'regs_rodas4',
         'local_dp5_plain', 'local_dp5_sens', 'local_rodas4',
         'smem_dp5_plain', 'smem_dp5_sens', 'smem_rodas4', 'cubin_bytes', 'from_cache')]

@@ -89,47 +89,6 @@ __device__ __forceinline__ int sbm_group_or(int v, unsigned gmask)
     return v;
 }
 
-// One evaluation of the (column-split) augmented right-hand side.
-//   x[c][:]  this lane's columns;  cid[c] their ids (0 = state column);  out[c][:] = d/dt of them.
-template <int G, int C, int SENS>
-__device__ __forceinline__ void sbm_rhs(const double t, const double (&x)[C][SBM_N],
-                                        const double* __restrict__ p, const int (&cid)[C],
-                                        const unsigned gmask, const int leader,
-                                        double (&out)[C][SBM_N])
-{
-    double Y[SBM_N];
-#pragma unroll
-    for (int i = 0; i < SBM_N; ++i)
-        Y[i] = (G == 1) ? x[0][i] : __shfl_sync(gmask, x[0][i], leader);
-    if (!SENS) {
-        sbm_f(t, Y, p, out[0]);
-    } else {
-        double f[SBM_N], Jv[SBM_NJ], Gv[SBM_NG];
-        sbm_fJG(t, Y, p, f, Jv, Gv);
-#pragma unroll
-        for (int c = 0; c < C; ++c) sbm_col(f, Jv, Gv, x[c], cid[c], out[c]);
-    }
-}
-
-// Weighted RMS norm pieces (Hairer's sk = atol + rtol*max(|y|,|ynew|)); padded columns hold zeros
-// and add nothing.
-template <int C>
-__device__ __forceinline__ double sbm_sq_scaled(const double (&v)[C][SBM_N], const double (&a)[C][SBM_N],
-                                                const double (&b)[C][SBM_N], const double rtol,
-                                                const double atol)
-{
-    double sq = 0.0;
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-#pragma unroll
-        for (int i = 0; i < SBM_N; ++i) {
-            const double sk = atol + rtol * fmax(fabs(a[c][i]), fabs(b[c][i]));
-            const double q = v[c][i] / sk;
-            sq = fma(q, q, sq);
-        }
-    return sq;
-}
-
 // Observable rows for one output time: value (state column) and d/dtheta row (sensitivity columns).
 template <int G, int C, int SENS>
 __device__ __forceinline__ void sbm_emit_rows(const SbmSolveArgs& a, const long long b, const int kt,
@@ -159,9 +118,110 @@ __device__ __forceinline__ void sbm_emit_rows(const SbmSolveArgs& a, const long 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stage-vector storage.  KSM = 0: the six k-vectors of this lane's columns live in registers.
+// KSM = 1: they live in dynamic shared memory, element-major / thread-minor (stride = CTA size) so a
+// warp's accesses are consecutive doubles - conflict-free LDS.64/STS.64.  Only x (and one transient
+// column of the stage input) stay in registers, which is what lets a lane own C > 1 columns of a
+// large system: the model's primal part (f, J, G) is then evaluated once per lane for C columns and
+// once per warp instruction for 32/G trajectories.
+// ---------------------------------------------------------------------------------------------
+template <int C, int KSM, int BLOCK>
+struct SbmStages {
+    double r[KSM ? 1 : 6][KSM ? 1 : C][KSM ? 1 : SBM_N];
+    double* s;
+    template <int V>
+    __device__ __forceinline__ double get(const int c, const int i) const
+    {
+        if (KSM) return s[((V * C + c) * SBM_N + i) * BLOCK];
+        return r[KSM ? 0 : V][KSM ? 0 : c][KSM ? 0 : i];
+    }
+    template <int V>
+    __device__ __forceinline__ void set(const int c, const int i, const double v)
+    {
+        if (KSM) s[((V * C + c) * SBM_N + i) * BLOCK] = v;
+        else r[KSM ? 0 : V][KSM ? 0 : c][KSM ? 0 : i] = v;
+    }
+};
+
+// stage input of column c for stage S (2..7):  x + h * sum_j a_Sj k_j   (slots: k1..k6 = 0..5)
+template <int S, int C, int KSM, int BLOCK>
+__device__ __forceinline__ double sbm_stage_in(const SbmStages<C, KSM, BLOCK>& K, const double xv,
+                                               const double h, const int c, const int i)
+{
+    if (S == 2) return fma(h * DP_A21, K.template get<0>(c, i), xv);
+    if (S == 3) return fma(h * DP_A32, K.template get<1>(c, i), fma(h * DP_A31, K.template get<0>(c, i), xv));
+    if (S == 4) return fma(h * DP_A43, K.template get<2>(c, i), fma(h * DP_A42, K.template get<1>(c, i),
+                       fma(h * DP_A41, K.template get<0>(c, i), xv)));
+    if (S == 5) return fma(h * DP_A54, K.template get<3>(c, i), fma(h * DP_A53, K.template get<2>(c, i),
+                       fma(h * DP_A52, K.template get<1>(c, i), fma(h * DP_A51, K.template get<0>(c, i), xv))));
+    if (S == 6) return fma(h * DP_A65, K.template get<4>(c, i), fma(h * DP_A64, K.template get<3>(c, i),
+                       fma(h * DP_A63, K.template get<2>(c, i), fma(h * DP_A62, K.template get<1>(c, i),
+                       fma(h * DP_A61, K.template get<0>(c, i), xv)))));
+    // S == 7: the 5th-order solution
+    return fma(h * DP_A76, K.template get<5>(c, i), fma(h * DP_A75, K.template get<4>(c, i),
+           fma(h * DP_A74, K.template get<3>(c, i), fma(h * DP_A73, K.template get<2>(c, i),
+           fma(h * DP_A71, K.template get<0>(c, i), xv)))));
+}
+
+// One stage: build the stage input column by column (transient, N doubles), evaluate the model's primal
+// part once for the group's state column, write k_S.  Stage 7 stores k7 into the k2 slot (k2 is dead by
+// then) and returns this lane's share of the squared scaled error.
+template <int S, int G, int C, int SENS, int KSM, int BLOCK>
+__device__ __forceinline__ double sbm_dp5_stage(SbmStages<C, KSM, BLOCK>& K, const double (&x)[C][SBM_N],
+                                                const double t, const double h, const double* __restrict__ p,
+                                                const int (&cid)[C], const unsigned gmask, const int leader,
+                                                const double rtol, const double atol)
+{
+    constexpr int N = SBM_N;
+    constexpr int VOUT = (S == 7) ? 1 : S - 1;          // slot receiving k_S
+    const double cs = (S == 2) ? DP_C2 : (S == 3) ? DP_C3 : (S == 4) ? DP_C4 : (S == 5) ? DP_C5 : 1.0;
+    double w[N], Y[N], out[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) w[i] = sbm_stage_in<S, C, KSM, BLOCK>(K, x[0][i], h, 0, i);
+#pragma unroll
+    for (int i = 0; i < N; ++i) Y[i] = (G == 1) ? w[i] : __shfl_sync(gmask, w[i], leader);
+    double sq = 0.0;
+    if (!SENS) {
+        sbm_f(t + cs * h, Y, p, out);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (S == 7) {
+                const double er = h * fma(DP_E7, out[i], fma(DP_E6, K.template get<5>(0, i), fma(DP_E5, K.template get<4>(0, i),
+                                  fma(DP_E4, K.template get<3>(0, i), fma(DP_E3, K.template get<2>(0, i), DP_E1 * K.template get<0>(0, i))))));
+                const double q = er / (atol + rtol * fmax(fabs(x[0][i]), fabs(w[i])));
+                sq = fma(q, q, sq);
+            }
+            K.template set<VOUT>(0, i, out[i]);
+        }
+        return sq;
+    }
+    double f[N], Jv[SBM_NJ], Gv[SBM_NG];
+    sbm_fJG(t + cs * h, Y, p, f, Jv, Gv);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        if (c > 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) w[i] = sbm_stage_in<S, C, KSM, BLOCK>(K, x[c][i], h, c, i);
+        }
+        sbm_col(f, Jv, Gv, w, cid[c], out);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (S == 7) {
+                const double er = h * fma(DP_E7, out[i], fma(DP_E6, K.template get<5>(c, i), fma(DP_E5, K.template get<4>(c, i),
+                                  fma(DP_E4, K.template get<3>(c, i), fma(DP_E3, K.template get<2>(c, i), DP_E1 * K.template get<0>(c, i))))));
+                const double q = er / (atol + rtol * fmax(fabs(x[c][i]), fabs(w[i])));
+                sq = fma(q, q, sq);
+            }
+            K.template set<VOUT>(c, i, out[i]);
+        }
+    }
+    return sq;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Adaptive Dormand-Prince 5(4), FSAL, PI step controller (Hairer's DOPRI5 constants)
 // ---------------------------------------------------------------------------------------------
-template <int G, int C, int SENS, int BLOCK>
+template <int G, int C, int SENS, int KSM, int BLOCK>
 __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
 {
     constexpr int N = SBM_N;
@@ -169,6 +229,7 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
     static_assert(G * C >= NCOL, "group too small for the augmented system");
     constexpr int GPB = BLOCK / G;                 // groups (trajectories) per block
     __shared__ double sp[GPB * SBM_NPP];
+    extern __shared__ double sbm_dyn[];            // KSM: [6][C][N][BLOCK] stage vectors
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -210,32 +271,51 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
     const int kt0 = a.tout_off[e], kt1 = a.tout_off[e + 1];
     const double tend = (kt1 > kt0) ? a.tout[kt1 - 1] : 0.0;
 
-    double k1[C][N], k2[C][N], k3[C][N], k4[C][N], k5[C][N], k6[C][N], w[C][N];
+    SbmStages<C, KSM, BLOCK> K;
+    K.s = sbm_dyn + tid;
     unsigned nstep = 0, nrej = 0, nrhs = 0;
     int status = SBM_OK;
     double t = 0.0;
 
-    sbm_rhs<G, C, SENS>(t, x, p, cid, gmask, leader, k1);
-    nrhs++;
-
-    // ---- initial step size (Hairer, Norsett, Wanner II.4) ----
+    // k1 = F(t0, x0): run "stage 2" with h = 0 into slot 1, then move it to slot 0
     double h;
     {
-        const double d0 = sqrt(sbm_group_sum<G>(sbm_sq_scaled<C>(x, x, x, rtol, atol), gmask) * inv_naug);
-        const double d1 = sqrt(sbm_group_sum<G>(sbm_sq_scaled<C>(k1, x, x, rtol, atol), gmask) * inv_naug);
+        // with h = 0 the stage input is x itself (slot 0 must hold finite numbers: 0 * NaN = NaN)
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int i = 0; i < N; ++i) K.template set<0>(c, i, 0.0);
+        sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, 0.0, p, cid, gmask, leader, rtol, atol);
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double kv = K.template get<1>(c, i);
+                K.template set<0>(c, i, kv);
+                const double sk = atol + rtol * fabs(x[c][i]);
+                d0 = fma(x[c][i] / sk, x[c][i] / sk, d0);
+                d1 = fma(kv / sk, kv / sk, d1);
+            }
+        nrhs++;
+        // ---- initial step size (Hairer, Norsett, Wanner II.4) ----
+        d0 = sqrt(sbm_group_sum<G>(d0, gmask) * inv_naug);
+        d1 = sqrt(sbm_group_sum<G>(d1, gmask) * inv_naug);
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h0 = fmin(h0, tend);
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int i = 0; i < N; ++i) w[c][i] = fma(h0, k1[c][i], x[c][i]);
-        sbm_rhs<G, C, SENS>(t + h0, w, p, cid, gmask, leader, k2);
+        // explicit Euler probe: stage 2 with step h0/A21 evaluates F(x + h0*k1) into slot 1
+        sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, h0 / DP_A21, p, cid, gmask, leader, rtol, atol);
         nrhs++;
+        double d2 = 0.0;
 #pragma unroll
         for (int c = 0; c < C; ++c)
 #pragma unroll
-            for (int i = 0; i < N; ++i) k2[c][i] -= k1[c][i];
-        const double d2 = sqrt(sbm_group_sum<G>(sbm_sq_scaled<C>(k2, x, x, rtol, atol), gmask) * inv_naug) / h0;
+            for (int i = 0; i < N; ++i) {
+                const double sk = atol + rtol * fabs(x[c][i]);
+                const double q = (K.template get<1>(c, i) - K.template get<0>(c, i)) / sk;
+                d2 = fma(q, q, d2);
+            }
+        d2 = sqrt(sbm_group_sum<G>(d2, gmask) * inv_naug) / h0;
         const double dm = fmax(d1, d2);
         const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
         h = fmin(fmin(100.0 * h0, h1), tend);
@@ -256,64 +336,14 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
             if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) { status = SBM_ERR_UNDERFLOW; break; }
             nstep++;
 
-            // stage 2
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-#pragma unroll
-                for (int i = 0; i < N; ++i) w[c][i] = fma(h * DP_A21, k1[c][i], x[c][i]);
-            sbm_rhs<G, C, SENS>(t + DP_C2 * h, w, p, cid, gmask, leader, k2);
-            // stage 3
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-#pragma unroll
-                for (int i = 0; i < N; ++i)
-                    w[c][i] = fma(h * DP_A32, k2[c][i], fma(h * DP_A31, k1[c][i], x[c][i]));
-            sbm_rhs<G, C, SENS>(t + DP_C3 * h, w, p, cid, gmask, leader, k3);
-            // stage 4
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-#pragma unroll
-                for (int i = 0; i < N; ++i)
-                    w[c][i] = fma(h * DP_A43, k3[c][i], fma(h * DP_A42, k2[c][i], fma(h * DP_A41, k1[c][i], x[c][i])));
-            sbm_rhs<G, C, SENS>(t + DP_C4 * h, w, p, cid, gmask, leader, k4);
-            // stage 5
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-#pragma unroll
-                for (int i = 0; i < N; ++i)
-                    w[c][i] = fma(h * DP_A54, k4[c][i], fma(h * DP_A53, k3[c][i],
-                              fma(h * DP_A52, k2[c][i], fma(h * DP_A51, k1[c][i], x[c][i]))));
-            sbm_rhs<G, C, SENS>(t + DP_C5 * h, w, p, cid, gmask, leader, k5);
-            // stage 6
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-#pragma unroll
-                for (int i = 0; i < N; ++i)
-                    w[c][i] = fma(h * DP_A65, k5[c][i], fma(h * DP_A64, k4[c][i], fma(h * DP_A63, k3[c][i],
-                              fma(h * DP_A62, k2[c][i], fma(h * DP_A61, k1[c][i], x[c][i])))));
-            sbm_rhs<G, C, SENS>(t + h, w, p, cid, gmask, leader, k6);
-            // 5th-order solution (k2 is dead from here on: it receives k7)
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-#pragma unroll
-                for (int i = 0; i < N; ++i)
-                    w[c][i] = fma(h * DP_A76, k6[c][i], fma(h * DP_A75, k5[c][i], fma(h * DP_A74, k4[c][i],
-                              fma(h * DP_A73, k3[c][i], fma(h * DP_A71, k1[c][i], x[c][i])))));
-            sbm_rhs<G, C, SENS>(t + h, w, p, cid, gmask, leader, k2);
+            sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
+            sbm_dp5_stage<3, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
+            sbm_dp5_stage<4, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
+            sbm_dp5_stage<5, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
+            sbm_dp5_stage<6, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
+            const double sq = sbm_dp5_stage<7, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
             nrhs += 6;
-
             // embedded error estimate, scaled RMS over the whole augmented state
-            double sq = 0.0;
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const double er = h * fma(DP_E7, k2[c][i], fma(DP_E6, k6[c][i], fma(DP_E5, k5[c][i],
-                                      fma(DP_E4, k4[c][i], fma(DP_E3, k3[c][i], DP_E1 * k1[c][i])))));
-                    const double sk = atol + rtol * fmax(fabs(x[c][i]), fabs(w[c][i]));
-                    const double q = er / sk;
-                    sq = fma(q, q, sq);
-                }
             const double err = sqrt(sbm_group_sum<G>(sq, gmask) * inv_naug);
 
             if (err <= 1.0) {
@@ -323,10 +353,14 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
                 fac = fmaxf(0.1f, fminf(5.0f, fac / 0.9f));
                 facold = fmaxf(ferr, 1e-4f);
                 t = clipped ? tk : t + h;
+                // x <- 5th-order solution (recomputed: the stage input is transient), k1 <- k7 (FSAL)
 #pragma unroll
                 for (int c = 0; c < C; ++c)
 #pragma unroll
-                    for (int i = 0; i < N; ++i) { x[c][i] = w[c][i]; k1[c][i] = k2[c][i]; }
+                    for (int i = 0; i < N; ++i) {
+                        x[c][i] = sbm_stage_in<7, C, KSM, BLOCK>(K, x[c][i], h, c, i);
+                        K.template set<0>(c, i, K.template get<1>(c, i));
+                    }
                 double hnew = h / (double)fac;
                 if (last_rejected) hnew = fmin(hnew, h);
                 if (clipped) hnew = fmax(hnew, hprop);   // a clipped step must not shrink the cruise step
@@ -661,9 +695,9 @@ __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
 // ---------------------------------------------------------------------------------------------
 // kernel entry points are instantiated by the host (sbm_api.cu appends SBM_DEFINE_* lines)
 // ---------------------------------------------------------------------------------------------
-#define SBM_DEFINE_DP5(NAME, G, C, SENS, BLOCK)                                             \
+#define SBM_DEFINE_DP5(NAME, G, C, SENS, KSM, BLOCK)                                        \
     extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \
-    { sbm_dp5_impl<G, C, SENS, BLOCK>(a); }
+    { sbm_dp5_impl<G, C, SENS, KSM, BLOCK>(a); }
 
 #define SBM_DEFINE_RODAS4(NAME, BLOCK)                                                      \
     extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \

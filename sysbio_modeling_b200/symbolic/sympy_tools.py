@@ -353,10 +353,27 @@ class sbm_rcp(sp.Function):
         return -sbm_rcp(self.args[0]) ** 2
 
 
-def _share_reciprocals(e):
-    """Rewrite x**-k as sbm_rcp(x)**k so that the emitted code divides once per denominator."""
-    return e.replace(lambda n: n.is_Pow and n.exp.is_Integer and n.exp < 0,
-                     lambda n: sbm_rcp(n.base) ** (-n.exp))
+class sbm_exp(sp.Function):
+    """Opaque exp/log pair used to print x**a (a symbolic) as exp(a*log(x)): SymPy would otherwise fold
+    it back into a Pow.  Lets CSE share log(x) between x**a and d(x**a)/da = x**a*log(x)."""
+    nargs = 1
+
+
+class sbm_log(sp.Function):
+    nargs = 1
+
+
+def _share_reciprocals(e, pow_via_explog=True):
+    """Rewrite x**-k as sbm_rcp(x)**k so that the emitted code divides once per denominator, and
+    (optionally) x**a with a non-numeric exponent as exp(a*log(x)) - valid for positive bases, which is
+    what real powers of concentrations require anyway (a negative base gives NaN either way)."""
+    e = e.replace(lambda n: n.is_Pow and n.exp.is_Integer and n.exp < 0,
+                  lambda n: sbm_rcp(n.base) ** (-n.exp))
+    if pow_via_explog:
+        e = e.replace(lambda n: n.is_Pow and not n.exp.is_number,
+                      lambda n: sbm_exp(n.exp * sbm_log(n.base)))
+        e = e.replace(lambda n: isinstance(n, sp.log), lambda n: sbm_log(n.args[0]))
+    return e
 
 
 class _CudaPrinter(C99CodePrinter):
@@ -364,6 +381,12 @@ class _CudaPrinter(C99CodePrinter):
 
     def _print_sbm_rcp(self, expr):
         return '(1.0/(%s))' % self._print(expr.args[0])
+
+    def _print_sbm_exp(self, expr):
+        return 'exp(%s)' % self._print(expr.args[0])
+
+    def _print_sbm_log(self, expr):
+        return 'log(%s)' % self._print(expr.args[0])
 
     def _print_Pow(self, expr):
         base, ex = expr.base, expr.exp
@@ -488,7 +511,7 @@ def _emit_block(lines, rep, outs, printer, pad='    '):
         lines.append(pad + '%s = %s;' % (target, printer.doprint(e)))
 
 
-def emit_cuda(sm):
+def emit_cuda(sm, pow_via_explog=True):
     """Emit the device functions the integrator kernels are compiled against (NVRTC, sm_100a)."""
     pr = _CudaPrinter()
     N, NP, NF = sm.n_vars, sm.n_params, sm.n_free
@@ -503,7 +526,7 @@ def emit_cuda(sm):
     sub.update(psub)
 
     def X(e):
-        return _share_reciprocals(sp.sympify(e).xreplace(sub))
+        return _share_reciprocals(sp.sympify(e).xreplace(sub), pow_via_explog)
 
     f_x = [X(e) for e in sm.f]
     J_x = [X(sm.J[k]) for k in jkeys]

@@ -1,0 +1,107 @@
+"""CPU: the symbolic front end (reference symbolic/sympy_tools.py) - parsing, sensitivity derivation, the
+Python emitter in the reference's generated-file layout and the CUDA emitter's structure and op counts.
+Intent of the reference's (stale) tests/test_sympy_tools.py: generated model == hand model under odeint."""
+import numpy as np
+import sympy as sp
+from scipy.integrate import odeint
+
+from sysbio_modeling_b200 import model_files
+from sysbio_modeling_b200.symbolic import (parse_model_file, process_model_dict, symbolic_model_from_file,
+                                           trace_rhs_callable, emit_python, emit_cuda, make_ode_model, count_flops)
+
+
+def test_parse_sections_and_name_collisions():
+    d = parse_model_file(model_files.path('reversible_mm'))
+    assert list(d['Parameters']) == ['k1f', 'k1r', 'k2f', 'k2r']
+    assert list(d['Variables']) == ['S', 'E', 'ES', 'P']          # S, E are SymPy globals: must stay Symbols
+    assert all(isinstance(v, sp.Symbol) for v in d['Variables'].values())
+    assert set(d['Rate Laws']) == {'r1', 'r2'}
+    sm = symbolic_model_from_file(model_files.path('reversible_mm'))
+    S, E, ES, P = sm.var_syms
+    k1f, k1r, k2f, k2r = sm.param_syms
+    assert sp.simplify(sm.f[0] - (-(k1f * E * S - k1r * ES))) == 0
+    assert sm.n_free == 4 and len(sm.J) == 14 and sm.autonomous
+
+
+def test_generated_python_matches_hand_written_rhs():
+    sm = symbolic_model_from_file(model_files.path('michaelis_menten'))
+    f = make_ode_model(sm, sensitivities=False)
+    p = np.array([1e-3, 0.001, 0.01, 0.01, 0.001])
+
+    def hand(y, t):
+        v = p[0] * y[0] / (p[1] + y[0])
+        return [p[2] - v - p[3] * y[0], v - p[4] * y[1]]
+    out = np.zeros(2)
+
+    def gen(y, t):
+        f(y, t, out, p)
+        return out.copy()
+    t = np.linspace(0, 100, 30)
+    assert np.allclose(odeint(hand, [0, 0], t, rtol=1e-10, atol=1e-12),
+                       odeint(gen, [0, 0], t, rtol=1e-10, atol=1e-12), rtol=1e-7, atol=1e-12)
+
+
+def test_sensitivity_layout_and_values_vs_finite_differences():
+    """yout[N + i*P + j] = d/dt (dx_i/dp_j) (reference sympy_tools.py:135-145 ordering)."""
+    sm = symbolic_model_from_file(model_files.path('michaelis_menten'))
+    s = make_ode_model(sm, sensitivities=True)
+    assert 'yout[11]' in s.source and 'sens_s_vmax = y[2]' in s.source and 'sens_p_k_deg_p = y[11]' in s.source
+    p = np.array([1e-3, 0.002, 0.01, 0.01, 0.001])
+    out = np.zeros(12)
+
+    def rhs(y, t):
+        s(y, t, out, p)
+        return out.copy()
+    t = np.linspace(0, 50, 6)
+    sol = odeint(rhs, np.zeros(12), t, rtol=1e-11, atol=1e-13)
+    f = make_ode_model(sm, sensitivities=False)
+    o2 = np.zeros(2)
+    for j in range(5):
+        def run(pp):
+            def r(y, tt):
+                f(y, tt, o2, pp)
+                return o2.copy()
+            return odeint(r, np.zeros(2), t, rtol=1e-11, atol=1e-13)
+        h = 1e-6 * p[j]
+        pp, pm = p.copy(), p.copy()
+        pp[j] += h
+        pm[j] -= h
+        fd = (run(pp) - run(pm)) / (2 * h)
+        for i in range(2):
+            assert np.allclose(sol[:, 2 + i * 5 + j], fd[:, i], rtol=2e-4, atol=1e-7)
+
+
+def test_fixed_parameters_drop_columns():
+    sm = symbolic_model_from_file(model_files.path('michaelis_menten'), fixed_params=['km', 'k_deg_p'])
+    assert sm.free == ['vmax', 'k_synt_s', 'k_deg_s'] and sm.free_idx == [0, 2, 3]
+    cs = emit_cuda(sm)
+    assert cs.n_free == 3 and '#define SBM_NF 3' in cs.source and 'sbm_free_idx[3] = {0, 2, 3}' in cs.source
+    d = process_model_dict(parse_model_file(model_files.path('michaelis_menten')), fixed_params=['km'])
+    assert d['Parameters']['km'] == 'fixed' and len(d['Sensitivity Equations']) == 8
+    assert list(d['Sensitivity Equations'])[0] == 'd_sens_s_vmax'
+
+
+def test_trace_callable_equals_model_file():
+    sm = symbolic_model_from_file(model_files.path('michaelis_menten'))
+    f = make_ode_model(sm, False)
+    tr = trace_rhs_callable(f, 2, sm.param_order)
+    sub = dict(zip(tr.var_syms, sm.var_syms))
+    sub.update(dict(zip(tr.param_syms, sm.param_syms)))
+    for a, b in zip(tr.f, sm.f):
+        assert sp.simplify(a.xreplace(sub) - b) == 0
+    assert tr.fingerprint() != sm.fingerprint()          # different symbol names, same maths
+
+
+def test_cuda_emitter_structure_and_flop_model():
+    sm = symbolic_model_from_file(model_files.path('mapk_kholodenko'))
+    cs = emit_cuda(sm)
+    assert (cs.n_vars, cs.n_params, cs.n_free, cs.nnz_J, cs.nnz_G) == (8, 22, 22, 26, 44)
+    for fn in ('sbm_f', 'sbm_fJG', 'sbm_col', 'sbm_jac_dense', 'sbm_dfdt'):
+        assert 'void %s(' % fn in cs.source
+    # one reciprocal per distinct denominator: 10 Michaelis-Menten terms + Ki + Hill denominator + 1/MAPK_PP
+    assert cs.source.split('void sbm_fJG')[1].split('void sbm_col')[0].count('1.0/') == 13
+    # algorithmic cost of one augmented RHS = f,J,G once + 22 x (2 flops per Jacobian non-zero) + 44 adds
+    assert cs.flops_col == 2 * 26
+    assert cs.flops_sens_rhs == cs.flops_fJG + 22 * cs.flops_col + 44
+    assert 1200 < cs.flops_sens_rhs < 1500
+    assert count_flops([sp.sympify('a*b + c')]) == 2 and count_flops([sp.sympify('a**3/b')]) == 4
