@@ -73,19 +73,13 @@
 // ---------------------------------------------------------------------------------------------
 // group helpers
 // ---------------------------------------------------------------------------------------------
+// xor-butterfly over the G lanes of a group; the whole warp takes part (warp-uniform control flow), so the
+// mask is the constant full mask and offsets < G keep the exchange inside each group
 template <int G>
-__device__ __forceinline__ double sbm_group_sum(double v, unsigned gmask)
+__device__ __forceinline__ double sbm_group_sum(double v)
 {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
-    return v;
-}
-
-template <int G>
-__device__ __forceinline__ int sbm_group_or(int v, unsigned gmask)
-{
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(gmask, v, o);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
@@ -169,7 +163,7 @@ __device__ __forceinline__ double sbm_stage_in(const SbmStages<C, KSM, BLOCK>& K
 template <int S, int G, int C, int SENS, int KSM, int BLOCK>
 __device__ __forceinline__ double sbm_dp5_stage(SbmStages<C, KSM, BLOCK>& K, const double (&x)[C][SBM_N],
                                                 const double t, const double h, const double* __restrict__ p,
-                                                const int (&cid)[C], const unsigned gmask, const int leader,
+                                                const int (&cid)[C], const int leader,
                                                 const double rtol, const double atol)
 {
     constexpr int N = SBM_N;
@@ -179,7 +173,7 @@ __device__ __forceinline__ double sbm_dp5_stage(SbmStages<C, KSM, BLOCK>& K, con
 #pragma unroll
     for (int i = 0; i < N; ++i) w[i] = sbm_stage_in<S, C, KSM, BLOCK>(K, x[0][i], h, 0, i);
 #pragma unroll
-    for (int i = 0; i < N; ++i) Y[i] = (G == 1) ? w[i] : __shfl_sync(gmask, w[i], leader);
+    for (int i = 0; i < N; ++i) Y[i] = (G == 1) ? w[i] : __shfl_sync(0xffffffffu, w[i], leader);
     double sq = 0.0;
     if (!SENS) {
         sbm_f(t + cs * h, Y, p, out);
@@ -188,7 +182,7 @@ __device__ __forceinline__ double sbm_dp5_stage(SbmStages<C, KSM, BLOCK>& K, con
             if (S == 7) {
                 const double er = h * fma(DP_E7, out[i], fma(DP_E6, K.template get<5>(0, i), fma(DP_E5, K.template get<4>(0, i),
                                   fma(DP_E4, K.template get<3>(0, i), fma(DP_E3, K.template get<2>(0, i), DP_E1 * K.template get<0>(0, i))))));
-                const double q = er / (atol + rtol * fmax(fabs(x[0][i]), fabs(w[i])));
+                const double q = er * sbm_rcp(atol + rtol * fmax(fabs(x[0][i]), fabs(w[i])));
                 sq = fma(q, q, sq);
             }
             K.template set<VOUT>(0, i, out[i]);
@@ -209,7 +203,7 @@ __device__ __forceinline__ double sbm_dp5_stage(SbmStages<C, KSM, BLOCK>& K, con
             if (S == 7) {
                 const double er = h * fma(DP_E7, out[i], fma(DP_E6, K.template get<5>(c, i), fma(DP_E5, K.template get<4>(c, i),
                                   fma(DP_E4, K.template get<3>(c, i), fma(DP_E3, K.template get<2>(c, i), DP_E1 * K.template get<0>(c, i))))));
-                const double q = er / (atol + rtol * fmax(fabs(x[c][i]), fabs(w[i])));
+                const double q = er * sbm_rcp(atol + rtol * fmax(fabs(x[c][i]), fabs(w[i])));
                 sq = fma(q, q, sq);
             }
             K.template set<VOUT>(c, i, out[i]);
@@ -220,12 +214,18 @@ __device__ __forceinline__ double sbm_dp5_stage(SbmStages<C, KSM, BLOCK>& K, con
 
 // ---------------------------------------------------------------------------------------------
 // Adaptive Dormand-Prince 5(4), FSAL, PI step controller (Hairer's DOPRI5 constants)
+//
+// Control flow is WARP-UNIFORM: every lane of a warp runs the same flat loop until all groups of the
+// warp are done; a finished (or out-of-range) group keeps executing with its writes predicated off.
+// That costs nothing under SIMT (the warp would wait for its slowest group anyway) and lets every
+// shuffle use the constant full mask - no per-shuffle convergence barriers, one basic block per stage.
 // ---------------------------------------------------------------------------------------------
 template <int G, int C, int SENS, int KSM, int BLOCK>
 __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
 {
     constexpr int N = SBM_N;
     constexpr int NCOL = SENS ? (SBM_NF + 1) : 1;
+    constexpr unsigned FULL = 0xffffffffu;
     static_assert(G * C >= NCOL, "group too small for the augmented system");
     constexpr int GPB = BLOCK / G;                 // groups (trajectories) per block
     __shared__ double sp[GPB * SBM_NPP];
@@ -235,9 +235,10 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
     const int lane = tid & 31;
     const int lig = (G == 1) ? 0 : (lane & (G - 1));
     const int leader = lane - lig;
-    const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << leader);
-    const long long traj = ((long long)blockIdx.x * BLOCK + tid) / G;
-    if (traj >= a.B * (long long)a.E) return;      // whole groups leave together
+    const long long ntraj = a.B * (long long)a.E;
+    const long long traj_raw = ((long long)blockIdx.x * BLOCK + tid) / G;
+    const bool active = traj_raw < ntraj;
+    const long long traj = active ? traj_raw : 0;  // idle groups shadow trajectory 0 and write nothing
     const int e = (int)(traj % a.E);
     const long long b = traj / a.E;
 
@@ -247,7 +248,7 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
         const int c = a.pmap[e * SBM_NP + m];
         p[m] = (c >= 0) ? exp(a.theta[b * a.theta_sb + c * a.theta_sp]) : a.pfix[e * SBM_NP + m];
     }
-    __syncwarp(gmask);
+    __syncwarp();
 
     int cid[C], pcol[C];
     double pscale[C];
@@ -268,8 +269,11 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
 
     const double rtol = a.rtol, atol = a.atol;
     const double inv_naug = 1.0 / (double)(N * NCOL);
-    const int kt0 = a.tout_off[e], kt1 = a.tout_off[e + 1];
-    const double tend = (kt1 > kt0) ? a.tout[kt1 - 1] : 0.0;
+    int kt = a.tout_off[e];
+    const int kt1 = a.tout_off[e + 1];
+    const double tend = (kt1 > kt) ? a.tout[kt1 - 1] : 1.0;
+    bool done = !active || kt >= kt1;
+    double tk = done ? 0.0 : a.tout[kt];
 
     SbmStages<C, KSM, BLOCK> K;
     K.s = sbm_dyn + tid;
@@ -285,7 +289,7 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
         for (int c = 0; c < C; ++c)
 #pragma unroll
             for (int i = 0; i < N; ++i) K.template set<0>(c, i, 0.0);
-        sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, 0.0, p, cid, gmask, leader, rtol, atol);
+        sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, 0.0, p, cid, leader, rtol, atol);
         double d0 = 0.0, d1 = 0.0;
 #pragma unroll
         for (int c = 0; c < C; ++c)
@@ -293,29 +297,28 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
             for (int i = 0; i < N; ++i) {
                 const double kv = K.template get<1>(c, i);
                 K.template set<0>(c, i, kv);
-                const double sk = atol + rtol * fabs(x[c][i]);
-                d0 = fma(x[c][i] / sk, x[c][i] / sk, d0);
-                d1 = fma(kv / sk, kv / sk, d1);
+                const double isk = sbm_rcp(atol + rtol * fabs(x[c][i]));
+                d0 = fma(x[c][i] * isk, x[c][i] * isk, d0);
+                d1 = fma(kv * isk, kv * isk, d1);
             }
         nrhs++;
         // ---- initial step size (Hairer, Norsett, Wanner II.4) ----
-        d0 = sqrt(sbm_group_sum<G>(d0, gmask) * inv_naug);
-        d1 = sqrt(sbm_group_sum<G>(d1, gmask) * inv_naug);
+        d0 = sqrt(sbm_group_sum<G>(d0) * inv_naug);
+        d1 = sqrt(sbm_group_sum<G>(d1) * inv_naug);
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h0 = fmin(h0, tend);
         // explicit Euler probe: stage 2 with step h0/A21 evaluates F(x + h0*k1) into slot 1
-        sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, h0 / DP_A21, p, cid, gmask, leader, rtol, atol);
+        sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, h0 / DP_A21, p, cid, leader, rtol, atol);
         nrhs++;
         double d2 = 0.0;
 #pragma unroll
         for (int c = 0; c < C; ++c)
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                const double sk = atol + rtol * fabs(x[c][i]);
-                const double q = (K.template get<1>(c, i) - K.template get<0>(c, i)) / sk;
+                const double q = (K.template get<1>(c, i) - K.template get<0>(c, i)) * sbm_rcp(atol + rtol * fabs(x[c][i]));
                 d2 = fma(q, q, d2);
             }
-        d2 = sqrt(sbm_group_sum<G>(d2, gmask) * inv_naug) / h0;
+        d2 = sqrt(sbm_group_sum<G>(d2) * inv_naug) / h0;
         const double dm = fmax(d1, d2);
         const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
         h = fmin(fmin(100.0 * h0, h1), tend);
@@ -323,29 +326,40 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
     }
 
     float facold = 1e-4f;
-    bool poison = false, last_rejected = false;
+    bool last_rejected = false;
 
-    for (int kt = kt0; kt < kt1; ++kt) {
-        const double tk = a.tout[kt];
-        while (status == SBM_OK && t < tk) {
-            // clip onto the output time; remember the unclipped proposal
-            const double hprop = h;
-            bool clipped = false;
+    while (__any_sync(FULL, !done)) {
+        // ---- arrived at an output time (or failed: flush the remaining rows as NaN) ----
+        if (!done && (t >= tk || status != SBM_OK)) {
+            sbm_emit_rows<G, C, SENS>(a, b, kt, x, cid, pcol, pscale, status != SBM_OK);
+            kt++;
+            done = kt >= kt1;
+            if (!done) tk = a.tout[kt];
+        }
+        const bool stepping = !done && status == SBM_OK && t < tk;
+        // clip onto the output time; remember the unclipped proposal
+        const double hprop = h;
+        bool clipped = false;
+        if (stepping) {
             if (t + 1.01 * h >= tk) { h = tk - t; clipped = true; }
-            if (nstep >= (unsigned)a.max_steps) { status = SBM_ERR_MAXSTEPS; break; }
-            if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) { status = SBM_ERR_UNDERFLOW; break; }
+            if (nstep >= (unsigned)a.max_steps) status = SBM_ERR_MAXSTEPS;
+            else if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) status = SBM_ERR_UNDERFLOW;
+        }
+        const bool go = stepping && status == SBM_OK;
+        const double hs = go ? h : 0.0;             // idle groups take a harmless zero-length step
+
+        sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
+        sbm_dp5_stage<3, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
+        sbm_dp5_stage<4, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
+        sbm_dp5_stage<5, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
+        sbm_dp5_stage<6, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
+        const double sq = sbm_dp5_stage<7, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
+        // embedded error estimate, scaled RMS over the whole augmented state
+        const double err = sqrt(sbm_group_sum<G>(sq) * inv_naug);
+
+        if (go) {
             nstep++;
-
-            sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
-            sbm_dp5_stage<3, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
-            sbm_dp5_stage<4, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
-            sbm_dp5_stage<5, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
-            sbm_dp5_stage<6, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
-            const double sq = sbm_dp5_stage<7, G, C, SENS, KSM, BLOCK>(K, x, t, h, p, cid, gmask, leader, rtol, atol);
             nrhs += 6;
-            // embedded error estimate, scaled RMS over the whole augmented state
-            const double err = sqrt(sbm_group_sum<G>(sq, gmask) * inv_naug);
-
             if (err <= 1.0) {
                 // accept; PI controller (DOPRI5: beta = 0.04, safe = 0.9, fac in [0.2, 10])
                 const float ferr = fmaxf((float)err, 1e-30f);
@@ -374,15 +388,13 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
                     h = h / (double)fminf(5.0f, __powf(ferr, 0.2f - 0.04f * 0.75f) / 0.9f);
                 } else {
                     h *= 0.1;                            // NaN/Inf in the trial state: retreat hard
-                    if (h < 1e-300) { status = SBM_ERR_NONFINITE; break; }
+                    if (h < 1e-300) status = SBM_ERR_NONFINITE;
                 }
             }
         }
-        if (status != SBM_OK) poison = true;
-        sbm_emit_rows<G, C, SENS>(a, b, kt, x, cid, pcol, pscale, poison);
     }
 
-    if (lig == 0) {
+    if (active && lig == 0) {
         a.status[traj] = status;
         atomicAdd(a.counters + SBM_CNT_STEPS, (unsigned long long)nstep);
         atomicAdd(a.counters + SBM_CNT_REJECT, (unsigned long long)nrej);
@@ -452,7 +464,7 @@ __device__ __forceinline__ bool sbm_lu_factor(double (&A)[SBM_N * SBM_N], int (&
             }
         }
         if (!(best > 0.0)) ok = false;
-        const double inv = 1.0 / A[k * N + k];
+        const double inv = sbm_rcp(A[k * N + k]);
 #pragma unroll
         for (int i = k + 1; i < N; ++i) {
             const double l = A[i * N + k] * inv;
@@ -643,7 +655,7 @@ __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 const double sk = atol + rtol * fmax(fabs(y[0][i]), fabs(yn[0][i]));
-                const double q = k6[i] / sk;
+                const double q = k6[i] * sbm_rcp(sk);
                 sq = fma(q, q, sq);
             }
             const double err = sqrt(sq / N);

@@ -380,7 +380,8 @@ class _CudaPrinter(C99CodePrinter):
     """C printer that expands small integer powers into multiplies and reciprocals."""
 
     def _print_sbm_rcp(self, expr):
-        return '(1.0/(%s))' % self._print(expr.args[0])
+        # branch-free reciprocal defined in csrc/sbm_device_math.h (MUFU seed + Newton steps)
+        return 'sbm_rcp(%s)' % self._print(expr.args[0])
 
     def _print_sbm_exp(self, expr):
         return 'exp(%s)' % self._print(expr.args[0])

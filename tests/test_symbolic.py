@@ -99,7 +99,7 @@ def test_cuda_emitter_structure_and_flop_model():
     for fn in ('sbm_f', 'sbm_fJG', 'sbm_col', 'sbm_jac_dense', 'sbm_dfdt'):
         assert 'void %s(' % fn in cs.source
     # one reciprocal per distinct denominator: 10 Michaelis-Menten terms + Ki + Hill denominator + 1/MAPK_PP
-    assert cs.source.split('void sbm_fJG')[1].split('void sbm_col')[0].count('1.0/') == 13
+    assert cs.source.split('void sbm_fJG')[1].split('void sbm_col')[0].count('sbm_rcp(') == 13
     # algorithmic cost of one augmented RHS = f,J,G once + 22 x (2 flops per Jacobian non-zero) + 44 adds
     assert cs.flops_col == 2 * 26
     assert cs.flops_sens_rhs == cs.flops_fJG + 22 * cs.flops_col + 44
