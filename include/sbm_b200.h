@@ -62,7 +62,7 @@ typedef struct sbm_model_desc_t {
     int         group_lanes;     /* lanes per trajectory for the sensitivity kernel, 0 = auto */
     int         cols_per_lane;   /* columns per lane, 0 = auto                          */
     int         block_threads;   /* CTA size of the sensitivity kernel, 0 = auto        */
-    int         stage_smem;      /* Runge-Kutta stage vectors: 0 registers, 1 shared memory, -1 auto */
+    int         stage_smem;      /* reserved (stage vectors always live in shared memory); pass -1   */
     const char* arch;            /* NULL -> "sm_100a"                                   */
     const char* cache_dir;       /* NULL -> no on-disk cubin cache                      */
 } sbm_model_desc_t;

@@ -14,8 +14,9 @@
 //     lane l of the group owns columns l, l+G, ... (C slots); column 0 is the state y itself.
 //     Column dynamics are independent given y:  dS_j/dt = J(y) S_j + df/dp_j, so a stage needs one
 //     broadcast of the stage value of y (shuffles from the group leader) and nothing else.
-//   * every stage vector lives in registers (8*C*N doubles per lane); nothing but the final
-//     observable rows ever goes to HBM - full trajectories never exist.
+//   * the state x of a lane's columns lives in registers, the six Runge-Kutta stage vectors in shared
+//     memory (thread-minor, conflict-free); nothing but the final observable rows ever goes to HBM -
+//     full trajectories never exist.
 //   * all lanes of a group share t, h and the accept/reject decision (error norm by xor-shuffle
 //     butterfly), so there is no divergence inside a group; groups in one warp may diverge.
 //   * output: the integrator steps exactly onto each snapped measurement time (no dense output) and
@@ -112,115 +113,53 @@ __device__ __forceinline__ void sbm_emit_rows(const SbmSolveArgs& a, const long 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage-vector storage.  KSM = 0: the six k-vectors of this lane's columns live in registers.
-// KSM = 1: they live in dynamic shared memory, element-major / thread-minor (stride = CTA size) so a
-// warp's accesses are consecutive doubles - conflict-free LDS.64/STS.64.  Only x (and one transient
-// column of the stage input) stay in registers, which is what lets a lane own C > 1 columns of a
-// large system: the model's primal part (f, J, G) is then evaluated once per lane for C columns and
-// once per warp instruction for 32/G trajectories.
+// Stage-vector storage: the six Runge-Kutta k-vectors of this lane's columns live in dynamic shared
+// memory, element-major / thread-minor (stride = CTA size), so a warp's accesses are consecutive
+// doubles - conflict-free LDS.64/STS.64.  Only x (and one transient column of the stage input) stay in
+// registers, which is what lets a lane own C > 1 columns of a large system: the model's primal part
+// (f, J, G) is then evaluated once per lane for C columns and once per warp instruction for 32/G
+// trajectories.  Slots are addressed at run time, which lets ONE copy of the stage code serve all
+// stages (the model code is large; seven inlined copies thrash the instruction cache - measured).
 // ---------------------------------------------------------------------------------------------
-template <int C, int KSM, int BLOCK>
+template <int C, int BLOCK>
 struct SbmStages {
-    double r[KSM ? 1 : 6][KSM ? 1 : C][KSM ? 1 : SBM_N];
     double* s;
-    template <int V>
-    __device__ __forceinline__ double get(const int c, const int i) const
+    __device__ __forceinline__ double get(const int v, const int c, const int i) const
     {
-        if (KSM) return s[((V * C + c) * SBM_N + i) * BLOCK];
-        return r[KSM ? 0 : V][KSM ? 0 : c][KSM ? 0 : i];
+        return s[((v * C + c) * SBM_N + i) * BLOCK];
     }
-    template <int V>
-    __device__ __forceinline__ void set(const int c, const int i, const double v)
+    __device__ __forceinline__ void set(const int v, const int c, const int i, const double val)
     {
-        if (KSM) s[((V * C + c) * SBM_N + i) * BLOCK] = v;
-        else r[KSM ? 0 : V][KSM ? 0 : c][KSM ? 0 : i] = v;
+        s[((v * C + c) * SBM_N + i) * BLOCK] = val;
     }
 };
 
-// stage input of column c for stage S (2..7):  x + h * sum_j a_Sj k_j   (slots: k1..k6 = 0..5)
-template <int S, int C, int KSM, int BLOCK>
-__device__ __forceinline__ double sbm_stage_in(const SbmStages<C, KSM, BLOCK>& K, const double xv,
-                                               const double h, const int c, const int i)
-{
-    if (S == 2) return fma(h * DP_A21, K.template get<0>(c, i), xv);
-    if (S == 3) return fma(h * DP_A32, K.template get<1>(c, i), fma(h * DP_A31, K.template get<0>(c, i), xv));
-    if (S == 4) return fma(h * DP_A43, K.template get<2>(c, i), fma(h * DP_A42, K.template get<1>(c, i),
-                       fma(h * DP_A41, K.template get<0>(c, i), xv)));
-    if (S == 5) return fma(h * DP_A54, K.template get<3>(c, i), fma(h * DP_A53, K.template get<2>(c, i),
-                       fma(h * DP_A52, K.template get<1>(c, i), fma(h * DP_A51, K.template get<0>(c, i), xv))));
-    if (S == 6) return fma(h * DP_A65, K.template get<4>(c, i), fma(h * DP_A64, K.template get<3>(c, i),
-                       fma(h * DP_A63, K.template get<2>(c, i), fma(h * DP_A62, K.template get<1>(c, i),
-                       fma(h * DP_A61, K.template get<0>(c, i), xv)))));
-    // S == 7: the 5th-order solution
-    return fma(h * DP_A76, K.template get<5>(c, i), fma(h * DP_A75, K.template get<4>(c, i),
-           fma(h * DP_A74, K.template get<3>(c, i), fma(h * DP_A73, K.template get<2>(c, i),
-           fma(h * DP_A71, K.template get<0>(c, i), xv)))));
-}
-
-// One stage: build the stage input column by column (transient, N doubles), evaluate the model's primal
-// part once for the group's state column, write k_S.  Stage 7 stores k7 into the k2 slot (k2 is dead by
-// then) and returns this lane's share of the squared scaled error.
-template <int S, int G, int C, int SENS, int KSM, int BLOCK>
-__device__ __forceinline__ double sbm_dp5_stage(SbmStages<C, KSM, BLOCK>& K, const double (&x)[C][SBM_N],
-                                                const double t, const double h, const double* __restrict__ p,
-                                                const int (&cid)[C], const int leader,
-                                                const double rtol, const double atol)
-{
-    constexpr int N = SBM_N;
-    constexpr int VOUT = (S == 7) ? 1 : S - 1;          // slot receiving k_S
-    const double cs = (S == 2) ? DP_C2 : (S == 3) ? DP_C3 : (S == 4) ? DP_C4 : (S == 5) ? DP_C5 : 1.0;
-    double w[N], Y[N], out[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) w[i] = sbm_stage_in<S, C, KSM, BLOCK>(K, x[0][i], h, 0, i);
-#pragma unroll
-    for (int i = 0; i < N; ++i) Y[i] = (G == 1) ? w[i] : __shfl_sync(0xffffffffu, w[i], leader);
-    double sq = 0.0;
-    if (!SENS) {
-        sbm_f(t + cs * h, Y, p, out);
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            if (S == 7) {
-                const double er = h * fma(DP_E7, out[i], fma(DP_E6, K.template get<5>(0, i), fma(DP_E5, K.template get<4>(0, i),
-                                  fma(DP_E4, K.template get<3>(0, i), fma(DP_E3, K.template get<2>(0, i), DP_E1 * K.template get<0>(0, i))))));
-                const double q = er * sbm_rcp(atol + rtol * fmax(fabs(x[0][i]), fabs(w[i])));
-                sq = fma(q, q, sq);
-            }
-            K.template set<VOUT>(0, i, out[i]);
-        }
-        return sq;
-    }
-    double f[N], Jv[SBM_NJ], Gv[SBM_NG];
-    sbm_fJG(t + cs * h, Y, p, f, Jv, Gv);
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        if (c > 0) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) w[i] = sbm_stage_in<S, C, KSM, BLOCK>(K, x[c][i], h, c, i);
-        }
-        sbm_col(f, Jv, Gv, w, cid[c], out);
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            if (S == 7) {
-                const double er = h * fma(DP_E7, out[i], fma(DP_E6, K.template get<5>(c, i), fma(DP_E5, K.template get<4>(c, i),
-                                  fma(DP_E4, K.template get<3>(c, i), fma(DP_E3, K.template get<2>(c, i), DP_E1 * K.template get<0>(c, i))))));
-                const double q = er * sbm_rcp(atol + rtol * fmax(fabs(x[c][i]), fabs(w[i])));
-                sq = fma(q, q, sq);
-            }
-            K.template set<VOUT>(c, i, out[i]);
-        }
-    }
-    return sq;
-}
+// Butcher tableau by stage id.  Stage ids 0 and 1 are the start-up evaluations (k1 = F(x0) and the
+// explicit-Euler probe of Hairer's initial-step rule); 2..6 are the Dormand-Prince stages and 7 is the
+// 5th-order solution whose derivative is both the FSAL k1 of the next step and the 7th error stage.
+__constant__ double sbm_dp_a[8][6] = {
+    {0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {1.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {DP_A21, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {DP_A31, DP_A32, 0.0, 0.0, 0.0, 0.0},
+    {DP_A41, DP_A42, DP_A43, 0.0, 0.0, 0.0},
+    {DP_A51, DP_A52, DP_A53, DP_A54, 0.0, 0.0},
+    {DP_A61, DP_A62, DP_A63, DP_A64, DP_A65, 0.0},
+    {DP_A71, 0.0, DP_A73, DP_A74, DP_A75, DP_A76}};
+__constant__ double sbm_dp_c[8] = {0.0, 1.0, DP_C2, DP_C3, DP_C4, DP_C5, 1.0, 1.0};
+__constant__ int sbm_dp_nt[8] = {0, 1, 1, 2, 3, 4, 5, 6};      // number of k-vectors entering the stage input
+__constant__ int sbm_dp_out[8] = {0, 1, 1, 2, 3, 4, 5, 1};     // logical k-slot receiving the stage derivative
 
 // ---------------------------------------------------------------------------------------------
 // Adaptive Dormand-Prince 5(4), FSAL, PI step controller (Hairer's DOPRI5 constants)
 //
-// Control flow is WARP-UNIFORM: every lane of a warp runs the same flat loop until all groups of the
-// warp are done; a finished (or out-of-range) group keeps executing with its writes predicated off.
-// That costs nothing under SIMT (the warp would wait for its slowest group anyway) and lets every
-// shuffle use the constant full mask - no per-shuffle convergence barriers, one basic block per stage.
+// Control flow is WARP-UNIFORM: every lane of a warp runs the same flat loop - one Runge-Kutta stage
+// per iteration - until all groups of the warp are done; a finished (or out-of-range) group keeps
+// executing with zero step and its writes predicated off.  That costs nothing under SIMT (the warp
+// would wait for its slowest group anyway), lets every shuffle use the constant full mask, and keeps
+// a single copy of the generated model code in the loop body.
 // ---------------------------------------------------------------------------------------------
-template <int G, int C, int SENS, int KSM, int BLOCK>
+template <int G, int C, int SENS, int BLOCK>
 __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
 {
     constexpr int N = SBM_N;
@@ -229,7 +168,7 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
     static_assert(G * C >= NCOL, "group too small for the augmented system");
     constexpr int GPB = BLOCK / G;                 // groups (trajectories) per block
     __shared__ double sp[GPB * SBM_NPP];
-    extern __shared__ double sbm_dyn[];            // KSM: [6][C][N][BLOCK] stage vectors
+    extern __shared__ double sbm_dyn[];            // [6][C][N][BLOCK] stage vectors
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -275,122 +214,191 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
     bool done = !active || kt >= kt1;
     double tk = done ? 0.0 : a.tout[kt];
 
-    SbmStages<C, KSM, BLOCK> K;
+    SbmStages<C, BLOCK> K;
     K.s = sbm_dyn + tid;
+    // slots 0/1 swap roles on every accepted step (FSAL: k7 becomes the next k1 without a copy)
+    int s0 = 0, s1 = 1;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i) { K.set(0, c, i, 0.0); K.set(1, c, i, 0.0); }
+
     unsigned nstep = 0, nrej = 0, nrhs = 0;
     int status = SBM_OK;
-    double t = 0.0;
-
-    // k1 = F(t0, x0): run "stage 2" with h = 0 into slot 1, then move it to slot 0
-    double h;
-    {
-        // with h = 0 the stage input is x itself (slot 0 must hold finite numbers: 0 * NaN = NaN)
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int i = 0; i < N; ++i) K.template set<0>(c, i, 0.0);
-        sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, 0.0, p, cid, leader, rtol, atol);
-        double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double kv = K.template get<1>(c, i);
-                K.template set<0>(c, i, kv);
-                const double isk = sbm_rcp(atol + rtol * fabs(x[c][i]));
-                d0 = fma(x[c][i] * isk, x[c][i] * isk, d0);
-                d1 = fma(kv * isk, kv * isk, d1);
-            }
-        nrhs++;
-        // ---- initial step size (Hairer, Norsett, Wanner II.4) ----
-        d0 = sqrt(sbm_group_sum<G>(d0) * inv_naug);
-        d1 = sqrt(sbm_group_sum<G>(d1) * inv_naug);
-        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        h0 = fmin(h0, tend);
-        // explicit Euler probe: stage 2 with step h0/A21 evaluates F(x + h0*k1) into slot 1
-        sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, h0 / DP_A21, p, cid, leader, rtol, atol);
-        nrhs++;
-        double d2 = 0.0;
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double q = (K.template get<1>(c, i) - K.template get<0>(c, i)) * sbm_rcp(atol + rtol * fabs(x[c][i]));
-                d2 = fma(q, q, d2);
-            }
-        d2 = sqrt(sbm_group_sum<G>(d2) * inv_naug) / h0;
-        const double dm = fmax(d1, d2);
-        const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
-        h = fmin(fmin(100.0 * h0, h1), tend);
-        if (a.h0 > 0.0) h = fmin(a.h0, tend);
-    }
-
+    double t = 0.0, h = 0.0, hprop = 0.0, h0 = 0.0, d1 = 0.0;
     float facold = 1e-4f;
-    bool last_rejected = false;
+    bool last_rejected = false, clipped = false, go = false;
+    int stage = 0;                                  // warp-uniform
 
     while (__any_sync(FULL, !done)) {
-        // ---- arrived at an output time (or failed: flush the remaining rows as NaN) ----
-        if (!done && (t >= tk || status != SBM_OK)) {
-            sbm_emit_rows<G, C, SENS>(a, b, kt, x, cid, pcol, pscale, status != SBM_OK);
-            kt++;
-            done = kt >= kt1;
-            if (!done) tk = a.tout[kt];
+        if (stage == 2) {
+            // ---- step start: arrived at an output time (or failed: flush the remaining rows as NaN) ----
+            if (!done && (t >= tk || status != SBM_OK)) {
+                sbm_emit_rows<G, C, SENS>(a, b, kt, x, cid, pcol, pscale, status != SBM_OK);
+                kt++;
+                done = kt >= kt1;
+                if (!done) tk = a.tout[kt];
+            }
+            const bool stepping = !done && status == SBM_OK && t < tk;
+            // clip onto the output time; remember the unclipped proposal
+            hprop = h;
+            clipped = false;
+            if (stepping) {
+                if (t + 1.01 * h >= tk) { h = tk - t; clipped = true; }
+                if (nstep >= (unsigned)a.max_steps) status = SBM_ERR_MAXSTEPS;
+                else if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) status = SBM_ERR_UNDERFLOW;
+            }
+            go = stepping && status == SBM_OK;
         }
-        const bool stepping = !done && status == SBM_OK && t < tk;
-        // clip onto the output time; remember the unclipped proposal
-        const double hprop = h;
-        bool clipped = false;
-        if (stepping) {
-            if (t + 1.01 * h >= tk) { h = tk - t; clipped = true; }
-            if (nstep >= (unsigned)a.max_steps) status = SBM_ERR_MAXSTEPS;
-            else if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) status = SBM_ERR_UNDERFLOW;
-        }
-        const bool go = stepping && status == SBM_OK;
-        const double hs = go ? h : 0.0;             // idle groups take a harmless zero-length step
+        // idle groups take a harmless zero-length step
+        const double hs = (stage == 0) ? 0.0 : (stage == 1) ? h0 : (go ? h : 0.0);
 
-        sbm_dp5_stage<2, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
-        sbm_dp5_stage<3, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
-        sbm_dp5_stage<4, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
-        sbm_dp5_stage<5, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
-        sbm_dp5_stage<6, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
-        const double sq = sbm_dp5_stage<7, G, C, SENS, KSM, BLOCK>(K, x, t, hs, p, cid, leader, rtol, atol);
-        // embedded error estimate, scaled RMS over the whole augmented state
-        const double err = sqrt(sbm_group_sum<G>(sq) * inv_naug);
-
-        if (go) {
-            nstep++;
-            nrhs += 6;
-            if (err <= 1.0) {
-                // accept; PI controller (DOPRI5: beta = 0.04, safe = 0.9, fac in [0.2, 10])
-                const float ferr = fmaxf((float)err, 1e-30f);
-                float fac = __powf(ferr, 0.2f - 0.04f * 0.75f) / __powf(facold, 0.04f);
-                fac = fmaxf(0.1f, fminf(5.0f, fac / 0.9f));
-                facold = fmaxf(ferr, 1e-4f);
-                t = clipped ? tk : t + h;
-                // x <- 5th-order solution (recomputed: the stage input is transient), k1 <- k7 (FSAL)
+        // ================= one stage: input, model, derivative, (error) =================
+        const int nt = sbm_dp_nt[stage];
+        const int vout_l = sbm_dp_out[stage];
+        const int vout = (vout_l == 0) ? s0 : (vout_l == 1) ? s1 : vout_l;
+        const double ts = t + sbm_dp_c[stage] * hs;
+        double cf[6];
 #pragma unroll
-                for (int c = 0; c < C; ++c)
+        for (int j = 0; j < 6; ++j) cf[j] = hs * sbm_dp_a[stage][j];
+
+        double w[N], Y[N], out[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double acc = x[0][i];
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                if (j < nt) acc = fma(cf[j], K.get((j == 0) ? s0 : (j == 1) ? s1 : j, 0, i), acc);
+            w[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) Y[i] = (G == 1) ? w[i] : __shfl_sync(FULL, w[i], leader);
+
+        double sq = 0.0;
+        if (!SENS) {
+            sbm_f(ts, Y, p, out);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (stage == 7) {
+                    const double er = hs * fma(DP_E7, out[i], fma(DP_E6, K.get(5, 0, i), fma(DP_E5, K.get(4, 0, i),
+                                      fma(DP_E4, K.get(3, 0, i), fma(DP_E3, K.get(2, 0, i), DP_E1 * K.get(s0, 0, i))))));
+                    const double q = er * sbm_rcp(atol + rtol * fmax(fabs(x[0][i]), fabs(w[i])));
+                    sq = fma(q, q, sq);
+                }
+                K.set(vout, 0, i, out[i]);
+            }
+        } else {
+            double f[N], Jv[SBM_NJ], Gv[SBM_NG];
+            sbm_fJG(ts, Y, p, f, Jv, Gv);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                if (c > 0) {
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
-                        x[c][i] = sbm_stage_in<7, C, KSM, BLOCK>(K, x[c][i], h, c, i);
-                        K.template set<0>(c, i, K.template get<1>(c, i));
+                        double acc = x[c][i];
+#pragma unroll
+                        for (int j = 0; j < 6; ++j)
+                            if (j < nt) acc = fma(cf[j], K.get((j == 0) ? s0 : (j == 1) ? s1 : j, c, i), acc);
+                        w[i] = acc;
                     }
-                double hnew = h / (double)fac;
-                if (last_rejected) hnew = fmin(hnew, h);
-                if (clipped) hnew = fmax(hnew, hprop);   // a clipped step must not shrink the cruise step
-                h = hnew;
-                last_rejected = false;
-            } else {
-                nrej++;
-                last_rejected = true;
-                if (err == err && err < 1e300) {
-                    const float ferr = (float)fmin(err, 1e30);
-                    h = h / (double)fminf(5.0f, __powf(ferr, 0.2f - 0.04f * 0.75f) / 0.9f);
-                } else {
-                    h *= 0.1;                            // NaN/Inf in the trial state: retreat hard
-                    if (h < 1e-300) status = SBM_ERR_NONFINITE;
+                }
+                sbm_col(f, Jv, Gv, w, cid[c], out);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    if (stage == 7) {
+                        const double er = hs * fma(DP_E7, out[i], fma(DP_E6, K.get(5, c, i), fma(DP_E5, K.get(4, c, i),
+                                          fma(DP_E4, K.get(3, c, i), fma(DP_E3, K.get(2, c, i), DP_E1 * K.get(s0, c, i))))));
+                        const double q = er * sbm_rcp(atol + rtol * fmax(fabs(x[c][i]), fabs(w[i])));
+                        sq = fma(q, q, sq);
+                    }
+                    K.set(vout, c, i, out[i]);
                 }
             }
+        }
+
+        // ================= what the stage was for =================
+        if (stage == 0) {
+            // k1 = F(t0, x0) is in slot s0.  Initial step size (Hairer, Norsett, Wanner II.4), part 1.
+            double d0 = 0.0;
+            d1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double isk = sbm_rcp(atol + rtol * fabs(x[c][i]));
+                    const double kv = K.get(s0, c, i);
+                    d0 = fma(x[c][i] * isk, x[c][i] * isk, d0);
+                    d1 = fma(kv * isk, kv * isk, d1);
+                }
+            d0 = sqrt(sbm_group_sum<G>(d0) * inv_naug);
+            d1 = sqrt(sbm_group_sum<G>(d1) * inv_naug);
+            h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            h0 = fmin(h0, tend);
+            nrhs++;
+            stage = 1;
+        } else if (stage == 1) {
+            // slot s1 holds F(x0 + h0*k1): second-derivative estimate, part 2 of the initial step rule
+            double d2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double q = (K.get(s1, c, i) - K.get(s0, c, i)) * sbm_rcp(atol + rtol * fabs(x[c][i]));
+                    d2 = fma(q, q, d2);
+                }
+            d2 = sqrt(sbm_group_sum<G>(d2) * inv_naug) / h0;
+            const double dm = fmax(d1, d2);
+            const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
+            h = fmin(fmin(100.0 * h0, h1), tend);
+            if (a.h0 > 0.0) h = fmin(a.h0, tend);
+            nrhs++;
+            stage = 2;
+        } else if (stage < 7) {
+            stage++;
+        } else {
+            // ---- end of step: embedded error estimate, scaled RMS over the whole augmented state ----
+            const double err = sqrt(sbm_group_sum<G>(sq) * inv_naug);
+            if (go) {
+                nstep++;
+                nrhs += 6;
+                if (err <= 1.0) {
+                    // accept; PI controller (DOPRI5: beta = 0.04, safe = 0.9, fac in [0.2, 10])
+                    const float ferr = fmaxf((float)err, 1e-30f);
+                    float fac = __powf(ferr, 0.2f - 0.04f * 0.75f) / __powf(facold, 0.04f);
+                    fac = fmaxf(0.1f, fminf(5.0f, fac / 0.9f));
+                    facold = fmaxf(ferr, 1e-4f);
+                    t = clipped ? tk : t + h;
+                    // x <- 5th-order solution (recomputed: the stage input is transient)
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            double acc = x[c][i];
+#pragma unroll
+                            for (int j = 0; j < 6; ++j)
+                                if (j != 1) acc = fma(cf[j], K.get((j == 0) ? s0 : j, c, i), acc);
+                            x[c][i] = acc;
+                        }
+                    // FSAL: k7 (slot s1) is the next step's k1
+                    const int tmp = s0; s0 = s1; s1 = tmp;
+                    double hnew = h / (double)fac;
+                    if (last_rejected) hnew = fmin(hnew, h);
+                    if (clipped) hnew = fmax(hnew, hprop);   // a clipped step must not shrink the cruise step
+                    h = hnew;
+                    last_rejected = false;
+                } else {
+                    nrej++;
+                    last_rejected = true;
+                    if (err == err && err < 1e300) {
+                        const float ferr = (float)fmin(err, 1e30);
+                        h = h / (double)fminf(5.0f, __powf(ferr, 0.2f - 0.04f * 0.75f) / 0.9f);
+                    } else {
+                        h *= 0.1;                            // NaN/Inf in the trial state: retreat hard
+                        if (h < 1e-300) status = SBM_ERR_NONFINITE;
+                    }
+                }
+            }
+            stage = 2;
         }
     }
 
@@ -707,9 +715,9 @@ __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
 // ---------------------------------------------------------------------------------------------
 // kernel entry points are instantiated by the host (sbm_api.cu appends SBM_DEFINE_* lines)
 // ---------------------------------------------------------------------------------------------
-#define SBM_DEFINE_DP5(NAME, G, C, SENS, KSM, BLOCK)                                        \
+#define SBM_DEFINE_DP5(NAME, G, C, SENS, BLOCK)                                             \
     extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \
-    { sbm_dp5_impl<G, C, SENS, KSM, BLOCK>(a); }
+    { sbm_dp5_impl<G, C, SENS, BLOCK>(a); }
 
 #define SBM_DEFINE_RODAS4(NAME, BLOCK)                                                      \
     extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \

@@ -133,8 +133,8 @@ struct KernelSlot {
 struct sbm_model {
     sbm_model_desc_t desc{};
     std::string arch;
-    int G = 1, C = 1, KSM = 0, block = 128, block_plain = 128;
-    int dyn_smem = 0;
+    int G = 1, C = 1, block = 128, block_plain = 128;
+    int dyn_smem = 0, dyn_smem_plain = 0;
     std::string source;          // full NVRTC translation unit (kept for diagnostics)
     std::string log;
     std::vector<char> cubin;
@@ -152,20 +152,27 @@ static unsigned long long fnv1a(const std::string& s, unsigned long long seed)
     return h;
 }
 
-// Work decomposition of the sensitivity kernel (see kernels/sbm_ode_kernels.cuh):
-//   registers mode: 8 stage vectors of C*N doubles per lane must fit the register file -> C*N <= 12;
-//   shared mode   : only x (C*N doubles) in registers, 6 stage vectors in shared memory -> C*N <= 24,
-//                   CTA = one warp so that 6 CTAs (6*C*N*32*8 B <= 36.9 KB each) share an SM.
-// A smaller group evaluates the model's primal part for more trajectories per warp instruction, so the
-// shared mode wins as soon as the register mode would need (nearly) a whole warp per trajectory.
-static void pick_config(int N, int ncol, int& G, int& C, int& KSM, int& block)
+// Work decomposition of the sensitivity kernel (see kernels/sbm_ode_kernels.cuh): a group of G lanes per
+// trajectory, C columns of the augmented system per lane.  x (C*N doubles) stays in registers, the six
+// stage vectors in shared memory (6*C*N*8 B per lane).  A smaller group evaluates the model's primal part
+// for more trajectories per warp instruction, so take the smallest G whose per-lane state fits: C*N <= 24.
+static void pick_config(int N, int ncol, int& G, int& C)
 {
-    int gr = 32, cr = (ncol + 31) / 32, gs = 32, cs = (ncol + 31) / 32;
-    bool have_r = false, have_s = false;
-    for (int g = 1; g <= 32 && !have_r; g *= 2) { int c = (ncol + g - 1) / g; if (c * N <= 12) { gr = g; cr = c; have_r = true; } }
-    for (int g = 1; g <= 32 && !have_s; g *= 2) { int c = (ncol + g - 1) / g; if (c * N <= 24) { gs = g; cs = c; have_s = true; } }
-    if (have_r && !(have_s && gr >= 16 && gs * 2 <= gr)) { G = gr; C = cr; KSM = 0; block = 128; return; }
-    G = gs; C = cs; KSM = 1; block = 32;
+    for (int g = 1; g <= 32; g *= 2) {
+        int c = (ncol + g - 1) / g;
+        if (c * N <= 24) { G = g; C = c; return; }
+    }
+    G = 32;
+    C = (ncol + 31) / 32;
+}
+
+// CTA size: as large as possible (<= 128) while the stage vectors of one CTA stay below 48 KB, so that
+// several CTAs share an SM and no opt-in is needed; one warp per CTA for the largest systems.
+static int pick_block(int per_thread_bytes)
+{
+    for (int blk = 128; blk >= 64; blk /= 2)
+        if ((long long)per_thread_bytes * blk <= 48 * 1024) return blk;
+    return 32;
 }
 
 extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* desc, sbm_model** out)
@@ -177,31 +184,29 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     sbm_model* m = new sbm_model();
     m->desc = *desc;
     m->arch = desc->arch ? desc->arch : "sm_100a";
-    pick_config(desc->n_vars, desc->n_free + 1, m->G, m->C, m->KSM, m->block);
+    pick_config(desc->n_vars, desc->n_free + 1, m->G, m->C);
     if (desc->group_lanes > 0 && desc->cols_per_lane > 0) {
         m->G = desc->group_lanes;
         m->C = desc->cols_per_lane;
-        m->KSM = desc->stage_smem > 0 ? 1 : 0;
-        m->block = m->KSM ? 32 : 128;
-    } else if (desc->stage_smem >= 0 && desc->stage_smem != m->KSM) {
-        delete m;
-        return fail(SBM_E_INVALID, "stage_smem override needs explicit group_lanes and cols_per_lane");
     }
+    m->block = pick_block(6 * m->C * desc->n_vars * 8);
+    m->block_plain = pick_block(6 * desc->n_vars * 8);
     if (desc->block_threads > 0) m->block = desc->block_threads;
     if (m->G < 1 || m->G > 32 || (m->G & (m->G - 1)) || m->G * m->C < desc->n_free + 1 || (m->block % 32) || m->block > 1024) {
         delete m;
         return fail(SBM_E_INVALID, "invalid group_lanes / cols_per_lane / block_threads");
     }
-    m->dyn_smem = m->KSM ? 6 * m->C * desc->n_vars * m->block * 8 : 0;
-    if (m->dyn_smem > 227 * 1024) {
+    m->dyn_smem = 6 * m->C * desc->n_vars * m->block * 8;
+    m->dyn_smem_plain = 6 * desc->n_vars * m->block_plain * 8;
+    if (m->dyn_smem > 200 * 1024 || m->dyn_smem_plain > 200 * 1024) {
         delete m;
         return fail(SBM_E_INVALID, "stage vectors do not fit in shared memory for this group shape");
     }
 
     std::ostringstream src;
     src << sbm_embedded_args_header << "\n" << model_src << "\n" << sbm_embedded_kernels << "\n";
-    src << "SBM_DEFINE_DP5(sbm_dp5_plain, 1, 1, 0, 0, " << m->block_plain << ")\n";
-    src << "SBM_DEFINE_DP5(sbm_dp5_sens, " << m->G << ", " << m->C << ", 1, " << m->KSM << ", " << m->block << ")\n";
+    src << "SBM_DEFINE_DP5(sbm_dp5_plain, 1, 1, 0, " << m->block_plain << ")\n";
+    src << "SBM_DEFINE_DP5(sbm_dp5_sens, " << m->G << ", " << m->C << ", 1, " << m->block << ")\n";
     src << "SBM_DEFINE_RODAS4(sbm_rodas4_plain, " << m->block_plain << ")\n";
     m->source = src.str();
 
@@ -282,6 +287,8 @@ static int ensure_loaded(sbm_model* m)
     if ((rc = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return rc;
     if (m->dyn_smem > 48 * 1024)
         DRV(driver().cuFuncSetAttribute_(m->dp5_sens.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
+    if (m->dyn_smem_plain > 48 * 1024)
+        DRV(driver().cuFuncSetAttribute_(m->dp5_plain.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_plain));
     m->loaded = true;
     return 0;
 }
@@ -295,7 +302,7 @@ extern "C" int sbm_model_info(sbm_model* m, sbm_model_info_t* o)
     }
     o->n_vars = m->desc.n_vars; o->n_params = m->desc.n_params; o->n_free = m->desc.n_free;
     o->group_lanes = m->G; o->cols_per_lane = m->C; o->block_threads = m->block;
-    o->stage_smem = m->KSM; o->dyn_smem_bytes = m->dyn_smem;
+    o->stage_smem = 1; o->dyn_smem_bytes = m->dyn_smem;
     o->regs_dp5_plain = m->dp5_plain.regs; o->regs_dp5_sens = m->dp5_sens.regs; o->regs_rodas4 = m->rodas4.regs;
     o->local_dp5_plain = m->dp5_plain.local; o->local_dp5_sens = m->dp5_sens.local; o->local_rodas4 = m->rodas4.local;
     o->smem_dp5_plain = m->dp5_plain.smem; o->smem_dp5_sens = m->dp5_sens.smem; o->smem_rodas4 = m->rodas4.smem;
@@ -433,7 +440,7 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
     int block = m->block_plain, dyn = 0;
     if (o->solver == SBM_SOLVER_RODAS4) { ks = &m->rodas4; threads = ntraj; }
     else if (jac) { ks = &m->dp5_sens; threads = ntraj * m->G; block = m->block; dyn = m->dyn_smem; }
-    else { ks = &m->dp5_plain; threads = ntraj; }
+    else { ks = &m->dp5_plain; threads = ntraj; dyn = m->dyn_smem_plain; }
     const long long blocks = (threads + block - 1) / block;
     if (blocks > 2147483647ll) return fail(SBM_E_INVALID, "batch too large for one launch");
     void* params[] = {&a};
