@@ -262,31 +262,27 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
 #pragma unroll
         for (int j = 0; j < 6; ++j) cf[j] = hs * sbm_dp_a[stage][j];
 
+        // stage input: loads are unconditional (every slot always holds finite-or-garbage data that is
+        // simply not selected), so the common path of a stage has no branch at all
         double w[N], Y[N], out[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             double acc = x[0][i];
 #pragma unroll
-            for (int j = 0; j < 6; ++j)
-                if (j < nt) acc = fma(cf[j], K.get((j == 0) ? s0 : (j == 1) ? s1 : j, 0, i), acc);
+            for (int j = 0; j < 6; ++j) {
+                const double kv = K.get((j == 0) ? s0 : (j == 1) ? s1 : j, 0, i);
+                const double nx = fma(cf[j], kv, acc);
+                acc = (j < nt) ? nx : acc;
+            }
             w[i] = acc;
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) Y[i] = (G == 1) ? w[i] : __shfl_sync(FULL, w[i], leader);
 
-        double sq = 0.0;
         if (!SENS) {
             sbm_f(ts, Y, p, out);
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                if (stage == 7) {
-                    const double er = hs * fma(DP_E7, out[i], fma(DP_E6, K.get(5, 0, i), fma(DP_E5, K.get(4, 0, i),
-                                      fma(DP_E4, K.get(3, 0, i), fma(DP_E3, K.get(2, 0, i), DP_E1 * K.get(s0, 0, i))))));
-                    const double q = er * sbm_rcp(atol + rtol * fmax(fabs(x[0][i]), fabs(w[i])));
-                    sq = fma(q, q, sq);
-                }
-                K.set(vout, 0, i, out[i]);
-            }
+            for (int i = 0; i < N; ++i) K.set(vout, 0, i, out[i]);
         } else {
             double f[N], Jv[SBM_NJ], Gv[SBM_NG];
             sbm_fJG(ts, Y, p, f, Jv, Gv);
@@ -297,22 +293,17 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
                     for (int i = 0; i < N; ++i) {
                         double acc = x[c][i];
 #pragma unroll
-                        for (int j = 0; j < 6; ++j)
-                            if (j < nt) acc = fma(cf[j], K.get((j == 0) ? s0 : (j == 1) ? s1 : j, c, i), acc);
+                        for (int j = 0; j < 6; ++j) {
+                            const double kv = K.get((j == 0) ? s0 : (j == 1) ? s1 : j, c, i);
+                            const double nx = fma(cf[j], kv, acc);
+                            acc = (j < nt) ? nx : acc;
+                        }
                         w[i] = acc;
                     }
                 }
                 sbm_col(f, Jv, Gv, w, cid[c], out);
 #pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    if (stage == 7) {
-                        const double er = hs * fma(DP_E7, out[i], fma(DP_E6, K.get(5, c, i), fma(DP_E5, K.get(4, c, i),
-                                          fma(DP_E4, K.get(3, c, i), fma(DP_E3, K.get(2, c, i), DP_E1 * K.get(s0, c, i))))));
-                        const double q = er * sbm_rcp(atol + rtol * fmax(fabs(x[c][i]), fabs(w[i])));
-                        sq = fma(q, q, sq);
-                    }
-                    K.set(vout, c, i, out[i]);
-                }
+                for (int i = 0; i < N; ++i) K.set(vout, c, i, out[i]);
             }
         }
 
@@ -356,7 +347,22 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
         } else if (stage < 7) {
             stage++;
         } else {
-            // ---- end of step: embedded error estimate, scaled RMS over the whole augmented state ----
+            // ---- end of step: 5th-order solution and embedded error estimate in one pass over the stage
+            //      vectors (k7 sits in slot s1), scaled RMS over the whole augmented state ----
+            double xn[C][N];
+            double sq = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double k1v = K.get(s0, c, i), k3v = K.get(2, c, i), k4v = K.get(3, c, i);
+                    const double k5v = K.get(4, c, i), k6v = K.get(5, c, i), k7v = K.get(s1, c, i);
+                    xn[c][i] = fma(cf[5], k6v, fma(cf[4], k5v, fma(cf[3], k4v, fma(cf[2], k3v, fma(cf[0], k1v, x[c][i])))));
+                    const double er = hs * fma(DP_E7, k7v, fma(DP_E6, k6v, fma(DP_E5, k5v, fma(DP_E4, k4v,
+                                      fma(DP_E3, k3v, DP_E1 * k1v)))));
+                    const double q = er * sbm_rcp(atol + rtol * fmax(fabs(x[c][i]), fabs(xn[c][i])));
+                    sq = fma(q, q, sq);
+                }
             const double err = sqrt(sbm_group_sum<G>(sq) * inv_naug);
             if (go) {
                 nstep++;
@@ -368,17 +374,10 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
                     fac = fmaxf(0.1f, fminf(5.0f, fac / 0.9f));
                     facold = fmaxf(ferr, 1e-4f);
                     t = clipped ? tk : t + h;
-                    // x <- 5th-order solution (recomputed: the stage input is transient)
 #pragma unroll
                     for (int c = 0; c < C; ++c)
 #pragma unroll
-                        for (int i = 0; i < N; ++i) {
-                            double acc = x[c][i];
-#pragma unroll
-                            for (int j = 0; j < 6; ++j)
-                                if (j != 1) acc = fma(cf[j], K.get((j == 0) ? s0 : j, c, i), acc);
-                            x[c][i] = acc;
-                        }
+                        for (int i = 0; i < N; ++i) x[c][i] = xn[c][i];
                     // FSAL: k7 (slot s1) is the next step's k1
                     const int tmp = s0; s0 = s1; s1 = tmp;
                     double hnew = h / (double)fac;

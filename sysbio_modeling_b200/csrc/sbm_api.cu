@@ -189,8 +189,10 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
         m->G = desc->group_lanes;
         m->C = desc->cols_per_lane;
     }
-    m->block = pick_block(6 * m->C * desc->n_vars * 8);
-    m->block_plain = pick_block(6 * desc->n_vars * 8);
+    // per-thread shared memory: stage vectors + this thread's share of the group's parameter row
+    const int npp8 = (desc->n_params | 1) * 8;
+    m->block = pick_block(6 * m->C * desc->n_vars * 8 + (npp8 + m->G - 1) / m->G);
+    m->block_plain = pick_block(6 * desc->n_vars * 8 + npp8);
     if (desc->block_threads > 0) m->block = desc->block_threads;
     if (m->G < 1 || m->G > 32 || (m->G & (m->G - 1)) || m->G * m->C < desc->n_free + 1 || (m->block % 32) || m->block > 1024) {
         delete m;
@@ -285,10 +287,8 @@ static int ensure_loaded(sbm_model* m)
     if ((rc = slot_load(m, m->dp5_plain, "sbm_dp5_plain"))) return rc;
     if ((rc = slot_load(m, m->dp5_sens, "sbm_dp5_sens"))) return rc;
     if ((rc = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return rc;
-    if (m->dyn_smem > 48 * 1024)
-        DRV(driver().cuFuncSetAttribute_(m->dp5_sens.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
-    if (m->dyn_smem_plain > 48 * 1024)
-        DRV(driver().cuFuncSetAttribute_(m->dp5_plain.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_plain));
+    DRV(driver().cuFuncSetAttribute_(m->dp5_sens.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
+    DRV(driver().cuFuncSetAttribute_(m->dp5_plain.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_plain));
     m->loaded = true;
     return 0;
 }
