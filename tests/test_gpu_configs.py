@@ -247,3 +247,18 @@ def test_log_loss_and_sf_priors():
     m_p.loc[('~~SF_Prior', '~Lin'), :] = np.array([1.0, 2.0, np.nan])
     res = np.asarray(lf.residuals(sim_p, m_p))
     assert abs(res[-1] - (np.log(5) - 1) / 2.0) < 1e-12
+
+
+def test_device_reciprocal_accuracy(tmp_path):
+    """sbm_rcp (MUFU seed + Newton steps, no slow-path branch) stays within 1 ulp of IEEE division."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'check_device_math')
+    subprocess.run(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-o', exe,
+                    os.path.join(root, 'tests', 'cuda', 'check_device_math.cu')], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    print(out)
+    vals = dict(zip(out.split()[0::2], [float(v) for v in out.split()[1::2]]))
+    assert vals['sbm_rcp_ulp'] <= 1.0
+    assert vals['seed_relerr'] < 1e-5
