@@ -50,12 +50,12 @@ def make_thetas(nominal, B, seed):
     return np.log(nominal)[None, :] + 0.25 * rng.standard_normal((B, len(nominal)))
 
 
-def build_project(tol, data=None, shape=(0, 0, -1)):
+def build_project(tol, data=None, shape=(0, 0, 0)):
     import sysbio_modeling_b200 as sb
     from sysbio_modeling_b200 import model_files
     mod = model_files.module('mapk_kholodenko')
     om = sb.OdeModel.from_model_file(model_files.path('mapk_kholodenko'), model_name='mapk', group_lanes=shape[0],
-                                     cols_per_lane=shape[1], stage_smem=shape[2])
+                                     cols_per_lane=shape[1], sens_layout=shape[2])
     if data is None:
         data = {k: np.ones_like(T_OBS) for k in OBS}
     meas = [sb.TimecourseMeasurement(k, data[k], T_OBS, 0.05 * np.abs(data[k]) + 1e-3) for k in OBS]
@@ -220,7 +220,7 @@ def main():
     ap.add_argument('--tol', type=float, default=1e-10, help='rtol = atol (reference: 1e-10)')
     ap.add_argument('--cpu-sample', type=int, default=0, help='parameter sets in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--shape', default='0,0,-1', help='group_lanes,cols_per_lane,stage_smem of the sensitivity kernel (0,0,-1 = auto)')
+    ap.add_argument('--shape', default='0,0,0', help='group_lanes,cols_per_lane,sens_layout of the sensitivity kernel (0,0,0 = auto; layout 1 = lane-per-column groups, 2 = CTA-transposed)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = max(args.warmup, 1)
@@ -345,6 +345,20 @@ def main():
     peak_tf, peak_ms = _lib.fp64_peak()
     achieved_tf = flops_launch / (solve_ms * 1e-3) / 1e12
 
+    ct = info['sens_layout'] == 2
+    kname = 'sbm_dp5_ct' if ct else 'sbm_dp5_sens'
+    kern_info = {kname + '_ms': solve_ms, 'sbm_loss_kernel_ms': float(np.mean(ms_step)) - solve_ms,
+                 'sens_layout': 'cta-transposed (lane = trajectory, warp = column group)' if ct
+                 else 'lane-per-column warp groups'}
+    if ct:
+        kern_info.update({'warps_per_cta': info['ct_warps'], 'cols_per_warp': info['ct_cols'],
+                          'cols_on_state_warp': info['ct_cols_state'], 'dyn_smem_bytes': info['ct_dyn_smem_bytes'],
+                          'ctas_per_sm': info['ct_ctas_per_sm'], 'regs': info['regs_dp5_ct'],
+                          'local_bytes': info['local_dp5_ct']})
+    else:
+        kern_info.update({'group_lanes': info['group_lanes'], 'cols_per_lane': info['cols_per_lane'],
+                          'block_threads': info['block_threads'], 'dyn_smem_bytes': info['dyn_smem_bytes'],
+                          'regs': info['regs_dp5_sens'], 'local_bytes': info['local_dp5_sens']})
     line = None
     if rank == 0:
         line = {
@@ -355,15 +369,11 @@ def main():
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'calls': n_e2e, 'matches_device_path': same},
             'gpu_launches': 2 * args.steps,
-            'kernels': {'sbm_dp5_sens_ms': solve_ms, 'sbm_loss_kernel_ms': float(np.mean(ms_step)) - solve_ms,
-                        'group_lanes': info['group_lanes'], 'cols_per_lane': info['cols_per_lane'],
-                        'stage_smem': info['stage_smem'], 'block_threads': info['block_threads'],
-                        'dyn_smem_bytes': info['dyn_smem_bytes'],
-                        'regs': info['regs_dp5_sens'], 'local_bytes': info['local_dp5_sens']},
+            'kernels': kern_info,
             'counters_per_step': cnt, 'failed_trajectories': status_bad,
             'roofline': {'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': achieved_tf / peak_tf, 'traffic': None,
-                         'kernel': 'sbm_dp5_sens',
+                         'kernel': kname,
                          'peak_source': 'measured: sbm_fp64_peak DFMA microbenchmark in this run '
                                         '(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)',
                          'algorithmic_flops_per_launch': flops_launch,

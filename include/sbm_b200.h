@@ -62,7 +62,8 @@ typedef struct sbm_model_desc_t {
     int         group_lanes;     /* lanes per trajectory for the sensitivity kernel, 0 = auto */
     int         cols_per_lane;   /* columns per lane, 0 = auto                          */
     int         block_threads;   /* CTA size of the sensitivity kernel, 0 = auto        */
-    int         stage_smem;      /* reserved (stage vectors always live in shared memory); pass -1   */
+    int         sens_layout;     /* sensitivity kernel: <=0 auto, 1 lane-per-column warp groups (sbm_dp5_sens),
+                                    2 CTA-transposed: lane = trajectory, warp = column group (sbm_dp5_ct)  */
     const char* arch;            /* NULL -> "sm_100a"                                   */
     const char* cache_dir;       /* NULL -> no on-disk cubin cache                      */
 } sbm_model_desc_t;
@@ -75,6 +76,10 @@ typedef struct sbm_model_info_t {
     int smem_dp5_plain, smem_dp5_sens, smem_rodas4;          /* static shared memory bytes per CTA                  */
     int cubin_bytes;
     int from_cache;
+    int sens_layout;                                         /* layout sbm_solve uses for sensitivity solves (1 | 2) */
+    int ct_warps, ct_cols, ct_cols_state, ct_dyn_smem_bytes, ct_ctas_per_sm; /* CTA-transposed kernel: warps per CTA,
+                                                                columns per sensitivity warp / on the state warp */
+    int regs_dp5_ct, local_dp5_ct, smem_dp5_ct;
 } sbm_model_info_t;
 
 int         sbm_model_compile(const char* model_src, const sbm_model_desc_t* desc, sbm_model** out);

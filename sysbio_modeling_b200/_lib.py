@@ -26,7 +26,7 @@ class SbmError(RuntimeError):
 class ModelDesc(ctypes.Structure):
     _fields_ = [('n_vars', ctypes.c_int), ('n_params', ctypes.c_int), ('n_free', ctypes.c_int),
                 ('group_lanes', ctypes.c_int), ('cols_per_lane', ctypes.c_int), ('block_threads', ctypes.c_int),
-                ('stage_smem', ctypes.c_int), ('arch', ctypes.c_char_p), ('cache_dir', ctypes.c_char_p)]
+                ('sens_layout', ctypes.c_int), ('arch', ctypes.c_char_p), ('cache_dir', ctypes.c_char_p)]
 
 
 class ModelInfo(ctypes.Structure):
@@ -35,7 +35,9 @@ class ModelInfo(ctypes.Structure):
         'dyn_smem_bytes',
         'regs_dp5_plain', 'regs_dp5_sens', 'regs_rodas4',
         'local_dp5_plain', 'local_dp5_sens', 'local_rodas4',
-        'smem_dp5_plain', 'smem_dp5_sens', 'smem_rodas4', 'cubin_bytes', 'from_cache')]
+        'smem_dp5_plain', 'smem_dp5_sens', 'smem_rodas4', 'cubin_bytes', 'from_cache',
+        'sens_layout', 'ct_warps', 'ct_cols', 'ct_cols_state', 'ct_dyn_smem_bytes', 'ct_ctas_per_sm',
+        'regs_dp5_ct', 'local_dp5_ct', 'smem_dp5_ct')]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -66,6 +66,7 @@ struct Driver {
     CUresult (*cuLaunchKernel_)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                                 unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*cuGetErrorString_)(CUresult, const char**) = nullptr;
+    CUresult (*cuOccupancy_)(int*, CUfunction, int, size_t) = nullptr;
     bool ok = false;
     std::string why;
 };
@@ -88,6 +89,7 @@ static Driver& driver()
         LOAD(cuFuncSetAttribute_, "cuFuncSetAttribute")
         LOAD(cuLaunchKernel_, "cuLaunchKernel")
         LOAD(cuGetErrorString_, "cuGetErrorString")
+        LOAD(cuOccupancy_, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
 #undef LOAD
         d.ok = true;
     });
@@ -135,13 +137,17 @@ struct sbm_model {
     std::string arch;
     int G = 1, C = 1, block = 128, block_plain = 128;
     int dyn_smem = 0, dyn_smem_plain = 0;
+    // CTA-transposed sensitivity kernel (kernels/sbm_dp5_ct.cuh): W sensitivity warps x C columns + 1 state warp
+    int ctW = 0, ctC = 0, ctCS = 0, ct_dyn_smem = 0, ct_ctas_per_sm = 0, sm_count = 0;
+    bool ct_ok = false;
+    int layout = 0;              // 0 auto, 1 lane-per-column groups, 2 CTA-transposed
     std::string source;          // full NVRTC translation unit (kept for diagnostics)
     std::string log;
     std::vector<char> cubin;
     bool from_cache = false;
     bool loaded = false;
     CUmodule mod = nullptr;
-    KernelSlot dp5_plain, dp5_sens, rodas4;
+    KernelSlot dp5_plain, dp5_sens, dp5_ct, rodas4;
     std::mutex mu;
 };
 
@@ -205,8 +211,40 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
         return fail(SBM_E_INVALID, "stage vectors do not fit in shared memory for this group shape");
     }
 
+    // CTA-transposed layout: C columns per sensitivity warp with C*N <= 24 (three vectors of a thread's
+    // elements stay in registers), W = ceil(NF / C) sensitivity warps + the state warp
+    m->layout = desc->sens_layout > 0 ? desc->sens_layout : 0;
+    {
+        const int N = desc->n_vars, NF = desc->n_free;
+        int NJ = 1, NG = 1;
+        const char* q;
+        if ((q = strstr(model_src, "#define SBM_NJ "))) NJ = atoi(q + 15);
+        if ((q = strstr(model_src, "#define SBM_NG "))) NG = atoi(q + 15);
+        if (NF >= 1 && N <= 24) {
+            // C columns per pure sensitivity warp, up to CSmax on the state warp (it also holds the state column)
+            int C = 24 / N;
+            if (desc->sens_layout == 2 && desc->cols_per_lane > 0 && desc->cols_per_lane * N <= 32) C = desc->cols_per_lane;
+            int CSmax = (24 - N) / N;
+            if (CSmax > C) CSmax = C;
+            int rest = NF - CSmax;
+            const int Wp = rest > 0 ? (rest + C - 1) / C : 0;     // pure sensitivity warps
+            const int CS = NF - Wp * C > 0 ? NF - Wp * C : 0;
+            const int W = Wp + 1;
+            if (Wp == 0) C = 1;
+            const int CM = C > CS ? C : CS;
+            const long long doubles = 2ll * NJ * 32 + 2ll * NG * 32 + 3ll * W * 32 + 32 + (long long)desc->n_params * 32 +
+                                      32 + 48 + (long long)W * 2 * CM * N * 32;
+            // more than 8 warps would leave fewer than 255 registers per thread (two warps per scheduler)
+            if (W <= 8 && doubles * 8 <= 227 * 1024) {
+                m->ctW = W; m->ctC = C; m->ctCS = CS; m->ct_dyn_smem = (int)(doubles * 8); m->ct_ok = true;
+            }
+        }
+        if (m->layout == 2 && !m->ct_ok) { delete m; return fail(SBM_E_INVALID, "CTA-transposed layout does not fit this model"); }
+    }
+
     std::ostringstream src;
     src << sbm_embedded_args_header << "\n" << model_src << "\n" << sbm_embedded_kernels << "\n";
+    if (m->ct_ok) src << "SBM_DEFINE_DP5_CT(sbm_dp5_ct, " << m->ctW << ", " << m->ctC << ", " << m->ctCS << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_plain, 1, 1, 0, " << m->block_plain << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_sens, " << m->G << ", " << m->C << ", 1, " << m->block << ")\n";
     src << "SBM_DEFINE_RODAS4(sbm_rodas4_plain, " << m->block_plain << ")\n";
@@ -289,6 +327,15 @@ static int ensure_loaded(sbm_model* m)
     if ((rc = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return rc;
     DRV(driver().cuFuncSetAttribute_(m->dp5_sens.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
     DRV(driver().cuFuncSetAttribute_(m->dp5_plain.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_plain));
+    if (m->ct_ok) {
+        if ((rc = slot_load(m, m->dp5_ct, "sbm_dp5_ct"))) return rc;
+        DRV(driver().cuFuncSetAttribute_(m->dp5_ct.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->ct_dyn_smem));
+        int dev = 0;
+        RT(cudaGetDevice(&dev));
+        RT(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev));
+        DRV(driver().cuOccupancy_(&m->ct_ctas_per_sm, m->dp5_ct.fn, m->ctW * 32, (size_t)m->ct_dyn_smem));
+        if (m->ct_ctas_per_sm < 1) m->ct_ok = false;
+    }
     m->loaded = true;
     return 0;
 }
@@ -308,6 +355,10 @@ extern "C" int sbm_model_info(sbm_model* m, sbm_model_info_t* o)
     o->smem_dp5_plain = m->dp5_plain.smem; o->smem_dp5_sens = m->dp5_sens.smem; o->smem_rodas4 = m->rodas4.smem;
     o->cubin_bytes = (int)m->cubin.size();
     o->from_cache = m->from_cache ? 1 : 0;
+    o->ct_warps = m->ct_ok ? m->ctW : 0; o->ct_cols = m->ct_ok ? m->ctC : 0; o->ct_cols_state = m->ct_ok ? m->ctCS : 0;
+    o->ct_dyn_smem_bytes = m->ct_dyn_smem; o->ct_ctas_per_sm = m->ct_ctas_per_sm;
+    o->regs_dp5_ct = m->dp5_ct.regs; o->local_dp5_ct = m->dp5_ct.local; o->smem_dp5_ct = m->dp5_ct.smem;
+    o->sens_layout = (m->layout == 1 || !m->ct_ok) ? 1 : 2;
     return 0;
 }
 
@@ -438,10 +489,19 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
     KernelSlot* ks;
     long long threads;
     int block = m->block_plain, dyn = 0;
+    long long blocks = -1;
     if (o->solver == SBM_SOLVER_RODAS4) { ks = &m->rodas4; threads = ntraj; }
+    else if (jac && m->ct_ok && m->layout != 1) {
+        // persistent CTAs, 32 trajectories in flight each, refilled from a global queue
+        ks = &m->dp5_ct; block = m->ctW * 32; dyn = m->ct_dyn_smem; threads = 0;
+        blocks = (ntraj + 31) / 32;
+        const long long resident = (long long)m->sm_count * m->ct_ctas_per_sm;
+        if (blocks > resident) blocks = resident;
+        RT(cudaMemsetAsync(counters + SBM_CNT_QUEUE, 0, sizeof(unsigned long long), st));
+    }
     else if (jac) { ks = &m->dp5_sens; threads = ntraj * m->G; block = m->block; dyn = m->dyn_smem; }
     else { ks = &m->dp5_plain; threads = ntraj; dyn = m->dyn_smem_plain; }
-    const long long blocks = (threads + block - 1) / block;
+    if (blocks < 0) blocks = (threads + block - 1) / block;
     if (blocks > 2147483647ll) return fail(SBM_E_INVALID, "batch too large for one launch");
     void* params[] = {&a};
     DRV(driver().cuLaunchKernel_(ks->fn, (unsigned)blocks, 1, 1, (unsigned)block, 1, 1, (unsigned)dyn, (CUstream)st, params, nullptr));

@@ -16,6 +16,7 @@
 #define SBM_CNT_RHS     2     /* augmented right-hand-side evaluations         */
 #define SBM_CNT_LU      3     /* LU factorisations (Rosenbrock)                */
 #define SBM_CNT_TRAJ    4     /* trajectories finished                         */
+#define SBM_CNT_QUEUE   7     /* work-queue cursor of the persistent kernels (zeroed by sbm_solve) */
 #define SBM_N_COUNTERS  8
 
 typedef struct SbmSolveArgs {

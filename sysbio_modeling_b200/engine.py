@@ -29,7 +29,7 @@ def _ptr(arr):
 class CompiledModel(object):
     """Emit + NVRTC-compile the model (reference analogue: numba ``enable_jit``, ode_model.py:46-74)."""
 
-    def __init__(self, symbolic, group_lanes=0, cols_per_lane=0, block_threads=0, stage_smem=-1,
+    def __init__(self, symbolic, group_lanes=0, cols_per_lane=0, block_threads=0, sens_layout=0,
                  cache_dir=_lib.CACHE_DIR):
         if not isinstance(symbolic, SymbolicModel):
             raise TypeError('symbolic must be a SymbolicModel')
@@ -38,8 +38,10 @@ class CompiledModel(object):
         self.n_vars, self.n_params, self.n_free = self.cuda.n_vars, self.cuda.n_params, self.cuda.n_free
         L = _lib.lib()
         cache = cache_dir.encode() if cache_dir else None
+        if not sens_layout:
+            sens_layout = int(os.environ.get('SBM_SENS_LAYOUT', '0'))
         desc = ModelDesc(self.n_vars, self.n_params, self.n_free, group_lanes, cols_per_lane, block_threads,
-                         stage_smem, None, cache)
+                         sens_layout, None, cache)
         h = ctypes.c_void_p()
         _lib.check(L.sbm_model_compile(self.cuda.source.encode(), ctypes.byref(desc), ctypes.byref(h)))
         self._h = h

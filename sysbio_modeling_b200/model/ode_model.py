@@ -36,7 +36,7 @@ class OdeModel(ModelABC):
 
     def __init__(self, model, sens_model, n_vars, param_order, model_name='Model', use_jit=True,
                  model_jac=None, sens_model_jac=None, jit_type='numba', *, symbolic=None, fixed_params=None,
-                 rtol=1e-10, atol=1e-10, solver='dp5', max_steps=0, group_lanes=0, cols_per_lane=0, stage_smem=-1):
+                 rtol=1e-10, atol=1e-10, solver='dp5', max_steps=0, group_lanes=0, cols_per_lane=0, sens_layout=0):
         super(OdeModel, self).__init__(model, n_vars, param_order, model_name)
         self.sens_model = sens_model
         self.model_jac = model_jac
@@ -53,7 +53,7 @@ class OdeModel(ModelABC):
         if symbolic.n_vars != n_vars or list(symbolic.param_order) != list(param_order):
             raise ValueError('symbolic model does not match n_vars / param_order')
         self.symbolic = symbolic
-        self._group = (group_lanes, cols_per_lane, stage_smem)
+        self._group = (group_lanes, cols_per_lane, sens_layout)
         self._compiled = None
         self._jit_enabled = bool(use_jit)
 
@@ -79,7 +79,7 @@ class OdeModel(ModelABC):
     def compiled(self):
         if self._compiled is None:
             self._compiled = engine.compiled_model_for(self.symbolic, group_lanes=self._group[0],
-                                                       cols_per_lane=self._group[1], stage_smem=self._group[2])
+                                                       cols_per_lane=self._group[1], sens_layout=self._group[2])
         return self._compiled
 
     @property

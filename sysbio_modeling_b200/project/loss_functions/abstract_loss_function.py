@@ -128,11 +128,13 @@ class LossFunctionWithScaleFactors(LossFunctionABC):
         dev = torch.device('cuda')
         f64 = dict(dtype=torch.float64, device=dev)
         n, G = tables.n_rows, tables.n_groups
-        sims = torch.tensor(np.asarray(simulations['mean'].values, dtype=np.float64)[None, :], **f64)
+        sims = torch.from_numpy(np.ascontiguousarray(simulations['mean'].values, dtype=np.float64)[None, :].copy()).to(dev)
         theta = torch.zeros((1, max(n_proj, 1)), **f64)
         jac = None
         if simulations_jacobian is not None:
-            jac = torch.tensor(np.asarray(simulations_jacobian.values, dtype=np.float64)[None, :, :], **f64)
+            # C-contiguous [1][n_rows][n_proj]: DataFrame.values is often column-major and torch keeps strides
+            jac = torch.from_numpy(np.ascontiguousarray(simulations_jacobian.values, dtype=np.float64)[None, :, :]
+                                   .copy()).to(dev).contiguous()
         resid = torch.zeros((1, n), **f64)
         ssr = torch.zeros((1,), **f64)
         sf = torch.zeros((1, max(G, 1)), **f64)

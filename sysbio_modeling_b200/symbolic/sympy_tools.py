@@ -571,11 +571,16 @@ def emit_cuda(sm, pow_via_explog=True):
                                                              for q, (i, k) in enumerate(jkeys)))
     L.append('// Gv[q] = df_i/dp_free[j] for (i,j) in: %s' % ' '.join('%d:(%d,%d)' % (q, i, j)
                                                                    for q, (i, j) in enumerate(gkeys)))
+    L.append('// PS = stride of the parameter vector (32 when it lives in shared memory as [param][lane])')
+    L.append('template <int PS = 1>')
     L.append('__device__ __forceinline__ void sbm_fJG(const double t, const double* __restrict__ y,')
     L.append('        const double* __restrict__ p, double* __restrict__ f,')
     L.append('        double* __restrict__ Jv, double* __restrict__ Gv)')
     L.append('{')
-    _emit_block(L, rep, outs, pr)
+    blk = []
+    _emit_block(blk, rep, outs, pr)
+    import re as _re
+    L.extend(_re.sub(r'p\[(\d+)\]', r'p[\1 * PS]', ln) for ln in blk)
     L.append('}')
     L.append('')
 
@@ -601,6 +606,34 @@ def emit_cuda(sm, pow_via_explog=True):
         L.append('        out[%d] = (cid == 0) ? f[%d] : d;' % (i, i))
         L.append('    }')
     L.append('}')
+    L.append('')
+
+    # --- row i of J*w for C columns at once, J read from shared memory ([entry][lane]); used by the
+    #     CTA-transposed kernel (kernels/sbm_dp5_ct.cuh), where `i` is a constant after unrolling
+    L.append('template <int C>')
+    L.append('__device__ __forceinline__ void sbm_jrow(const int i, const double* __restrict__ Jp,')
+    L.append('        const double (&w)[C][SBM_N], double (&acc)[C])')
+    L.append('{')
+    for i in range(N):
+        ent = [(q, k) for q, (ii, k) in enumerate(jkeys) if ii == i]
+        L.append('    %sif (i == %d) {' % ('else ' if i else '', i))
+        for q, k in ent:
+            L.append('        const double j%d = Jp[%d * 32];' % (q, q))
+        if ent:
+            expr = 'acc[c]'
+            for q, k in ent:
+                expr = 'fma(j%d, w[c][%d], %s)' % (q, k, expr)
+            L.append('#pragma unroll')
+            L.append('        for (int c = 0; c < C; ++c) acc[c] = %s;' % expr)
+        L.append('    }')
+    L.append('}')
+    L.append('// sbm_gtab[j*N + i] = index q of Gv holding df_i/dp_free[j], or -1 (structural zero); padded with')
+    L.append('// empty columns so that a column group may overhang the last parameter')
+    npad = NF + 32
+    gt = [-1] * (npad * N)
+    for q, (i, j) in enumerate(gkeys):
+        gt[j * N + i] = q
+    L.append('__device__ __constant__ short sbm_gtab[%d] = {%s};' % (npad * N, ', '.join(str(v) for v in gt)))
     L.append('')
 
     # --- dense Jacobian (row-major Jd[i*N+k]) and df/dt for the Rosenbrock kernel

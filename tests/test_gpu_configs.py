@@ -87,13 +87,19 @@ def test_c4_mapk_sensitivities_vs_lsoda_and_fd():
     nominal = np.array([mod.nominal[k] for k in sm.param_order])
     rng = np.random.default_rng(4)
     P = nominal * np.exp(0.25 * rng.standard_normal((6, 22)))
-    t = np.concatenate([[0.0], np.linspace(150, 3000, 20)])
+    # the reference integrates on its 1000-node grid and reads the nodes at / after the measurement times
+    # (base_project.py:418-420, utils.py:18-21); LSODA also needs the fine grid to stay inside its
+    # per-interval step budget on this oscillator
+    grid = np.linspace(0, 3000, 1000)
+    idx = np.concatenate([[0], np.searchsorted(grid, np.linspace(150, 3000, 20))])
+    t = grid[idx]
     y0 = np.array(mod.initial_conditions)
     y, S = om.calc_jacobian_batch(P, t, y0)
     assert (om.last_status == 0).all()
     for b in range(6):
-        yr, Sr = O.calc_jacobian(s, 8, P[b], t, np.concatenate([y0, np.zeros(176)]), rtol=1e-10, atol=1e-10,
+        yr, Sr = O.calc_jacobian(s, 8, P[b], grid, np.concatenate([y0, np.zeros(176)]), rtol=1e-10, atol=1e-10,
                                  return_states=True)
+        yr, Sr = yr[idx], Sr[idx]
         # LSODA's own global error at 1e-10 is ~1e-7 relative on this oscillating system; 10x tol is checked
         # against the tighter reference below
         assert np.all(np.abs(y[b] - yr) <= 1e-6 * (1 + np.abs(yr)))
@@ -262,3 +268,28 @@ def test_device_reciprocal_accuracy(tmp_path):
     vals = dict(zip(out.split()[0::2], [float(v) for v in out.split()[1::2]]))
     assert vals['sbm_rcp_ulp'] <= 1.0
     assert vals['seed_relerr'] < 1e-5
+
+
+def test_cta_transposed_layout_matches_warp_group_layout():
+    """The two sensitivity kernels (lane = column warp groups, and lane = trajectory / warp = column group with a
+    state warp) integrate the same augmented system: states and sensitivities agree to the solver tolerance, on the
+    MAPK cascade (8 warps per CTA) and on the 2-state Michaelis-Menten fixture (single-warp CTAs)."""
+    import sysbio_modeling_b200 as sb
+    from sysbio_modeling_b200 import model_files
+    for name, nb, tgrid in (('mapk_kholodenko', 70, np.concatenate([[0.0], np.linspace(150, 3000, 20)])),
+                            ('michaelis_menten', 37, np.linspace(0, 30, 13))):
+        mod = model_files.module(name)
+        out = {}
+        for layout in (1, 2):
+            om = sb.OdeModel.from_model_file(model_files.path(name), sens_layout=layout)
+            assert om.compiled.info()['sens_layout'] == layout
+            nom = getattr(mod, 'nominal', {'vmax': 1.0, 'km': 0.5, 'k_synt_s': 0.3, 'k_deg_s': 0.01, 'k_deg_p': 0.05})
+            nominal = np.array([nom[k] for k in om.param_order])
+            P = nominal * np.exp(0.25 * np.random.default_rng(11).standard_normal((nb, len(nominal))))
+            y0 = np.array(getattr(mod, 'initial_conditions', np.zeros(om.n_vars)), dtype=float)
+            out[layout] = om.calc_jacobian_batch(P, tgrid, y0)
+            assert (om.last_status == 0).all()
+            assert om.last_counters['trajectories'] == nb
+        (y1, S1), (y2, S2) = out[1], out[2]
+        assert np.all(np.abs(y1 - y2) <= 1e-8 * (1 + np.abs(y1)))
+        assert np.all(np.abs(S1 - S2) <= 1e-7 * (1 + np.abs(S1)))
