@@ -78,7 +78,7 @@ typedef struct sbm_model_info_t {
     int from_cache;
     int sens_layout;                                         /* layout sbm_solve uses for sensitivity solves (1 | 2) */
     int ct_warps, ct_cols, ct_cols_state, ct_dyn_smem_bytes, ct_ctas_per_sm; /* CTA-transposed kernel: warps per CTA,
-                                                                columns per sensitivity warp / on the state warp */
+                                                                columns per warp / on the last warp */
     int regs_dp5_ct, local_dp5_ct, smem_dp5_ct;
 } sbm_model_info_t;
 

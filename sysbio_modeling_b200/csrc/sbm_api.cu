@@ -211,32 +211,25 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
         return fail(SBM_E_INVALID, "stage vectors do not fit in shared memory for this group shape");
     }
 
-    // CTA-transposed layout: C columns per sensitivity warp with C*N <= 24 (three vectors of a thread's
-    // elements stay in registers), W = ceil(NF / C) sensitivity warps + the state warp
+    // CTA-transposed layout (kernels/sbm_dp5_ct.cuh): the emitter chose W warps x C column slots and split the
+    // model's primal part into W shares (SBM_CT_W / SBM_CT_C in the model source; 0 = does not fit)
     m->layout = desc->sens_layout > 0 ? desc->sens_layout : 0;
     {
         const int N = desc->n_vars, NF = desc->n_free;
-        int NJ = 1, NG = 1;
+        int NJ = 1, NG = 1, W = 0, C = 0;
         const char* q;
         if ((q = strstr(model_src, "#define SBM_NJ "))) NJ = atoi(q + 15);
         if ((q = strstr(model_src, "#define SBM_NG "))) NG = atoi(q + 15);
-        if (NF >= 1 && N <= 24) {
-            // C columns per pure sensitivity warp, up to CSmax on the state warp (it also holds the state column)
-            int C = 24 / N;
-            if (desc->sens_layout == 2 && desc->cols_per_lane > 0 && desc->cols_per_lane * N <= 32) C = desc->cols_per_lane;
-            int CSmax = (24 - N) / N;
-            if (CSmax > C) CSmax = C;
-            int rest = NF - CSmax;
-            const int Wp = rest > 0 ? (rest + C - 1) / C : 0;     // pure sensitivity warps
-            const int CS = NF - Wp * C > 0 ? NF - Wp * C : 0;
-            const int W = Wp + 1;
-            if (Wp == 0) C = 1;
-            const int CM = C > CS ? C : CS;
-            const long long doubles = 2ll * NJ * 32 + 2ll * NG * 32 + 3ll * W * 32 + 32 + (long long)desc->n_params * 32 +
-                                      32 + 48 + (long long)W * 2 * CM * N * 32;
-            // more than 8 warps would leave fewer than 255 registers per thread (two warps per scheduler)
-            if (W <= 8 && doubles * 8 <= 227 * 1024) {
-                m->ctW = W; m->ctC = C; m->ctCS = CS; m->ct_dyn_smem = (int)(doubles * 8); m->ct_ok = true;
+        if ((q = strstr(model_src, "#define SBM_CT_W "))) W = atoi(q + 17);
+        if ((q = strstr(model_src, "#define SBM_CT_C "))) C = atoi(q + 17);
+        (void)NG;
+        if (W >= 1 && C >= 1 && NF >= 1) {
+            const int CL = NF - (W - 1) * C;
+            const long long bytes = 8ll * (2 * NJ * 32 + 2 * NF * N * 32 + 7 * N * 32 + N * 32 + desc->n_params * 32 +
+                                           3 * W * 32 + 32 + 6 * 32 + 4 * 32 + 32) +
+                                    4ll * (8 * 32 + 3 * 32) + 8ll * ((W - 1) * C + CL) * 2 * N * 32;
+            if (CL >= 1 && CL <= C && W <= 32 && bytes <= 227 * 1024) {
+                m->ctW = W; m->ctC = C; m->ctCS = CL; m->ct_dyn_smem = (int)bytes; m->ct_ok = true;
             }
         }
         if (m->layout == 2 && !m->ct_ok) { delete m; return fail(SBM_E_INVALID, "CTA-transposed layout does not fit this model"); }
@@ -244,7 +237,7 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
 
     std::ostringstream src;
     src << sbm_embedded_args_header << "\n" << model_src << "\n" << sbm_embedded_kernels << "\n";
-    if (m->ct_ok) src << "SBM_DEFINE_DP5_CT(sbm_dp5_ct, " << m->ctW << ", " << m->ctC << ", " << m->ctCS << ")\n";
+    if (m->ct_ok) src << "SBM_DEFINE_DP5_CT(sbm_dp5_ct, " << m->ctW << ", " << m->ctC << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_plain, 1, 1, 0, " << m->block_plain << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_sens, " << m->G << ", " << m->C << ", 1, " << m->block << ")\n";
     src << "SBM_DEFINE_RODAS4(sbm_rodas4_plain, " << m->block_plain << ")\n";
@@ -253,6 +246,14 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     const std::string archopt = "--gpu-architecture=" + m->arch;
     std::vector<const char*> opts = {archopt.c_str(), "--std=c++17", "-lineinfo", "--fmad=true",
                                      "--ptxas-options=-v", "-DSBM_NVRTC=1"};
+    // extra -D options for experiments (e.g. SBM_KERNEL_DEFINES="-DSBM_CT_PROF=1 -DSBM_CT_Y_SMEM=1")
+    std::vector<std::string> extra_defs;
+    if (const char* ed = getenv("SBM_KERNEL_DEFINES")) {
+        std::istringstream is(ed);
+        std::string tok;
+        while (is >> tok) extra_defs.push_back(tok);
+    }
+    for (auto& d : extra_defs) opts.push_back(d.c_str());
     std::string key_material = m->source;
     for (auto o : opts) { key_material += o; key_material += "\n"; }
     char key[64];

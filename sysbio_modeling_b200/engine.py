@@ -34,12 +34,12 @@ class CompiledModel(object):
         if not isinstance(symbolic, SymbolicModel):
             raise TypeError('symbolic must be a SymbolicModel')
         self.symbolic = symbolic
-        self.cuda = emit_cuda(symbolic)
+        if not sens_layout:
+            sens_layout = int(os.environ.get('SBM_SENS_LAYOUT', '0'))
+        self.cuda = emit_cuda(symbolic, ct_cols=cols_per_lane if sens_layout == 2 else 0)
         self.n_vars, self.n_params, self.n_free = self.cuda.n_vars, self.cuda.n_params, self.cuda.n_free
         L = _lib.lib()
         cache = cache_dir.encode() if cache_dir else None
-        if not sens_layout:
-            sens_layout = int(os.environ.get('SBM_SENS_LAYOUT', '0'))
         desc = ModelDesc(self.n_vars, self.n_params, self.n_free, group_lanes, cols_per_lane, block_threads,
                          sens_layout, None, cache)
         h = ctypes.c_void_p()

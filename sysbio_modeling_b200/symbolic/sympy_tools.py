@@ -512,7 +512,150 @@ def _emit_block(lines, rep, outs, printer, pad='    '):
         lines.append(pad + '%s = %s;' % (target, printer.doprint(e)))
 
 
-def emit_cuda(sm, pow_via_explog=True):
+
+def ct_layout(n_vars, n_free, cols=0):
+    """Shape of the CTA-transposed sensitivity kernel (csrc/kernels/sbm_dp5_ct.cuh): W warps per CTA, each
+    carrying C column slots of N states (three register-resident vectors per slot -> C*N <= 24), W*C >= n_free.
+    Returns (W, C), or (0, 0) when the model does not fit (W <= 8 keeps two warps per scheduler and so the full
+    255 registers per thread; the caller then uses the warp-group kernel)."""
+    if n_free < 1 or n_vars > 24:
+        return 0, 0
+    C = min(max(24 // n_vars, 1), n_free)
+    if cols and cols * n_vars <= 32:
+        C = min(cols, n_free)
+    W = -(-n_free // C)
+    if W > 8:
+        return 0, 0
+    return W, C
+
+
+def _instr_cost(e):
+    """Rough instruction count of an expression on the FP64 pipe (balancing only)."""
+    c = count_flops([e])
+    for node in sp.preorder_traversal(e):
+        if isinstance(node, sbm_rcp):
+            c += 6
+        elif isinstance(node, (sbm_log, sp.log)):
+            c += 34
+        elif isinstance(node, (sbm_exp, sp.exp)):
+            c += 29
+        elif isinstance(node, sp.Pow) and not node.exp.is_Integer:
+            c += 60
+    return c
+
+
+def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms):
+    """Split the model's primal part - f, the non-zeros of J = df/dy and of G = df/dp - into W shares, one per
+    warp of the CTA-transposed kernel.  Each share is straight-line code that recomputes the sub-expressions it
+    needs (a share that owns several outputs of one rate law computes its reciprocal once), reads only the stage
+    values of the states it depends on, and stores its outputs straight into shared memory ([entry][lane]).
+    Greedy longest-processing-time assignment on an instruction-count estimate; the starting load of a warp
+    is the work of its real sensitivity columns, so warps with empty column slots take more of the model."""
+    outs = [('f', i, e) for i, e in enumerate(f_x)] + [('J', q, e) for q, e in enumerate(J_x)] + \
+           [('G', q, e) for q, e in enumerate(G_x)]
+    rep, red = sp.cse([e for _, _, e in outs], symbols=sp.numbered_symbols('s_'), optimizations='basic')
+    rsym = [r[0] for r in rep]
+    rexpr = dict(rep)
+    rset = set(rsym)
+    rcost = {k: _instr_cost(v) for k, v in rep}
+    deps = {k: [x for x in v.free_symbols if x in rset] for k, v in rep}
+
+    def closure(expr):
+        todo = [x for x in expr.free_symbols if x in rset]
+        seen = set()
+        while todo:
+            x = todo.pop()
+            if x in seen:
+                continue
+            seen.add(x)
+            todo.extend(deps[x])
+        return seen
+    items = []
+    for (kind, idx, _), e in zip(outs, red):
+        cl = closure(e)
+        items.append((kind, idx, e, cl, _instr_cost(e) + 2 + sum(rcost[x] for x in cl)))
+    items.sort(key=lambda it: -it[4])
+    # starting load of a warp = estimated instructions of its sensitivity columns per stage: the J entries are
+    # loaded once per warp, each column costs nnz(J) FMAs plus ~12 instructions per state for the tableau
+    # updates and their loads/stores; warp 0 also runs the step controller
+    nnzJ = len(J_x)
+    loads = []
+    for w in range(W):
+        real = max(0, min(C, NF - w * C))
+        loads.append(float(nnzJ + real * (nnzJ + 12 * N)) + (60.0 if w == 0 else 0.0))
+    have = [set() for _ in range(W)]
+    mine = [[] for _ in range(W)]
+    ycomp = [set() for _ in range(W)]
+    yset = set(ysyms)
+    Y_COST = 12                                 # 6 LDS + 6 FMA to form the stage value of one state
+
+    def ys_of(e, cl):
+        out = set(x for x in e.free_symbols if x in yset)
+        for x in cl:
+            out |= set(z for z in rexpr[x].free_symbols if z in yset)
+        return out
+    for kind, idx, e, cl, _ in items:
+        best, bestv = 0, None
+        yneed = ys_of(e, cl)
+        for w in range(W):
+            v = loads[w] + _instr_cost(e) + 2 + sum(rcost[x] for x in cl if x not in have[w]) + \
+                Y_COST * len(yneed - ycomp[w])
+            if bestv is None or v < bestv:
+                best, bestv = w, v
+        loads[best] = bestv
+        have[best] |= cl
+        ycomp[best] |= yneed
+        mine[best].append((kind, idx, e))
+    L.append('// primal shares of the CTA-transposed kernel: estimated instructions per warp = %s'
+             % ', '.join('%d' % int(v) for v in loads))
+    L.append('template <int PS>')
+    L.append('__device__ __forceinline__ void sbm_primal_share(const int share, const double t,')
+    L.append('        const double* __restrict__ yb, const double* __restrict__ fh, const double (&cf)[6],')
+    L.append('        const double* __restrict__ p, double* __restrict__ Jo, double* __restrict__ Go,')
+    L.append('        double* __restrict__ fo)')
+    L.append('{')
+    L.append('    switch (share) {')
+    ypat = {str(sy): i for i, sy in enumerate(ysyms)}
+    for w in range(W):
+        L.append('    case %d: {' % w)
+        need_syms = set()
+        for x in have[w]:
+            need_syms |= rexpr[x].free_symbols
+        for _, _, e in mine[w]:
+            need_syms |= e.free_symbols
+        need = sorted(ypat[str(x)] for x in need_syms if str(x) in ypat)
+        for i in need:
+            # stage value of state i:  y_i + sum_j cf[j] f_j[i]   (cf[j] = h a_sj, zero beyond the stage)
+            acc = 'yb[%d * 32]' % i
+            for j in range(6):
+                acc = 'fma(cf[%d], fh[%d * 32], %s)' % (j, j * N + i, acc)
+            L.append('        const double Y%d = %s;' % (i, acc))
+        body = []
+        for k in rsym:
+            if k in have[w]:
+                body.append('        const double %s = %s;' % (k, pr.doprint(rexpr[k])))
+        for kind, idx, e in mine[w]:
+            if kind == 'f':
+                body.append('        fo[%d * 32] = %s;' % (idx, pr.doprint(e)))
+            elif kind == 'J':
+                body.append('        Jo[%d * 32] = %s;' % (idx, pr.doprint(e)))
+            else:
+                i, j = gkeys[idx]
+                body.append('        Go[%d * 32] = %s;' % (j * N + i, pr.doprint(e)))
+        import re as _re
+        for ln in body:
+            ln = _re.sub(r'p\[(\d+)\]', r'p[\1 * PS]', ln)
+            ln = _re.sub(r'y\[(\d+)\]', r'Y\1', ln)
+            L.append(ln)
+        L.append('    } break;')
+    L.append('    default: break;')
+    L.append('    }')
+    L.append('}')
+    L.append('')
+    return [int(v) for v in loads]
+
+
+def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     """Emit the device functions the integrator kernels are compiled against (NVRTC, sm_100a)."""
     pr = _CudaPrinter()
     N, NP, NF = sm.n_vars, sm.n_params, sm.n_free
@@ -627,14 +770,12 @@ def emit_cuda(sm, pow_via_explog=True):
             L.append('        for (int c = 0; c < C; ++c) acc[c] = %s;' % expr)
         L.append('    }')
     L.append('}')
-    L.append('// sbm_gtab[j*N + i] = index q of Gv holding df_i/dp_free[j], or -1 (structural zero); padded with')
-    L.append('// empty columns so that a column group may overhang the last parameter')
-    npad = NF + 32
-    gt = [-1] * (npad * N)
-    for q, (i, j) in enumerate(gkeys):
-        gt[j * N + i] = q
-    L.append('__device__ __constant__ short sbm_gtab[%d] = {%s};' % (npad * N, ', '.join(str(v) for v in gt)))
-    L.append('')
+    W_ct, C_ct = ct_layout(N, NF, ct_cols)
+    L.append('#define SBM_CT_W %d' % W_ct)
+    L.append('#define SBM_CT_C %d' % C_ct)
+    if W_ct:
+        ysyms = [sp.Symbol('y[%d]' % i, real=True) for i in range(N)]
+        _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms)
 
     # --- dense Jacobian (row-major Jd[i*N+k]) and df/dt for the Rosenbrock kernel
     rep, red = sp.cse(J_x, symbols=sp.numbered_symbols('c_'), optimizations='basic')
