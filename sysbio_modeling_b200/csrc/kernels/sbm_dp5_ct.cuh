@@ -255,7 +255,8 @@ struct SbmCtShared {
     double* fh;          // [7][N][32]         stage derivatives f_1..f_7 of the state column
     double* yb;          // [N][32]            state y at the start of the step
     double* pb;          // [NP][32]           model parameters of each lane's trajectory
-    double* sqb;         // [3][W][32]         partial sums: error, |y|, |f| (per warp)
+    double* sqb;         // [W][32]            partial sums of the squared error norm (per warp); on start-up steps
+                         //                    the |y| and |f| partial sums are parked in the first two elements of each warp's S4
     double* hb;          // [32]               step of each lane (0: zero-length step / idle)
     double* cd;          // [SBM_CT_ND][32]    controller doubles
     unsigned long long* cnt;   // [4][32]      steps, rejects, rhs evaluations, trajectories
@@ -270,7 +271,7 @@ struct SbmCtShared {
 // -------------------------------------------------------------------------------------------------
 // step controller, trajectory queue and the state column (warp 0, one lane per trajectory)
 // -------------------------------------------------------------------------------------------------
-template <int W>
+template <int W, int C, int CL>
 __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane)
 {
     constexpr int N = SBM_N;
@@ -297,7 +298,7 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
         // ---- the state column of the step just taken: 5th-order solution, embedded error, norms ----
         double sq = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
-        for (int w = 0; w < W; ++w) sq += sh.sqb[(0 * W + w) * 32 + lane];
+        for (int w = 0; w < W; ++w) sq += sh.sqb[w * 32 + lane];
         double ynew[N], f7[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -365,8 +366,10 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
                 // upper bound 100 h0 and let the controller (and, if needed, one rejection) settle it
 #pragma unroll
                 for (int w = 0; w < W; ++w) {
-                    q0 += sh.sqb[(1 * W + w) * 32 + lane];
-                    q1 += sh.sqb[(2 * W + w) * 32 + lane];
+                    const int cw = (w == W - 1) ? CL : C;
+                    const double* park = sh.V + ((w * 2 * C + cw) * N) * 32 + lane;    // that warp's S4
+                    q0 += park[0];
+                    q1 += park[32];
                 }
                 const double n0 = sqrt(q0 * inv_naug), n1 = sqrt(q1 * inv_naug);
                 const double h0 = (n0 < 1e-5 || n1 < 1e-5) ? 1e-6 : 0.01 * n0 / n1;
@@ -505,6 +508,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
     const int col0 = warp * C;                     // first sensitivity column (free-parameter index) of this warp
     double* V1 = sh.V + (warp * 2 * C * N) * 32 + lane;
     double* V4 = V1 + CW * N * 32;
+    static_assert(CW * N >= 2, "start-up norms are parked in two elements of S4");
     double y[CW][N], s2[CW][N], s3[CW][N];
 #pragma unroll
     for (int c = 0; c < CW; ++c)
@@ -517,7 +521,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
     const double rtol = a.rtol, atol = a.atol;
 
     for (;;) {
-        if (warp == 0) sbm_ct_control<W>(a, sh, lane);
+        if (warp == 0) sbm_ct_control<W, C, SBM_NF - (W - 1) * C>(a, sh, lane);
         SBM_CT_BAR(NT);                            // controller output published
         const int cflags = sh.cta[0];
         if (!(cflags & SBM_CT_ALIVE)) break;
@@ -537,9 +541,8 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
             }
             if (s < 7) sbm_ct_primal<W>(sh, warp, lane, s + 1, h);
             else {
-                sh.sqb[(0 * W + warp) * 32 + lane] = sq;
-                sh.sqb[(1 * W + warp) * 32 + lane] = d0;
-                sh.sqb[(2 * W + warp) * 32 + lane] = d1;
+                sh.sqb[warp * 32 + lane] = sq;
+                if (anyinit) { V4[0] = d0; V4[32] = d1; }      // S4 is dead once the error norm is formed
             }
             SBM_CT_BAR(NT);
         }
@@ -548,7 +551,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
 
 // W warps per CTA; warps 0..W-2 carry C sensitivity columns each, warp W-1 the remaining CL = NF - (W-1)*C.
 // Shared-memory carve-up in doubles (sbm_api.cu computes the same size on the host):
-//   2*NJ*32 + 2*NF*N*32 + 7*N*32 + N*32 + NP*32 + 3*W*32 + 32 + ND*32 + 4*32 + 32 + (NI*32 + 3*32)/2
+//   2*NJ*32 + 2*NF*N*32 + 7*N*32 + N*32 + NP*32 + W*32 + 32 + ND*32 + 4*32 + 32 + (NI*32 + 3*32)/2
 //   + ((W-1)*C + CL)*2*N*32
 template <int W, int C>
 __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
@@ -564,7 +567,7 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     sh.yb = sh.fh + 7 * N * 32;
     sh.pb = sh.yb + N * 32;
     sh.sqb = sh.pb + SBM_NP * 32;
-    sh.hb = sh.sqb + 3 * W * 32;
+    sh.hb = sh.sqb + W * 32;
     sh.cd = sh.hb + 32;
     sh.cnt = (unsigned long long*)(sh.cd + SBM_CT_ND * 32);
     sh.trj = (long long*)(sh.cnt + 4 * 32);
@@ -580,7 +583,7 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     for (int q = threadIdx.x; q < 2 * SBM_NF * N * 32; q += W * 32) sh.Gd[q] = 0.0;      // structural zeros of G
     for (int q = threadIdx.x; q < 2 * SBM_NJ * 32; q += W * 32) sh.Jb[q] = 0.0;
     for (int q = threadIdx.x; q < 7 * N * 32; q += W * 32) sh.fh[q] = 0.0;
-    for (int q = threadIdx.x; q < 3 * W * 32; q += W * 32) sh.sqb[q] = 0.0;
+    for (int q = threadIdx.x; q < W * 32; q += W * 32) sh.sqb[q] = 0.0;
     if (warp == 0) {
         for (int i = 0; i < N; ++i) sh.yb[i * 32 + lane] = 0.0;
         for (int m = 0; m < SBM_NP; ++m) sh.pb[m * 32 + lane] = 1.0;

@@ -515,18 +515,41 @@ def _emit_block(lines, rep, outs, printer, pad='    '):
 
 def ct_layout(n_vars, n_free, cols=0):
     """Shape of the CTA-transposed sensitivity kernel (csrc/kernels/sbm_dp5_ct.cuh): W warps per CTA, each
-    carrying C column slots of N states (three register-resident vectors per slot -> C*N <= 24), W*C >= n_free.
-    Returns (W, C), or (0, 0) when the model does not fit (W <= 8 keeps two warps per scheduler and so the full
-    255 registers per thread; the caller then uses the warp-group kernel)."""
+    carrying C sensitivity columns of N states (three register-resident vectors per column), W*C >= n_free.
+    Small systems (N * NF <= 24) run one warp per CTA = one thread per trajectory.  Larger ones take the
+    smallest C that needs at most 11 warps (168 registers per thread; measured on the MAPK model: C = 2 x 11
+    warps beats C = 3 x 8 warps, because the unrolled stage code is smaller and more warps hide latency).
+    Returns (W, C), or (0, 0) when the model does not fit (the caller then uses the warp-group kernel)."""
     if n_free < 1 or n_vars > 24:
         return 0, 0
-    C = min(max(24 // n_vars, 1), n_free)
+    cmax = min(max(24 // n_vars, 1), n_free)
     if cols and cols * n_vars <= 32:
         C = min(cols, n_free)
+    elif n_vars * n_free <= 24:
+        C = n_free
+    else:
+        C = cmax
+        for c in range(1, cmax + 1):
+            if -(-n_free // c) <= 11:
+                C = c
+                break
     W = -(-n_free // C)
-    if W > 8:
+    if W > (32 if cols else 11):
         return 0, 0
     return W, C
+
+
+def ct_share_warps(W, n_shares):
+    """Warps that evaluate the model's primal shares: spread over the schedulers (warp w runs on scheduler w % 4)
+    that host the fewest warps, highest warp index first."""
+    count = [len(range(q, W, 4)) for q in range(4)]
+    free = [sorted(range(q, W, 4)) for q in range(4)]
+    out = []
+    while len(out) < min(n_shares, W):
+        q = min((q for q in range(4) if free[q]), key=lambda q: (count[q], -q))
+        out.append(free[q].pop())
+        count[q] += 1
+    return out
 
 
 def _instr_cost(e):
@@ -574,15 +597,19 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms):
     for (kind, idx, _), e in zip(outs, red):
         cl = closure(e)
         items.append((kind, idx, e, cl, _instr_cost(e) + 2 + sum(rcost[x] for x in cl)))
-    items.sort(key=lambda it: -it[4])
     # starting load of a warp = estimated instructions of its sensitivity columns per stage: the J entries are
     # loaded once per warp, each column costs nnz(J) FMAs plus ~12 instructions per state for the tableau
     # updates and their loads/stores; warp 0 also runs the step controller
     nnzJ = len(J_x)
+    import os as _os
+    n_shares = int(_os.environ.get('SBM_CT_SHARES', '0')) or min(W, 3)
+    share_warps = [int(x) for x in _os.environ.get('SBM_CT_SHARE_WARPS', '').split(',') if x.strip()] or \
+        ct_share_warps(W, n_shares)
     loads = []
     for w in range(W):
         real = max(0, min(C, NF - w * C))
-        loads.append(float(nnzJ + real * (nnzJ + 12 * N)) + (60.0 if w == 0 else 0.0))
+        loads.append(float(nnzJ + real * (nnzJ + 12 * N)) + (60.0 if w == 0 else 0.0) +
+                     (0.0 if w in share_warps else 1e9))
     have = [set() for _ in range(W)]
     mine = [[] for _ in range(W)]
     ycomp = [set() for _ in range(W)]
@@ -594,18 +621,50 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms):
         for x in cl:
             out |= set(z for z in rexpr[x].free_symbols if z in yset)
         return out
-    for kind, idx, e, cl, _ in items:
-        best, bestv = 0, None
-        yneed = ys_of(e, cl)
-        for w in range(W):
-            v = loads[w] + _instr_cost(e) + 2 + sum(rcost[x] for x in cl if x not in have[w]) + \
-                Y_COST * len(yneed - ycomp[w])
-            if bestv is None or v < bestv:
-                best, bestv = w, v
-        loads[best] = bestv
-        have[best] |= cl
-        ycomp[best] |= yneed
-        mine[best].append((kind, idx, e))
+
+    def assign(w, group):
+        for kind, idx, e, cl, _ in group:
+            loads[w] += _instr_cost(e) + 2 + sum(rcost[x] for x in cl if x not in have[w]) + \
+                Y_COST * len(ys_of(e, cl) - ycomp[w])
+            have[w] |= cl
+            ycomp[w] |= ys_of(e, cl)
+            mine[w].append((kind, idx, e))
+
+    def incr(w, group):
+        h, yc, v = set(have[w]), set(ycomp[w]), 0.0
+        for kind, idx, e, cl, _ in group:
+            v += _instr_cost(e) + 2 + sum(rcost[x] for x in cl if x not in h) + Y_COST * len(ys_of(e, cl) - yc)
+            h |= cl
+            yc |= ys_of(e, cl)
+        return v
+    # clusters: J and G outputs that share an expensive sub-expression (a reciprocal, exp, log ...) stay in
+    # one share - in a reaction network these are the outputs of one rate law
+    jg = [it for it in items if it[0] != 'f']
+    parent = list(range(len(jg)))
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+    owner = {}
+    for n, it in enumerate(jg):
+        for x in it[3]:
+            if rcost[x] >= 4:
+                if x in owner:
+                    parent[find(n)] = find(owner[x])
+                else:
+                    owner[x] = n
+    clusters = {}
+    for n, it in enumerate(jg):
+        clusters.setdefault(find(n), []).append(it)
+    groups = sorted(clusters.values(), key=lambda g: -sum(it[4] for it in g))
+    for g in groups:
+        w = min(share_warps, key=lambda w: loads[w] + incr(w, g))
+        assign(w, g)
+    for it in sorted([it for it in items if it[0] == 'f'], key=lambda it: -it[4]):
+        w = min(share_warps, key=lambda w: loads[w] + incr(w, [it]))
+        assign(w, [it])
     L.append('// primal shares of the CTA-transposed kernel: estimated instructions per warp = %s'
              % ', '.join('%d' % int(v) for v in loads))
     L.append('template <int PS>')
