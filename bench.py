@@ -171,7 +171,7 @@ def run_reference(args):
         return 0
     sm, nominal, _ = mapk_model_info()
     cores = os.cpu_count() or 1
-    per_step = args.cpu_sample if args.cpu_sample > 0 else max(2 * cores, 32)
+    per_step = args.cpu_sample if args.cpu_sample > 0 else 100 * cores      # ~3 s of CPU work per step
     thetas = make_thetas(nominal, per_step * (args.steps + args.warmup), 4)
     import multiprocessing as mp
     _single_thread_env()
@@ -191,7 +191,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args, per_step),
+            'config': dict(workload_config(args, args.batch), sample_per_step=per_step),
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': '%d parameter sets per step, SciPy odeint (LSODA) rtol=atol=%g on the reference\'s '
                                        '1000-node grid, numba-compiled generated sensitivity RHS, %d processes'
@@ -359,6 +359,16 @@ def main():
         kern_info.update({'group_lanes': info['group_lanes'], 'cols_per_lane': info['cols_per_lane'],
                           'block_threads': info['block_threads'], 'dyn_smem_bytes': info['dyn_smem_bytes'],
                           'regs': info['regs_dp5_sens'], 'local_bytes': info['local_dp5_sens']})
+    # DRAM traffic of the dominant kernel from the committed ncu capture, scaled to this launch's batch
+    traffic, traffic_note = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+        if tr.get('kernel') == kname:
+            traffic = (tr['dram_bytes_read'] + tr['dram_bytes_write']) * B / float(tr['param_sets'])
+            traffic_note = 'dram read+write of one launch at %d parameter sets (%s), scaled by batch' % (
+                tr['param_sets'], tr['source'])
+    except Exception:
+        pass
     line = None
     if rank == 0:
         line = {
@@ -372,7 +382,8 @@ def main():
             'kernels': kern_info,
             'counters_per_step': cnt, 'failed_trajectories': status_bad,
             'roofline': {'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                         'frac': achieved_tf / peak_tf, 'traffic': None,
+                         'frac': achieved_tf / peak_tf, 'traffic': traffic, 'traffic_note': traffic_note,
+                         'algorithmic_bytes_per_launch': B * t.E * (8 * (sm.n_params + sm.n_vars) + 8 * 40 * (1 + t.n_proj) + 4),
                          'kernel': kname,
                          'peak_source': 'measured: sbm_fp64_peak DFMA microbenchmark in this run '
                                         '(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)',
@@ -386,7 +397,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = args.cpu_sample if args.cpu_sample > 0 else min(512, max(4 * cores, 64))
+        sample = args.cpu_sample if args.cpu_sample > 0 else min(B, 400 * cores)       # ~12 s of CPU work
         th = make_thetas(nominal, sample, 4)
         rate, dt, cores = cpu_reference_rate(th, args.tol, cores)
         line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',

@@ -539,7 +539,12 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
                 const double* Gw = sh.Gd + ((s & 1) * SBM_NF + col0) * N * 32 + lane;
                 sbm_ct_cols_stage<CW>(s, h, Jp, Gw, y, s2, s3, V1, V4, rtol, atol, anyinit, sq, d0, d1);
             }
+#ifdef SBM_CT_PRIMAL_REPEAT
+            // experiment: evaluate the share several times to measure how much of the critical path it is
+            if (s < 7) for (int rep = 0; rep < SBM_CT_PRIMAL_REPEAT; ++rep) sbm_ct_primal<W>(sh, warp, lane, s + 1, h);
+#else
             if (s < 7) sbm_ct_primal<W>(sh, warp, lane, s + 1, h);
+#endif
             else {
                 sh.sqb[warp * 32 + lane] = sq;
                 if (anyinit) { V4[0] = d0; V4[32] = d1; }      // S4 is dead once the error norm is formed

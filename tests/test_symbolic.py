@@ -105,3 +105,34 @@ def test_cuda_emitter_structure_and_flop_model():
     assert cs.flops_sens_rhs == cs.flops_fJG + 22 * cs.flops_col + 44
     assert 1200 < cs.flops_sens_rhs < 1500
     assert count_flops([sp.sympify('a*b + c')]) == 2 and count_flops([sp.sympify('a**3/b')]) == 4
+
+
+def test_ct_layout_and_primal_shares_cover_every_output_once():
+    """The CTA-transposed kernel splits the model's primal part (f, nnz J, nnz G) into per-warp shares: every output
+    must be written by exactly one share, into the slot the kernel reads it from."""
+    import re
+    from sysbio_modeling_b200 import model_files
+    from sysbio_modeling_b200.symbolic import symbolic_model_from_file, emit_cuda
+    from sysbio_modeling_b200.symbolic.sympy_tools import ct_layout, ct_share_warps
+    assert ct_layout(8, 22) == (11, 2)          # MAPK: 11 warps x 2 columns
+    assert ct_layout(4, 4) == (1, 4)            # small systems: one thread per trajectory
+    assert ct_layout(25, 10) == (0, 0)          # does not fit: warp-group kernel
+    assert ct_layout(8, 22, cols=3) == (8, 3)
+    assert sorted(ct_share_warps(11, 3)) == [3, 7, 10]
+    for name in ('mapk_kholodenko', 'reversible_mm', 'michaelis_menten'):
+        sm = symbolic_model_from_file(model_files.path(name), name=name)
+        cs = emit_cuda(sm)
+        src = cs.source
+        W = int(re.search(r'#define SBM_CT_W (\d+)', src).group(1))
+        C = int(re.search(r'#define SBM_CT_C (\d+)', src).group(1))
+        assert (W, C) == ct_layout(sm.n_vars, sm.n_free)
+        body = src[src.index('void sbm_primal_share('):]
+        body = body[:body.index('\n}\n')]
+        f_idx = sorted(int(x) for x in re.findall(r'fo\[(\d+) \* 32\] =', body))
+        j_idx = sorted(int(x) for x in re.findall(r'Jo\[(\d+) \* 32\] =', body))
+        g_idx = sorted(int(x) for x in re.findall(r'Go\[(\d+) \* 32\] =', body))
+        assert f_idx == list(range(sm.n_vars))
+        assert j_idx == list(range(cs.nnz_J))
+        # dense G slot = parameter * N + state, one per structural non-zero
+        assert g_idx == sorted(j * sm.n_vars + i for (i, j) in sm.G.keys())
+        assert body.count('case ') == W
