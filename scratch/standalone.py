@@ -11,5 +11,5 @@ cs = emit_cuda(sm)
 H = os.path.join(ROOT, 'sysbio_modeling_b200', 'csrc')
 src = open(os.path.join(H, 'sbm_kernel_args.h')).read() + open(os.path.join(H, 'sbm_device_math.h')).read() + \
     cs.source + open(os.path.join(H, 'kernels', 'sbm_ode_kernels.cuh')).read() + \
-    open(os.path.join(H, 'kernels', 'sbm_dp5_ct.cuh')).read() + '\nSBM_DEFINE_DP5_CT(sbm_dp5_ct, %d, %d)\n' % (W, C) + extra
+    open(os.path.join(H, 'kernels', 'sbm_dp5_ct.cuh')).read() + '\nSBM_DEFINE_DP5_CT(sbm_dp5_ct, %d, %d, %d)\n' % (W, C, int(os.environ.get("XW", "1"))) + extra
 open(out, 'w').write(src)

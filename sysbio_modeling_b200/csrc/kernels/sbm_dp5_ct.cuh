@@ -254,6 +254,7 @@ struct SbmCtShared {
     double* Gd;          // [2][NF*N][32]      dense G (column-major per parameter), structural zeros stay 0
     double* fh;          // [7][N][32]         stage derivatives f_1..f_7 of the state column
     double* yb;          // [N][32]            state y at the start of the step
+    double* Pb;          // [2][N][32]         partial stage values y + h sum_{j<S-1} a_Sj f_j, prepared one iteration ahead
     double* pb;          // [NP][32]           model parameters of each lane's trajectory
     double* sqb;         // [W][32]            partial sums of the squared error norm (per warp); on start-up steps
                          //                    the |y| and |f| partial sums are parked in the first two elements of each warp's S4
@@ -486,25 +487,49 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
     sh.ci[SBM_CT_I_NSTEP * 32 + lane] = (int)nstep_traj;
 }
 
-// this warp's share of the model at the input of stage s (s = 2..7), written into the buffers of stage s
-template <int W>
-__device__ __forceinline__ void sbm_ct_primal(const SbmCtShared& sh, const int warp, const int lane, const int s,
+// Tableau rows without their last entry: the stage value of stage S is prepared one iteration ahead as
+// P_S = y + h sum_{j <= S-2} a_Sj f_j (any warp, see sbm_ct_prepare) and completed by the shares with the newest f
+__constant__ double sbm_dp_ap[8][5] = {
+    {0.0, 0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0, 0.0},
+    {DP_A31, 0.0, 0.0, 0.0, 0.0},
+    {DP_A41, DP_A42, 0.0, 0.0, 0.0},
+    {DP_A51, DP_A52, DP_A53, 0.0, 0.0},
+    {DP_A61, DP_A62, DP_A63, DP_A64, 0.0},
+    {DP_A71, 0.0, DP_A73, DP_A74, DP_A75}};
+
+// this warp's share of the model at the input of stage S (S = 2..7), written into the buffers of stage S
+__device__ __forceinline__ void sbm_ct_primal(const SbmCtShared& sh, const int warp, const int lane, const int S,
                                               const double h)
 {
-    double cf[6];
+    const double ts = fma(sbm_dp_c[S], h, sh.cd[SBM_CT_D_T * 32 + lane]);
+    const double* Pp = (S == 2) ? sh.yb + lane : sh.Pb + (S & 1) * SBM_N * 32 + lane;
+    sbm_primal_share<32>(warp, ts, Pp, sh.fh + (S - 2) * SBM_N * 32 + lane, h * sbm_dp_a[S][S - 2], sh.pb + lane,
+                         sh.Jb + (S & 1) * SBM_NJ * 32 + lane, sh.Gd + (S & 1) * SBM_NF * SBM_N * 32 + lane,
+                         sh.fh + (S - 1) * SBM_N * 32 + lane);
+}
+
+// partial stage values of stage S (3..7) for the state components this warp looks after (any warp can: the state
+// column lives in shared memory); runs one iteration before the shares need them
+template <int WT>
+__device__ __forceinline__ void sbm_ct_prepare(const SbmCtShared& sh, const int warp, const int lane, const int S,
+                                               const double h)
+{
+    double cf[5];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) cf[j] = h * sbm_dp_a[s][j];
-    const double ts = fma(sbm_dp_c[s], h, sh.cd[SBM_CT_D_T * 32 + lane]);
-    sbm_primal_share<32>(warp, ts, sh.yb + lane, sh.fh + lane, cf, sh.pb + lane,
-                         sh.Jb + (s & 1) * SBM_NJ * 32 + lane, sh.Gd + (s & 1) * SBM_NF * SBM_N * 32 + lane,
-                         sh.fh + (s - 1) * SBM_N * 32 + lane);
+    for (int j = 0; j < 5; ++j) cf[j] = h * sbm_dp_ap[S][j];
+    for (int i = warp; i < SBM_N; i += WT) {
+        double v = sh.yb[i * 32 + lane];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) v = fma(cf[j], sh.fh[(j * SBM_N + i) * 32 + lane], v);
+        sh.Pb[((S & 1) * SBM_N + i) * 32 + lane] = v;
+    }
 }
 
 // one warp: CW sensitivity columns + primal share `warp`
-template <int W, int C, int CW>
+template <int W, int C, int CW, int XW>
 __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtShared& sh, const int warp, const int lane)
 {
-    constexpr int N = SBM_N, NT = W * 32;
+    constexpr int N = SBM_N, NT = (W + XW) * 32;
     const int col0 = warp * C;                     // first sensitivity column (free-parameter index) of this warp
     double* V1 = sh.V + (warp * 2 * C * N) * 32 + lane;
     double* V4 = V1 + CW * N * 32;
@@ -521,7 +546,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
     const double rtol = a.rtol, atol = a.atol;
 
     for (;;) {
-        if (warp == 0) sbm_ct_control<W, C, SBM_NF - (W - 1) * C>(a, sh, lane);
+        if (XW == 0 && warp == 0) sbm_ct_control<W, C, SBM_NF - (W - 1) * C>(a, sh, lane);
         SBM_CT_BAR(NT);                            // controller output published
         const int cflags = sh.cta[0];
         if (!(cflags & SBM_CT_ALIVE)) break;
@@ -539,11 +564,12 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
                 const double* Gw = sh.Gd + ((s & 1) * SBM_NF + col0) * N * 32 + lane;
                 sbm_ct_cols_stage<CW>(s, h, Jp, Gw, y, s2, s3, V1, V4, rtol, atol, anyinit, sq, d0, d1);
             }
+            if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
 #ifdef SBM_CT_PRIMAL_REPEAT
             // experiment: evaluate the share several times to measure how much of the critical path it is
-            if (s < 7) for (int rep = 0; rep < SBM_CT_PRIMAL_REPEAT; ++rep) sbm_ct_primal<W>(sh, warp, lane, s + 1, h);
+            if (s < 7) for (int rep = 0; rep < SBM_CT_PRIMAL_REPEAT; ++rep) sbm_ct_primal(sh, warp, lane, s + 1, h);
 #else
-            if (s < 7) sbm_ct_primal<W>(sh, warp, lane, s + 1, h);
+            if (s < 7) sbm_ct_primal(sh, warp, lane, s + 1, h);
 #endif
             else {
                 sh.sqb[warp * 32 + lane] = sq;
@@ -554,15 +580,36 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
     }
 }
 
-// W warps per CTA; warps 0..W-2 carry C sensitivity columns each, warp W-1 the remaining CL = NF - (W-1)*C.
-// Shared-memory carve-up in doubles (sbm_api.cu computes the same size on the host):
-//   2*NJ*32 + 2*NF*N*32 + 7*N*32 + N*32 + NP*32 + W*32 + 32 + ND*32 + 4*32 + 32 + (NI*32 + 3*32)/2
+// a warp without columns: evaluates its share of the model, runs the step controller
+template <int W, int C, int XW>
+__device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const SbmCtShared& sh, const int warp, const int lane)
+{
+    constexpr int NT = (W + XW) * 32;
+    for (;;) {
+        if (warp == W) sbm_ct_control<W, C, SBM_NF - (W - 1) * C>(a, sh, lane);
+        SBM_CT_BAR(NT);
+        if (!(sh.cta[0] & SBM_CT_ALIVE)) break;
+        const double h = sh.hb[lane];
+#pragma unroll 1
+        for (int s = 1; s <= 7; ++s) {
+            if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
+            if (s < 7) sbm_ct_primal(sh, warp, lane, s + 1, h);
+            SBM_CT_BAR(NT);
+        }
+    }
+}
+
+// W column warps per CTA (warps 0..W-2 carry C sensitivity columns each, warp W-1 the remaining
+// CL = NF - (W-1)*C) plus XW warps without columns.  Shared-memory carve-up in doubles (sbm_api.cu computes the same
+// size on the host):
+//   2*NJ*32 + 2*NF*N*32 + 7*N*32 + N*32 + 2*N*32 + NP*32 + W*32 + 32 + ND*32 + 4*32 + 32 + (NI*32 + 3*32)/2
 //   + ((W-1)*C + CL)*2*N*32
-template <int W, int C>
+template <int W, int C, int XW>
 __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
 {
     constexpr int N = SBM_N;
     constexpr int CL = SBM_NF - (W - 1) * C;
+    constexpr int WT = W + XW;
     static_assert(CL >= 1 && CL <= C, "column split does not cover the free parameters");
     extern __shared__ double sbm_dyn[];
     SbmCtShared sh;
@@ -570,7 +617,8 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     sh.Gd = sh.Jb + 2 * SBM_NJ * 32;
     sh.fh = sh.Gd + 2 * SBM_NF * N * 32;
     sh.yb = sh.fh + 7 * N * 32;
-    sh.pb = sh.yb + N * 32;
+    sh.Pb = sh.yb + N * 32;
+    sh.pb = sh.Pb + 2 * N * 32;
     sh.sqb = sh.pb + SBM_NP * 32;
     sh.hb = sh.sqb + W * 32;
     sh.cd = sh.hb + 32;
@@ -585,10 +633,11 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     // ---- one-time initialisation of the shared state ----
-    for (int q = threadIdx.x; q < 2 * SBM_NF * N * 32; q += W * 32) sh.Gd[q] = 0.0;      // structural zeros of G
-    for (int q = threadIdx.x; q < 2 * SBM_NJ * 32; q += W * 32) sh.Jb[q] = 0.0;
-    for (int q = threadIdx.x; q < 7 * N * 32; q += W * 32) sh.fh[q] = 0.0;
-    for (int q = threadIdx.x; q < W * 32; q += W * 32) sh.sqb[q] = 0.0;
+    for (int q = threadIdx.x; q < 2 * SBM_NF * N * 32; q += WT * 32) sh.Gd[q] = 0.0;      // structural zeros of G
+    for (int q = threadIdx.x; q < 2 * SBM_NJ * 32; q += WT * 32) sh.Jb[q] = 0.0;
+    for (int q = threadIdx.x; q < 7 * N * 32; q += WT * 32) sh.fh[q] = 0.0;
+    for (int q = threadIdx.x; q < 2 * N * 32; q += WT * 32) sh.Pb[q] = 0.0;
+    for (int q = threadIdx.x; q < W * 32; q += WT * 32) sh.sqb[q] = 0.0;
     if (warp == 0) {
         for (int i = 0; i < N; ++i) sh.yb[i * 32 + lane] = 0.0;
         for (int m = 0; m < SBM_NP; ++m) sh.pb[m * 32 + lane] = 1.0;
@@ -602,12 +651,14 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
         sh.ktb[lane] = 0;
         sh.cta[lane] = 0;
     }
-    SBM_CT_BAR(W * 32);
+    SBM_CT_BAR(WT * 32);
 
-    if (warp == W - 1 && CL != C) sbm_ct_warp<W, C, CL>(a, sh, warp, lane);
-    else sbm_ct_warp<W, C, C>(a, sh, warp, lane);
+    if (XW > 0 && warp >= W) sbm_ct_model_warp<W, C, XW>(a, sh, warp, lane);
+    else if (warp == W - 1 && CL != C) sbm_ct_warp<W, C, CL, XW>(a, sh, warp, lane);
+    else sbm_ct_warp<W, C, C, XW>(a, sh, warp, lane);
 
     // ---- counters: one atomic per CTA ----
+    SBM_CT_BAR(WT * 32);
     if (warp == 0) {
         unsigned long long v[4];
 #pragma unroll
@@ -625,6 +676,6 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     }
 }
 
-#define SBM_DEFINE_DP5_CT(NAME, W, C)                                                                   \
-    extern "C" __global__ void __launch_bounds__((W) * 32, 1) NAME(const SbmSolveArgs a)                \
-    { sbm_dp5_ct_impl<W, C>(a); }
+#define SBM_DEFINE_DP5_CT(NAME, W, C, XW)                                                               \
+    extern "C" __global__ void __launch_bounds__(((W) + (XW)) * 32, 1) NAME(const SbmSolveArgs a)       \
+    { sbm_dp5_ct_impl<W, C, XW>(a); }

@@ -138,7 +138,7 @@ struct sbm_model {
     int G = 1, C = 1, block = 128, block_plain = 128;
     int dyn_smem = 0, dyn_smem_plain = 0;
     // CTA-transposed sensitivity kernel (kernels/sbm_dp5_ct.cuh): W sensitivity warps x C columns + 1 state warp
-    int ctW = 0, ctC = 0, ctCS = 0, ct_dyn_smem = 0, ct_ctas_per_sm = 0, sm_count = 0;
+    int ctW = 0, ctC = 0, ctCS = 0, ctXW = 0, ct_dyn_smem = 0, ct_ctas_per_sm = 0, sm_count = 0;
     bool ct_ok = false;
     int layout = 0;              // 0 auto, 1 lane-per-column groups, 2 CTA-transposed
     std::string source;          // full NVRTC translation unit (kept for diagnostics)
@@ -216,20 +216,21 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     m->layout = desc->sens_layout > 0 ? desc->sens_layout : 0;
     {
         const int N = desc->n_vars, NF = desc->n_free;
-        int NJ = 1, NG = 1, W = 0, C = 0;
+        int NJ = 1, NG = 1, W = 0, C = 0, XW = 0;
         const char* q;
         if ((q = strstr(model_src, "#define SBM_NJ "))) NJ = atoi(q + 15);
         if ((q = strstr(model_src, "#define SBM_NG "))) NG = atoi(q + 15);
         if ((q = strstr(model_src, "#define SBM_CT_W "))) W = atoi(q + 17);
         if ((q = strstr(model_src, "#define SBM_CT_C "))) C = atoi(q + 17);
+        if ((q = strstr(model_src, "#define SBM_CT_XW "))) XW = atoi(q + 18);
         (void)NG;
         if (W >= 1 && C >= 1 && NF >= 1) {
             const int CL = NF - (W - 1) * C;
-            const long long bytes = 8ll * (2 * NJ * 32 + 2 * NF * N * 32 + 7 * N * 32 + N * 32 + desc->n_params * 32 +
+            const long long bytes = 8ll * (2 * NJ * 32 + 2 * NF * N * 32 + 7 * N * 32 + N * 32 + 2 * N * 32 + desc->n_params * 32 +
                                            W * 32 + 32 + 6 * 32 + 4 * 32 + 32) +
                                     4ll * (8 * 32 + 3 * 32) + 8ll * ((W - 1) * C + CL) * 2 * N * 32;
-            if (CL >= 1 && CL <= C && CL * N >= 2 && W <= 32 && bytes <= 227 * 1024) {
-                m->ctW = W; m->ctC = C; m->ctCS = CL; m->ct_dyn_smem = (int)bytes; m->ct_ok = true;
+            if (CL >= 1 && CL <= C && CL * N >= 2 && W + XW <= 32 && bytes <= 227 * 1024) {
+                m->ctW = W; m->ctC = C; m->ctCS = CL; m->ctXW = XW; m->ct_dyn_smem = (int)bytes; m->ct_ok = true;
             }
         }
         if (m->layout == 2 && !m->ct_ok) { delete m; return fail(SBM_E_INVALID, "CTA-transposed layout does not fit this model"); }
@@ -237,7 +238,7 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
 
     std::ostringstream src;
     src << sbm_embedded_args_header << "\n" << model_src << "\n" << sbm_embedded_kernels << "\n";
-    if (m->ct_ok) src << "SBM_DEFINE_DP5_CT(sbm_dp5_ct, " << m->ctW << ", " << m->ctC << ")\n";
+    if (m->ct_ok) src << "SBM_DEFINE_DP5_CT(sbm_dp5_ct, " << m->ctW << ", " << m->ctC << ", " << m->ctXW << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_plain, 1, 1, 0, " << m->block_plain << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_sens, " << m->G << ", " << m->C << ", 1, " << m->block << ")\n";
     src << "SBM_DEFINE_RODAS4(sbm_rodas4_plain, " << m->block_plain << ")\n";
@@ -334,7 +335,7 @@ static int ensure_loaded(sbm_model* m)
         int dev = 0;
         RT(cudaGetDevice(&dev));
         RT(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DRV(driver().cuOccupancy_(&m->ct_ctas_per_sm, m->dp5_ct.fn, m->ctW * 32, (size_t)m->ct_dyn_smem));
+        DRV(driver().cuOccupancy_(&m->ct_ctas_per_sm, m->dp5_ct.fn, (m->ctW + m->ctXW) * 32, (size_t)m->ct_dyn_smem));
         if (m->ct_ctas_per_sm < 1) m->ct_ok = false;
     }
     m->loaded = true;
@@ -356,7 +357,7 @@ extern "C" int sbm_model_info(sbm_model* m, sbm_model_info_t* o)
     o->smem_dp5_plain = m->dp5_plain.smem; o->smem_dp5_sens = m->dp5_sens.smem; o->smem_rodas4 = m->rodas4.smem;
     o->cubin_bytes = (int)m->cubin.size();
     o->from_cache = m->from_cache ? 1 : 0;
-    o->ct_warps = m->ct_ok ? m->ctW : 0; o->ct_cols = m->ct_ok ? m->ctC : 0; o->ct_cols_state = m->ct_ok ? m->ctCS : 0;
+    o->ct_warps = m->ct_ok ? m->ctW + m->ctXW : 0; o->ct_cols = m->ct_ok ? m->ctC : 0; o->ct_cols_state = m->ct_ok ? m->ctCS : 0;
     o->ct_dyn_smem_bytes = m->ct_dyn_smem; o->ct_ctas_per_sm = m->ct_ctas_per_sm;
     o->regs_dp5_ct = m->dp5_ct.regs; o->local_dp5_ct = m->dp5_ct.local; o->smem_dp5_ct = m->dp5_ct.smem;
     o->sens_layout = (m->layout == 1 || !m->ct_ok) ? 1 : 2;
@@ -494,7 +495,7 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
     if (o->solver == SBM_SOLVER_RODAS4) { ks = &m->rodas4; threads = ntraj; }
     else if (jac && m->ct_ok && m->layout != 1) {
         // persistent CTAs, 32 trajectories in flight each, refilled from a global queue
-        ks = &m->dp5_ct; block = m->ctW * 32; dyn = m->ct_dyn_smem; threads = 0;
+        ks = &m->dp5_ct; block = (m->ctW + m->ctXW) * 32; dyn = m->ct_dyn_smem; threads = 0;
         blocks = (ntraj + 31) / 32;
         const long long resident = (long long)m->sm_count * m->ct_ctas_per_sm;
         if (blocks > resident) blocks = resident;

@@ -567,7 +567,7 @@ def _instr_cost(e):
     return c
 
 
-def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms):
+def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0):
     """Split the model's primal part - f, the non-zeros of J = df/dy and of G = df/dp - into W shares, one per
     warp of the CTA-transposed kernel.  Each share is straight-line code that recomputes the sub-expressions it
     needs (a share that owns several outputs of one rate law computes its reciprocal once), reads only the stage
@@ -603,18 +603,20 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms):
     nnzJ = len(J_x)
     import os as _os
     n_shares = int(_os.environ.get('SBM_CT_SHARES', '0')) or min(W, 3)
-    share_warps = [int(x) for x in _os.environ.get('SBM_CT_SHARE_WARPS', '').split(',') if x.strip()] or \
-        ct_share_warps(W, n_shares)
+    WT = W + XW                                 # XW warps carry no columns: they only evaluate the model
+    share_warps = [int(x) for x in _os.environ.get('SBM_CT_SHARE_WARPS', '').split(',') if x.strip()]
+    if not share_warps:
+        share_warps = list(range(W, WT)) + [w for w in ct_share_warps(WT, n_shares + XW) if w < W][:n_shares - XW]
     loads = []
-    for w in range(W):
-        real = max(0, min(C, NF - w * C))
-        loads.append(float(nnzJ + real * (nnzJ + 12 * N)) + (60.0 if w == 0 else 0.0) +
+    for w in range(WT):
+        real = max(0, min(C, NF - w * C)) if w < W else 0
+        loads.append((float(nnzJ + real * (nnzJ + 12 * N)) if real else 0.0) + (60.0 if w == 0 else 0.0) +
                      (0.0 if w in share_warps else 1e9))
-    have = [set() for _ in range(W)]
-    mine = [[] for _ in range(W)]
-    ycomp = [set() for _ in range(W)]
+    have = [set() for _ in range(WT)]
+    mine = [[] for _ in range(WT)]
+    ycomp = [set() for _ in range(WT)]
     yset = set(ysyms)
-    Y_COST = 12                                 # 6 LDS + 6 FMA to form the stage value of one state
+    Y_COST = 3                                  # 2 LDS + 1 FMA to form the stage value of one state
 
     def ys_of(e, cl):
         out = set(x for x in e.free_symbols if x in yset)
@@ -668,14 +670,15 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms):
     L.append('// primal shares of the CTA-transposed kernel: estimated instructions per warp = %s'
              % ', '.join('%d' % int(v) for v in loads))
     L.append('template <int PS>')
+    L.append('// Pp: partial stage value y + h sum_{j<s} a_{s+1,j} f_j (prepared one iteration earlier), fl: f_s, cl = h a_{s+1,s}')
     L.append('__device__ __forceinline__ void sbm_primal_share(const int share, const double t,')
-    L.append('        const double* __restrict__ yb, const double* __restrict__ fh, const double (&cf)[6],')
+    L.append('        const double* __restrict__ Pp, const double* __restrict__ fl, const double cl,')
     L.append('        const double* __restrict__ p, double* __restrict__ Jo, double* __restrict__ Go,')
     L.append('        double* __restrict__ fo)')
     L.append('{')
     L.append('    switch (share) {')
     ypat = {str(sy): i for i, sy in enumerate(ysyms)}
-    for w in range(W):
+    for w in range(WT):
         L.append('    case %d: {' % w)
         need_syms = set()
         for x in have[w]:
@@ -684,11 +687,8 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms):
             need_syms |= e.free_symbols
         need = sorted(ypat[str(x)] for x in need_syms if str(x) in ypat)
         for i in need:
-            # stage value of state i:  y_i + sum_j cf[j] f_j[i]   (cf[j] = h a_sj, zero beyond the stage)
-            acc = 'yb[%d * 32]' % i
-            for j in range(6):
-                acc = 'fma(cf[%d], fh[%d * 32], %s)' % (j, j * N + i, acc)
-            L.append('        const double Y%d = %s;' % (i, acc))
+            # stage value of state i = prepared partial sum + the newest stage derivative
+            L.append('        const double Y%d = fma(cl, fl[%d * 32], Pp[%d * 32]);' % (i, i, i))
         body = []
         for k in rsym:
             if k in have[w]:
@@ -830,11 +830,18 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
         L.append('    }')
     L.append('}')
     W_ct, C_ct = ct_layout(N, NF, ct_cols)
+    import os as _os
+    # one extra warp without columns (it only evaluates the model) when that keeps the register budget:
+    # 9..11 column warps + 1 = at most 12 warps = 168 registers per thread, as without it
+    XW_ct = 1 if 9 <= W_ct <= 11 else 0
+    if 'SBM_CT_XW' in _os.environ:
+        XW_ct = int(_os.environ['SBM_CT_XW']) if W_ct else 0
     L.append('#define SBM_CT_W %d' % W_ct)
     L.append('#define SBM_CT_C %d' % C_ct)
+    L.append('#define SBM_CT_XW %d' % XW_ct)
     if W_ct:
         ysyms = [sp.Symbol('y[%d]' % i, real=True) for i in range(N)]
-        _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms)
+        _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct)
 
     # --- dense Jacobian (row-major Jd[i*N+k]) and df/dt for the Rosenbrock kernel
     rep, red = sp.cse(J_x, symbols=sp.numbered_symbols('c_'), optimizations='basic')

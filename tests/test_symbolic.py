@@ -135,4 +135,5 @@ def test_ct_layout_and_primal_shares_cover_every_output_once():
         assert j_idx == list(range(cs.nnz_J))
         # dense G slot = parameter * N + state, one per structural non-zero
         assert g_idx == sorted(j * sm.n_vars + i for (i, j) in sm.G.keys())
-        assert body.count('case ') == W
+        XW = int(re.search(r'#define SBM_CT_XW (\d+)', src).group(1))
+        assert body.count('case ') == W + XW
