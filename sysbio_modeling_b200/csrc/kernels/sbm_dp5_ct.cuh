@@ -119,7 +119,7 @@ __device__ __forceinline__ void sbm_ct_update(const double kk, const double h, c
 
 // -------------------------------------------------------------------------------------------------
 // one stage on CW sensitivity columns of 32 trajectories.  Gw points at this warp's first column of the
-// dense G buffer: the entry of (column c, state i) sits at Gw[(c*N + i)*32], structural zeros hold 0.
+// dense G buffer: the entry of (column c, state i) sits at Gw[SBM_GIDX(c*NE + i)], structural zeros hold 0.
 // -------------------------------------------------------------------------------------------------
 template <int S, int CW>
 __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* __restrict__ Jp,
@@ -138,28 +138,57 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
             const double v1 = (S <= 5) ? V1[(c * N + i) * 32] : 0.0;
             w[c][i] = sbm_ct_input<S>(h, y[c][i], v1, s2[c][i], s3[c][i]);
         }
+    // rows are processed SBM_CT_ROWS at a time: that many independent FMA chains per column hide the FP64 and
+    // shared-memory latencies that a single row exposes (2 warps x 2 columns per scheduler are not enough)
+#ifndef SBM_CT_ROWS
+#define SBM_CT_ROWS 2
+#endif
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        double acc[CW];
+    for (int i0 = 0; i0 < N; i0 += SBM_CT_ROWS) {
+        double acc[SBM_CT_ROWS][CW];
 #pragma unroll
-        for (int c = 0; c < CW; ++c) acc[c] = Gw[(c * N + i) * 32];
-        sbm_jrow<CW>(i, Jp, w, acc);
+        for (int r = 0; r < SBM_CT_ROWS; ++r)
+#pragma unroll
+            for (int c = 0; c < CW; ++c) acc[r][c] = 0.0;
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
-            double v1 = 0.0, v4 = 0.0;
-            if (S == 4) v1 = V1[(c * N + i) * 32];
-            if (S >= 5) v4 = V4[(c * N + i) * 32];
-            sbm_ct_update<S>(acc[c], h, y[c][i], v1, s2[c][i], s3[c][i], v4);
-            if (S == 4 || S == 7) V1[(c * N + i) * 32] = v1;
-            if (S >= 4 && S <= 6) V4[(c * N + i) * 32] = v4;
-            if (S == 7) {
-                const double isk = sbm_rcp_fast(fma(rtol, fmax(fabs(y[c][i]), fabs(s3[c][i])), atol));
-                const double q = v4 * isk;
-                sq = fma(q, q, sq);
-                if (anyinit) {
-                    const double q0 = y[c][i] * isk, q1 = acc[c] * isk;
-                    d0 = fma(q0, q0, d0);
-                    d1 = fma(q1, q1, d1);
+            // dense G, two states of a row pair per 128-bit load (layout: SBM_GIDX in the model source)
+            constexpr int NE = N + (N & 1);
+            if (SBM_CT_ROWS == 2 && i0 + 1 < N) {
+                const double2 g2 = *reinterpret_cast<const double2*>(Gw + SBM_GIDX(c * NE + i0));
+                acc[0][c] = g2.x;
+                acc[SBM_CT_ROWS - 1][c] = g2.y;
+            } else {
+#pragma unroll
+                for (int r = 0; r < SBM_CT_ROWS; ++r)
+                    if (i0 + r < N) acc[r][c] = Gw[SBM_GIDX(c * NE + i0 + r)];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SBM_CT_ROWS; ++r)
+            if (i0 + r < N) sbm_jrow<CW>(i0 + r, Jp, w, acc[r]);
+#pragma unroll
+        for (int r = 0; r < SBM_CT_ROWS; ++r) {
+            const int i = i0 + r;
+            if (i < N) {
+#pragma unroll
+                for (int c = 0; c < CW; ++c) {
+                    double v1 = 0.0, v4 = 0.0;
+                    if (S == 4) v1 = V1[(c * N + i) * 32];
+                    if (S >= 5) v4 = V4[(c * N + i) * 32];
+                    sbm_ct_update<S>(acc[r][c], h, y[c][i], v1, s2[c][i], s3[c][i], v4);
+                    if (S == 4 || S == 7) V1[(c * N + i) * 32] = v1;
+                    if (S >= 4 && S <= 6) V4[(c * N + i) * 32] = v4;
+                    if (S == 7) {
+                        const double isk = sbm_rcp_fast(fma(rtol, fmax(fabs(y[c][i]), fabs(s3[c][i])), atol));
+                        const double q = v4 * isk;
+                        sq = fma(q, q, sq);
+                        if (anyinit) {
+                            const double q0 = y[c][i] * isk, q1 = acc[r][c] * isk;
+                            d0 = fma(q0, q0, d0);
+                            d1 = fma(q1, q1, d1);
+                        }
+                    }
                 }
             }
         }
@@ -251,12 +280,14 @@ __device__ __forceinline__ void sbm_ct_cols_stage(const int s, const double h, c
 // shared-memory views of one CTA
 struct SbmCtShared {
     double* Jb;          // [2][NJ][32]        J of the stage being consumed / produced
-    double* Gd;          // [2][NF*N][32]      dense G (column-major per parameter), structural zeros stay 0
+    double* Gd;          // [2][NF*NE/2][32][2] dense G (column-major per parameter, row pairs adjacent), zeros stay 0
     double* fh;          // [7][N][32]         stage derivatives f_1..f_7 of the state column
     double* yb;          // [N][32]            state y at the start of the step
+    double* ynb;         // [N][32]            5th-order state of the step just taken (prepared by the model warp)
     double* Pb;          // [2][N][32]         partial stage values y + h sum_{j<S-1} a_Sj f_j, prepared one iteration ahead
     double* pb;          // [NP][32]           model parameters of each lane's trajectory
-    double* sqb;         // [W][32]            partial sums of the squared error norm (per warp); on start-up steps
+    double* sqb;         // [W+3][32]          partial sums of the squared error norm (per column warp), then the state
+                         //                    column's error / |y| / |f| sums; on start-up steps
                          //                    the |y| and |f| partial sums are parked in the first two elements of each warp's S4
     double* hb;          // [32]               step of each lane (0: zero-length step / idle)
     double* cd;          // [SBM_CT_ND][32]    controller doubles
@@ -272,7 +303,31 @@ struct SbmCtShared {
 // -------------------------------------------------------------------------------------------------
 // step controller, trajectory queue and the state column (warp 0, one lane per trajectory)
 // -------------------------------------------------------------------------------------------------
-template <int W, int C, int CL>
+// 5th-order solution, embedded error and start-up norms of the state column from its stage derivatives f_1..f_7
+__device__ __forceinline__ void sbm_ct_state_column(const SbmCtShared& sh, const int lane, const double hdone,
+                                                    const double rtol, const double atol, double (&ynew)[SBM_N],
+                                                    double (&f7)[SBM_N], double& sq, double& q0, double& q1)
+{
+    constexpr int N = SBM_N;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double f1 = sh.fh[(0 * N + i) * 32 + lane], f3 = sh.fh[(2 * N + i) * 32 + lane];
+        const double f4 = sh.fh[(3 * N + i) * 32 + lane], f5 = sh.fh[(4 * N + i) * 32 + lane];
+        const double f6 = sh.fh[(5 * N + i) * 32 + lane];
+        f7[i] = sh.fh[(6 * N + i) * 32 + lane];
+        const double yi = sh.yb[i * 32 + lane];
+        ynew[i] = fma(hdone, fma(DP_A76, f6, fma(DP_A75, f5, fma(DP_A74, f4, fma(DP_A73, f3, DP_A71 * f1)))), yi);
+        const double er = hdone * fma(DP_E7, f7[i], fma(DP_E6, f6, fma(DP_E5, f5, fma(DP_E4, f4,
+                                  fma(DP_E3, f3, DP_E1 * f1)))));
+        const double isk = sbm_rcp_fast(fma(rtol, fmax(fabs(yi), fabs(ynew[i])), atol));
+        const double q = er * isk, u0 = yi * isk, u1 = f7[i] * isk;
+        sq = fma(q, q, sq);
+        q0 = fma(u0, u0, q0);
+        q1 = fma(u1, u1, q1);
+    }
+}
+
+template <int W, int C, int CL, int PRE>
 __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane)
 {
     constexpr int N = SBM_N;
@@ -301,21 +356,17 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
 #pragma unroll
         for (int w = 0; w < W; ++w) sq += sh.sqb[w * 32 + lane];
         double ynew[N], f7[N];
+        if (PRE) {
+            // prepared by the model warp while the column warps were busy with stage 7
+            sq += sh.sqb[(W + 0) * 32 + lane];
+            q0 = sh.sqb[(W + 1) * 32 + lane];
+            q1 = sh.sqb[(W + 2) * 32 + lane];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double f1 = sh.fh[(0 * N + i) * 32 + lane], f3 = sh.fh[(2 * N + i) * 32 + lane];
-            const double f4 = sh.fh[(3 * N + i) * 32 + lane], f5 = sh.fh[(4 * N + i) * 32 + lane];
-            const double f6 = sh.fh[(5 * N + i) * 32 + lane];
-            f7[i] = sh.fh[(6 * N + i) * 32 + lane];
-            const double yi = sh.yb[i * 32 + lane];
-            ynew[i] = fma(hdone, fma(DP_A76, f6, fma(DP_A75, f5, fma(DP_A74, f4, fma(DP_A73, f3, DP_A71 * f1)))), yi);
-            const double er = hdone * fma(DP_E7, f7[i], fma(DP_E6, f6, fma(DP_E5, f5, fma(DP_E4, f4,
-                                      fma(DP_E3, f3, DP_E1 * f1)))));
-            const double isk = sbm_rcp_fast(fma(rtol, fmax(fabs(yi), fabs(ynew[i])), atol));
-            const double q = er * isk, u0 = yi * isk, u1 = f7[i] * isk;
-            sq = fma(q, q, sq);
-            q0 = fma(u0, u0, q0);
-            q1 = fma(u1, u1, q1);
+            for (int i = 0; i < N; ++i) { ynew[i] = sh.ynb[i * 32 + lane]; f7[i] = sh.fh[(6 * N + i) * 32 + lane]; }
+        } else {
+            double sqs = 0.0;
+            sbm_ct_state_column(sh, lane, hdone, rtol, atol, ynew, f7, sqs, q0, q1);
+            sq += sqs;
         }
         const double err = sqrt(sq * inv_naug);
         bool fsal = false;
@@ -503,9 +554,16 @@ __device__ __forceinline__ void sbm_ct_primal(const SbmCtShared& sh, const int w
 {
     const double ts = fma(sbm_dp_c[S], h, sh.cd[SBM_CT_D_T * 32 + lane]);
     const double* Pp = (S == 2) ? sh.yb + lane : sh.Pb + (S & 1) * SBM_N * 32 + lane;
-    sbm_primal_share<32>(warp, ts, Pp, sh.fh + (S - 2) * SBM_N * 32 + lane, h * sbm_dp_a[S][S - 2], sh.pb + lane,
-                         sh.Jb + (S & 1) * SBM_NJ * 32 + lane, sh.Gd + (S & 1) * SBM_NF * SBM_N * 32 + lane,
-                         sh.fh + (S - 1) * SBM_N * 32 + lane);
+    // stage 2 is the head of the step: its step size exists only after the previous step has been judged, so it
+    // overlaps with nothing and is split over more warps (sbm_primal_head) than the stages that run one ahead
+    if (S == 2)
+        sbm_primal_head<32>(warp, ts, Pp, sh.fh + lane, h * DP_A21, sh.pb + lane, sh.Jb + lane, sh.Gd + 2 * lane,
+                            sh.fh + SBM_N * 32 + lane);
+    else
+        sbm_primal_share<32>(warp, ts, Pp, sh.fh + (S - 2) * SBM_N * 32 + lane, h * sbm_dp_a[S][S - 2], sh.pb + lane,
+                             sh.Jb + (S & 1) * SBM_NJ * 32 + lane,
+                             sh.Gd + (S & 1) * SBM_NF * (SBM_N + (SBM_N & 1)) * 32 + 2 * lane,
+                             sh.fh + (S - 1) * SBM_N * 32 + lane);
 }
 
 // partial stage values of stage S (3..7) for the state components this warp looks after (any warp can: the state
@@ -546,7 +604,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
     const double rtol = a.rtol, atol = a.atol;
 
     for (;;) {
-        if (XW == 0 && warp == 0) sbm_ct_control<W, C, SBM_NF - (W - 1) * C>(a, sh, lane);
+        if (XW == 0 && warp == 0) sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 0>(a, sh, lane);
         SBM_CT_BAR(NT);                            // controller output published
         const int cflags = sh.cta[0];
         if (!(cflags & SBM_CT_ALIVE)) break;
@@ -561,7 +619,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
         for (int s = 1; s <= 7; ++s) {
             if (s >= 2) {
                 const double* Jp = sh.Jb + (s & 1) * SBM_NJ * 32 + lane;
-                const double* Gw = sh.Gd + ((s & 1) * SBM_NF + col0) * N * 32 + lane;
+                const double* Gw = sh.Gd + ((s & 1) * SBM_NF + col0) * (N + (N & 1)) * 32 + 2 * lane;
                 sbm_ct_cols_stage<CW>(s, h, Jp, Gw, y, s2, s3, V1, V4, rtol, atol, anyinit, sq, d0, d1);
             }
             if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
@@ -586,7 +644,7 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
 {
     constexpr int NT = (W + XW) * 32;
     for (;;) {
-        if (warp == W) sbm_ct_control<W, C, SBM_NF - (W - 1) * C>(a, sh, lane);
+        if (warp == W) sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 1>(a, sh, lane);
         SBM_CT_BAR(NT);
         if (!(sh.cta[0] & SBM_CT_ALIVE)) break;
         const double h = sh.hb[lane];
@@ -594,6 +652,16 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
         for (int s = 1; s <= 7; ++s) {
             if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
             if (s < 7) sbm_ct_primal(sh, warp, lane, s + 1, h);
+            else if (warp == W) {
+                // while the column warps finish stage 7: the state column's part of the controller's input
+                double ynew[SBM_N], f7[SBM_N], sqs = 0.0, q0 = 0.0, q1 = 0.0;
+                sbm_ct_state_column(sh, lane, h, a.rtol, a.atol, ynew, f7, sqs, q0, q1);
+#pragma unroll
+                for (int i = 0; i < SBM_N; ++i) sh.ynb[i * 32 + lane] = ynew[i];
+                sh.sqb[(W + 0) * 32 + lane] = sqs;
+                sh.sqb[(W + 1) * 32 + lane] = q0;
+                sh.sqb[(W + 2) * 32 + lane] = q1;
+            }
             SBM_CT_BAR(NT);
         }
     }
@@ -602,7 +670,7 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
 // W column warps per CTA (warps 0..W-2 carry C sensitivity columns each, warp W-1 the remaining
 // CL = NF - (W-1)*C) plus XW warps without columns.  Shared-memory carve-up in doubles (sbm_api.cu computes the same
 // size on the host):
-//   2*NJ*32 + 2*NF*N*32 + 7*N*32 + N*32 + 2*N*32 + NP*32 + W*32 + 32 + ND*32 + 4*32 + 32 + (NI*32 + 3*32)/2
+//   2*NJ*32 + 2*NF*NE*32 + 7*N*32 + 2*N*32 + 2*N*32 + NP*32 + (W+3)*32 + 32 + ND*32 + 4*32 + 32 + (NI*32 + 3*32)/2
 //   + ((W-1)*C + CL)*2*N*32
 template <int W, int C, int XW>
 __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
@@ -615,12 +683,13 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     SbmCtShared sh;
     sh.Jb = sbm_dyn;
     sh.Gd = sh.Jb + 2 * SBM_NJ * 32;
-    sh.fh = sh.Gd + 2 * SBM_NF * N * 32;
+    sh.fh = sh.Gd + 2 * SBM_NF * (N + (N & 1)) * 32;
     sh.yb = sh.fh + 7 * N * 32;
-    sh.Pb = sh.yb + N * 32;
+    sh.ynb = sh.yb + N * 32;
+    sh.Pb = sh.ynb + N * 32;
     sh.pb = sh.Pb + 2 * N * 32;
     sh.sqb = sh.pb + SBM_NP * 32;
-    sh.hb = sh.sqb + W * 32;
+    sh.hb = sh.sqb + (W + 3) * 32;
     sh.cd = sh.hb + 32;
     sh.cnt = (unsigned long long*)(sh.cd + SBM_CT_ND * 32);
     sh.trj = (long long*)(sh.cnt + 4 * 32);
@@ -633,11 +702,12 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     // ---- one-time initialisation of the shared state ----
-    for (int q = threadIdx.x; q < 2 * SBM_NF * N * 32; q += WT * 32) sh.Gd[q] = 0.0;      // structural zeros of G
+    for (int q = threadIdx.x; q < 2 * SBM_NF * (N + (N & 1)) * 32; q += WT * 32) sh.Gd[q] = 0.0;   // structural zeros of G
     for (int q = threadIdx.x; q < 2 * SBM_NJ * 32; q += WT * 32) sh.Jb[q] = 0.0;
     for (int q = threadIdx.x; q < 7 * N * 32; q += WT * 32) sh.fh[q] = 0.0;
     for (int q = threadIdx.x; q < 2 * N * 32; q += WT * 32) sh.Pb[q] = 0.0;
-    for (int q = threadIdx.x; q < W * 32; q += WT * 32) sh.sqb[q] = 0.0;
+    for (int q = threadIdx.x; q < (W + 3) * 32; q += WT * 32) sh.sqb[q] = 0.0;
+    for (int q = threadIdx.x; q < N * 32; q += WT * 32) sh.ynb[q] = 0.0;
     if (warp == 0) {
         for (int i = 0; i < N; ++i) sh.yb[i * 32 + lane] = 0.0;
         for (int m = 0; m < SBM_NP; ++m) sh.pb[m * 32 + lane] = 1.0;

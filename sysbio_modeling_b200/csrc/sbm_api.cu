@@ -226,8 +226,8 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
         (void)NG;
         if (W >= 1 && C >= 1 && NF >= 1) {
             const int CL = NF - (W - 1) * C;
-            const long long bytes = 8ll * (2 * NJ * 32 + 2 * NF * N * 32 + 7 * N * 32 + N * 32 + 2 * N * 32 + desc->n_params * 32 +
-                                           W * 32 + 32 + 6 * 32 + 4 * 32 + 32) +
+            const long long bytes = 8ll * (2 * NJ * 32 + 2 * NF * (N + (N & 1)) * 32 + 7 * N * 32 + 2 * N * 32 + 2 * N * 32 + desc->n_params * 32 +
+                                           (W + 3) * 32 + 32 + 6 * 32 + 4 * 32 + 32) +
                                     4ll * (8 * 32 + 3 * 32) + 8ll * ((W - 1) * C + CL) * 2 * N * 32;
             if (CL >= 1 && CL <= C && CL * N >= 2 && W + XW <= 32 && bytes <= 227 * 1024) {
                 m->ctW = W; m->ctC = C; m->ctCS = CL; m->ctXW = XW; m->ct_dyn_smem = (int)bytes; m->ct_ok = true;

@@ -567,7 +567,8 @@ def _instr_cost(e):
     return c
 
 
-def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0):
+def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0, fname='sbm_primal_share',
+                        n_shares=None, head=False):
     """Split the model's primal part - f, the non-zeros of J = df/dy and of G = df/dp - into W shares, one per
     warp of the CTA-transposed kernel.  Each share is straight-line code that recomputes the sub-expressions it
     needs (a share that owns several outputs of one rate law computes its reciprocal once), reads only the stage
@@ -602,16 +603,19 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0):
     # updates and their loads/stores; warp 0 also runs the step controller
     nnzJ = len(J_x)
     import os as _os
-    n_shares = int(_os.environ.get('SBM_CT_SHARES', '0')) or min(W, 3)
+    if n_shares is None:
+        n_shares = int(_os.environ.get('SBM_CT_SHARES', '0')) or (1 if XW else min(W, 3))
     WT = W + XW                                 # XW warps carry no columns: they only evaluate the model
-    share_warps = [int(x) for x in _os.environ.get('SBM_CT_SHARE_WARPS', '').split(',') if x.strip()]
+    share_warps = [int(x) for x in _os.environ.get('SBM_CT_SHARE_WARPS', '').split(',') if x.strip()] \
+        if not head else []
     if not share_warps:
-        share_warps = list(range(W, WT)) + [w for w in ct_share_warps(WT, n_shares + XW) if w < W][:n_shares - XW]
+        share_warps = list(range(W, WT)) + [w for w in ct_share_warps(WT, n_shares + XW) if w < W][:max(n_shares - XW, 0)]
     loads = []
     for w in range(WT):
         real = max(0, min(C, NF - w * C)) if w < W else 0
-        loads.append((float(nnzJ + real * (nnzJ + 12 * N)) if real else 0.0) + (60.0 if w == 0 else 0.0) +
-                     (0.0 if w in share_warps else 1e9))
+        # head = the model at the input of stage 2, evaluated while the column warps have nothing else to do
+        base = 0.0 if head else ((float(nnzJ + real * (nnzJ + 12 * N)) if real else 0.0) + (60.0 if w == 0 else 0.0))
+        loads.append(base + (0.0 if w in share_warps else 1e9))
     have = [set() for _ in range(WT)]
     mine = [[] for _ in range(WT)]
     ycomp = [set() for _ in range(WT)]
@@ -671,7 +675,7 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0):
              % ', '.join('%d' % int(v) for v in loads))
     L.append('template <int PS>')
     L.append('// Pp: partial stage value y + h sum_{j<s} a_{s+1,j} f_j (prepared one iteration earlier), fl: f_s, cl = h a_{s+1,s}')
-    L.append('__device__ __forceinline__ void sbm_primal_share(const int share, const double t,')
+    L.append('__device__ __forceinline__ void %s(const int share, const double t,' % fname)
     L.append('        const double* __restrict__ Pp, const double* __restrict__ fl, const double cl,')
     L.append('        const double* __restrict__ p, double* __restrict__ Jo, double* __restrict__ Go,')
     L.append('        double* __restrict__ fo)')
@@ -700,7 +704,7 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0):
                 body.append('        Jo[%d * 32] = %s;' % (idx, pr.doprint(e)))
             else:
                 i, j = gkeys[idx]
-                body.append('        Go[%d * 32] = %s;' % (j * N + i, pr.doprint(e)))
+                body.append('        Go[SBM_GIDX(%d)] = %s;' % (j * (N + (N & 1)) + i, pr.doprint(e)))
         import re as _re
         for ln in body:
             ln = _re.sub(r'p\[(\d+)\]', r'p[\1 * PS]', ln)
@@ -836,12 +840,21 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     XW_ct = 1 if 9 <= W_ct <= 11 else 0
     if 'SBM_CT_XW' in _os.environ:
         XW_ct = int(_os.environ['SBM_CT_XW']) if W_ct else 0
+    L.append('// dense G of the CTA-transposed kernel: element e = parameter * NE + state (NE = N rounded up to even) lives')
+    L.append('// at double index (e/2)*64 + 2*lane + (e&1): the two states of a row pair sit side by side (128-bit loads)')
+    L.append('#define SBM_GIDX(e) ((((e) >> 1) * 64) + ((e) & 1))')
     L.append('#define SBM_CT_W %d' % W_ct)
     L.append('#define SBM_CT_C %d' % C_ct)
     L.append('#define SBM_CT_XW %d' % XW_ct)
     if W_ct:
         ysyms = [sp.Symbol('y[%d]' % i, real=True) for i in range(N)]
         _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct)
+        # a second, wider split for the first stage of a step: its step size is only known once the previous step
+        # has been judged, so nothing overlaps it and every warp is free to help
+        n_head = int(_os.environ.get('SBM_CT_HEAD_SHARES', '0')) or min(W_ct + XW_ct, 2)
+        L.append('#define SBM_CT_HEAD_SHARES %d' % n_head)
+        _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct, fname='sbm_primal_head',
+                            n_shares=n_head, head=True)
 
     # --- dense Jacobian (row-major Jd[i*N+k]) and df/dt for the Rosenbrock kernel
     rep, red = sp.cse(J_x, symbols=sp.numbered_symbols('c_'), optimizations='basic')

@@ -130,10 +130,11 @@ def test_ct_layout_and_primal_shares_cover_every_output_once():
         body = body[:body.index('\n}\n')]
         f_idx = sorted(int(x) for x in re.findall(r'fo\[(\d+) \* 32\] =', body))
         j_idx = sorted(int(x) for x in re.findall(r'Jo\[(\d+) \* 32\] =', body))
-        g_idx = sorted(int(x) for x in re.findall(r'Go\[(\d+) \* 32\] =', body))
+        g_idx = sorted(int(x) for x in re.findall(r'Go\[SBM_GIDX\((\d+)\)\] =', body))
         assert f_idx == list(range(sm.n_vars))
         assert j_idx == list(range(cs.nnz_J))
         # dense G slot = parameter * N + state, one per structural non-zero
-        assert g_idx == sorted(j * sm.n_vars + i for (i, j) in sm.G.keys())
+        ne = sm.n_vars + (sm.n_vars & 1)
+        assert g_idx == sorted(j * ne + i for (i, j) in sm.G.keys())
         XW = int(re.search(r'#define SBM_CT_XW (\d+)', src).group(1))
         assert body.count('case ') == W + XW
