@@ -35,6 +35,8 @@
 // size).  Lanes fetch new trajectories from a global queue as they finish (persistent CTAs).
 // =================================================================================================
 
+#if defined(SBM_CT_W) && SBM_CT_W > 0      /* the emitter found a layout for this model */
+
 #define SBM_CT_F_ACCEPT 1
 #define SBM_CT_F_EMIT   2
 #define SBM_CT_F_POISON 4
@@ -749,3 +751,5 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
 #define SBM_DEFINE_DP5_CT(NAME, W, C, XW)                                                               \
     extern "C" __global__ void __launch_bounds__(((W) + (XW)) * 32, 1) NAME(const SbmSolveArgs a)       \
     { sbm_dp5_ct_impl<W, C, XW>(a); }
+
+#endif  /* SBM_CT_W > 0 */

@@ -140,6 +140,7 @@ struct sbm_model {
     // CTA-transposed sensitivity kernel (kernels/sbm_dp5_ct.cuh): W sensitivity warps x C columns + 1 state warp
     int ctW = 0, ctC = 0, ctCS = 0, ctXW = 0, ct_dyn_smem = 0, ct_ctas_per_sm = 0, sm_count = 0;
     bool ct_ok = false;
+    bool has_rodas = true;
     int layout = 0;              // 0 auto, 1 lane-per-column groups, 2 CTA-transposed
     std::string source;          // full NVRTC translation unit (kept for diagnostics)
     std::string log;
@@ -241,7 +242,9 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     if (m->ct_ok) src << "SBM_DEFINE_DP5_CT(sbm_dp5_ct, " << m->ctW << ", " << m->ctC << ", " << m->ctXW << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_plain, 1, 1, 0, " << m->block_plain << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_sens, " << m->G << ", " << m->C << ", 1, " << m->block << ")\n";
-    src << "SBM_DEFINE_RODAS4(sbm_rodas4_plain, " << m->block_plain << ")\n";
+    // the Rosenbrock kernel keeps the dense Jacobian and its LU in registers: fine up to ~12 states, hopeless beyond
+    m->has_rodas = desc->n_vars <= 12;
+    if (m->has_rodas) src << "SBM_DEFINE_RODAS4(sbm_rodas4_plain, " << m->block_plain << ")\n";
     m->source = src.str();
 
     const std::string archopt = "--gpu-architecture=" + m->arch;
@@ -326,7 +329,7 @@ static int ensure_loaded(sbm_model* m)
     DRV(driver().cuModuleLoadData_(&m->mod, m->cubin.data()));
     if ((rc = slot_load(m, m->dp5_plain, "sbm_dp5_plain"))) return rc;
     if ((rc = slot_load(m, m->dp5_sens, "sbm_dp5_sens"))) return rc;
-    if ((rc = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return rc;
+    if (m->has_rodas && (rc = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return rc;
     DRV(driver().cuFuncSetAttribute_(m->dp5_sens.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
     DRV(driver().cuFuncSetAttribute_(m->dp5_plain.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_plain));
     if (m->ct_ok) {
@@ -470,6 +473,8 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
     if (rc) return rc;
     if (o->solver == SBM_SOLVER_RODAS4 && jac) return fail(SBM_E_INVALID, "RODAS4 kernel integrates states only (no sensitivities)");
     if (o->solver != SBM_SOLVER_DP5 && o->solver != SBM_SOLVER_RODAS4) return fail(SBM_E_INVALID, "unknown solver");
+    if (o->solver == SBM_SOLVER_RODAS4 && !m->has_rodas)
+        return fail(SBM_E_INVALID, "RODAS4 kernel (in-register dense LU) supports at most 12 states");
     cudaStream_t st = (cudaStream_t)stream;
 
     SbmSolveArgs a;

@@ -128,8 +128,12 @@ class OdeModel(ModelABC):
         counters = torch.zeros(_lib.SBM_N_COUNTERS, dtype=torch.int64, device=dev)
         solver = self.solver if not with_sens else 'dp5'
         opts = plan.opts(solver, self.rtol, self.atol, self.max_steps, jac_raw=True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
         plan.solve_device(theta, opts, sims, jac, status, counters)
+        ev1.record()
         torch.cuda.synchronize()
+        self.last_solve_ms = ev0.elapsed_time(ev1)       # device time of the integrator launch (CUDA events)
         st = status.cpu().numpy().reshape(-1)
         self.last_status = st
         self.last_counters = dict(zip(_lib.COUNTER_NAMES, counters.cpu().numpy().tolist()))

@@ -293,3 +293,45 @@ def test_cta_transposed_layout_matches_warp_group_layout():
         (y1, S1), (y2, S2) = out[1], out[2]
         assert np.all(np.abs(y1 - y2) <= 1e-8 * (1 + np.abs(y1)))
         assert np.all(np.abs(S1 - S2) <= 1e-7 * (1 + np.abs(S1)))
+
+
+def test_c5_egfr_scale_ssr_ensemble():
+    """C5 shape at reduced size: 25-species EGFR-scale network, many parameter sets ("walkers"), residuals / SSR only
+    (no sensitivities) - plain DP5 kernel vs the reference path (LSODA), and the batched SSR vs the oracle project."""
+    import sysbio_modeling_b200 as sb
+    from sysbio_modeling_b200 import model_files
+    mod = model_files.module('egfr_signalling')
+    sm, m, s = python_rhs('egfr_signalling')
+    nominal = np.array([mod.nominal[k] for k in sm.param_order])
+    y0 = np.array(mod.initial_conditions)
+    rng = np.random.default_rng(5)
+    om = sb.OdeModel.from_model_file(model_files.path('egfr_signalling'))
+    t = np.linspace(0, 600, 13)
+    P = nominal * np.exp(0.2 * rng.standard_normal((8, len(nominal))))
+    y = om.simulate_batch(P, t, y0)
+    assert (om.last_status == 0).all()
+    for b in range(8):
+        yr = O.simulate(m, 25, P[b], t, y0, rtol=1e-11, atol=1e-11)
+        assert np.all(np.abs(y[b] - yr) <= 1e-7 * (1 + np.abs(yr))), (b, np.abs(y[b] - yr).max())
+    # conserved pools: Ras (15, 16), Raf (17, 18), MEK (19..21), ERK (22..24)
+    assert np.abs(y[:, :, 15] + y[:, :, 16] - 120.0).max() < 1e-8
+    assert np.abs(y[:, :, 22] + y[:, :, 23] + y[:, :, 24] - 200.0).max() < 1e-8
+    # ensemble SSR: data generated at the nominal parameters, 512 walkers around them
+    tm = np.linspace(50, 600, 12)
+    ynom = O.simulate(m, 25, nominal, np.concatenate([[0.0], tm]), y0, rtol=1e-11, atol=1e-11)[1:]
+
+    def exps():
+        return [sb.Experiment('EGF_stimulation',
+                              [sb.TimecourseMeasurement('ERKPP', ynom[:, 24], tm, 0.05 * ynom[:, 24] + 0.1),
+                               sb.TimecourseMeasurement('RasT', ynom[:, 16], tm, 0.05 * ynom[:, 16] + 0.1)],
+                              initial_conditions=mod.initial_conditions)]
+    mapping = {'ERKPP': ('direct', 24), 'RasT': ('direct', 16)}
+    proj = sb.Project(om, exps(), {}, mapping)
+    oracle = O.OracleProject(m, s, 25, sm.param_order, exps(), {}, mapping)
+    theta = np.log(nominal)[None, :] + 0.1 * rng.standard_normal((512, len(nominal)))
+    out = proj.residuals_batch(theta)
+    assert (out['status'] == 0).all()
+    assert np.allclose(out['ssr'], 0.5 * (out['resid'] ** 2).sum(axis=1), rtol=1e-12)
+    for b in (0, 17, 511):
+        ssr0 = oracle.sum_square_residuals(theta[b])
+        assert abs(out['ssr'][b] - ssr0) <= 1e-6 * ssr0 + 1e-9, (b, out['ssr'][b], ssr0)
