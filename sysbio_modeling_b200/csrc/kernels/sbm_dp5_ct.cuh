@@ -119,6 +119,73 @@ __device__ __forceinline__ void sbm_ct_update(const double kk, const double h, c
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Storage of the two vectors that do not fit in registers (S1 and S4 of every sensitivity column).
+//
+// SBM_CT_TMEM = 1 (default): Blackwell tensor memory used as a register-file extension.  TMEM is 128 lanes x 512
+// 32-bit columns per SM; a warp reaches the 32 lanes of its quadrant (warp % 4) and with the 32x32b shape thread t
+// reads / writes lane t - i.e. every thread owns a private row, exactly what lane = trajectory needs.  An element
+// (a double) is two columns; a row pair of one column of S is one tcgen05.ld/st ...x4.  This takes 43 % of the
+// kernel's shared-memory bytes (which bound the stage: see DESIGN.md) off the shared-memory pipe.
+// SBM_CT_TMEM = 0: shared memory, [element][lane].
+// -------------------------------------------------------------------------------------------------
+#ifndef SBM_CT_TMEM
+#define SBM_CT_TMEM 1
+#endif
+
+struct SbmCtPair { unsigned r0, r1, r2, r3; };      // two doubles in flight from TMEM (or already loaded from smem)
+
+#if SBM_CT_TMEM
+struct SbmCtStore { unsigned t1, t4; };             // TMEM addresses (lane quadrant | column) of S1[0] and S4[0]
+
+__device__ __forceinline__ void sbm_st_issue(const SbmCtStore& st, const int slot, const int e0, SbmCtPair& v)
+{
+    const unsigned ta = (slot == 1 ? st.t1 : st.t4) + 2u * e0;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.r0), "=r"(v.r1), "=r"(v.r2), "=r"(v.r3) : "r"(ta));
+}
+__device__ __forceinline__ void sbm_st_wait(SbmCtPair& v, double& a, double& b)
+{
+    // the registers are valid only after the wait: tie them to it so nothing reads them earlier
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v.r0), "+r"(v.r1), "+r"(v.r2), "+r"(v.r3));
+    a = __hiloint2double((int)v.r1, (int)v.r0);
+    b = __hiloint2double((int)v.r3, (int)v.r2);
+}
+__device__ __forceinline__ void sbm_st_store(const SbmCtStore& st, const int slot, const int e0, const double a,
+                                             const double b)
+{
+    const unsigned ta = (slot == 1 ? st.t1 : st.t4) + 2u * e0;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(ta), "r"(__double2loint(a)), "r"(__double2hiint(a)), "r"(__double2loint(b)),
+                    "r"(__double2hiint(b)) : "memory");
+}
+__device__ __forceinline__ void sbm_st_fence() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#else
+struct SbmCtStore { double* v1; double* v4; };      // shared memory, element e at [e * 32]
+
+__device__ __forceinline__ void sbm_st_issue(const SbmCtStore& st, const int slot, const int e0, SbmCtPair& v)
+{
+    const double* p = (slot == 1 ? st.v1 : st.v4) + e0 * 32;
+    const double a = p[0], b = p[32];
+    v.r0 = (unsigned)__double2loint(a); v.r1 = (unsigned)__double2hiint(a);
+    v.r2 = (unsigned)__double2loint(b); v.r3 = (unsigned)__double2hiint(b);
+}
+__device__ __forceinline__ void sbm_st_wait(SbmCtPair& v, double& a, double& b)
+{
+    a = __hiloint2double((int)v.r1, (int)v.r0);
+    b = __hiloint2double((int)v.r3, (int)v.r2);
+}
+__device__ __forceinline__ void sbm_st_store(const SbmCtStore& st, const int slot, const int e0, const double a,
+                                             const double b)
+{
+    double* p = (slot == 1 ? st.v1 : st.v4) + e0 * 32;
+    p[0] = a;
+    p[32] = b;
+}
+__device__ __forceinline__ void sbm_st_fence() {}
+#endif
+
 // -------------------------------------------------------------------------------------------------
 // one stage on CW sensitivity columns of 32 trajectories.  Gw points at this warp's first column of the
 // dense G buffer: the entry of (column c, state i) sits at Gw[SBM_GIDX(c*NE + i)], structural zeros hold 0.
@@ -127,63 +194,73 @@ template <int S, int CW>
 __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* __restrict__ Jp,
                                                   const double* __restrict__ Gw,
                                                   double (&y)[CW][SBM_N], double (&s2)[CW][SBM_N],
-                                                  double (&s3)[CW][SBM_N], double* __restrict__ V1,
-                                                  double* __restrict__ V4, const double rtol, const double atol,
+                                                  double (&s3)[CW][SBM_N], const SbmCtStore& st,
+                                                  const double rtol, const double atol,
                                                   const bool anyinit, double& sq, double& d0, double& d1)
 {
-    constexpr int N = SBM_N;
+    constexpr int N = SBM_N, NE = N + (N & 1), NP2 = NE / 2;
+    // ---- stage input of every element (element e = c*NE + i; S1 comes in row pairs) ----
     double w[CW][N];
+    if (S <= 5) {
+        SbmCtPair pv[CW][NP2];
 #pragma unroll
-    for (int c = 0; c < CW; ++c)
+        for (int c = 0; c < CW; ++c)
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double v1 = (S <= 5) ? V1[(c * N + i) * 32] : 0.0;
-            w[c][i] = sbm_ct_input<S>(h, y[c][i], v1, s2[c][i], s3[c][i]);
-        }
-    // rows are processed SBM_CT_ROWS at a time: that many independent FMA chains per column hide the FP64 and
-    // shared-memory latencies that a single row exposes (2 warps x 2 columns per scheduler are not enough)
-#ifndef SBM_CT_ROWS
-#define SBM_CT_ROWS 2
-#endif
+            for (int ip = 0; ip < NP2; ++ip) sbm_st_issue(st, 1, c * NE + 2 * ip, pv[c][ip]);
 #pragma unroll
-    for (int i0 = 0; i0 < N; i0 += SBM_CT_ROWS) {
-        double acc[SBM_CT_ROWS][CW];
+        for (int c = 0; c < CW; ++c)
 #pragma unroll
-        for (int r = 0; r < SBM_CT_ROWS; ++r)
+            for (int ip = 0; ip < NP2; ++ip) {
+                double va, vb;
+                sbm_st_wait(pv[c][ip], va, vb);
+                w[c][2 * ip] = sbm_ct_input<S>(h, y[c][2 * ip], va, s2[c][2 * ip], s3[c][2 * ip]);
+                if (2 * ip + 1 < N)
+                    w[c][2 * ip + 1] = sbm_ct_input<S>(h, y[c][2 * ip + 1], vb, s2[c][2 * ip + 1], s3[c][2 * ip + 1]);
+            }
+    } else {
 #pragma unroll
-            for (int c = 0; c < CW; ++c) acc[r][c] = 0.0;
+        for (int c = 0; c < CW; ++c)
+#pragma unroll
+            for (int i = 0; i < N; ++i) w[c][i] = sbm_ct_input<S>(h, y[c][i], 0.0, s2[c][i], s3[c][i]);
+    }
+    // ---- rows in pairs: two independent FMA chains per column, one 128-bit load of G, one transfer of S1 / S4 ----
+#pragma unroll
+    for (int i0 = 0; i0 < N; i0 += 2) {
+        const bool two = (i0 + 1 < N);
+        SbmCtPair p1[CW], p4[CW];
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
-            // dense G, two states of a row pair per 128-bit load (layout: SBM_GIDX in the model source)
-            constexpr int NE = N + (N & 1);
-            if (SBM_CT_ROWS == 2 && i0 + 1 < N) {
-                const double2 g2 = *reinterpret_cast<const double2*>(Gw + SBM_GIDX(c * NE + i0));
-                acc[0][c] = g2.x;
-                acc[SBM_CT_ROWS - 1][c] = g2.y;
-            } else {
-#pragma unroll
-                for (int r = 0; r < SBM_CT_ROWS; ++r)
-                    if (i0 + r < N) acc[r][c] = Gw[SBM_GIDX(c * NE + i0 + r)];
-            }
+            if (S == 4) sbm_st_issue(st, 1, c * NE + i0, p1[c]);       // k1, for the in-place conversion
+            if (S >= 5) sbm_st_issue(st, 4, c * NE + i0, p4[c]);       // error accumulator
         }
+        double acc[2][CW];
 #pragma unroll
-        for (int r = 0; r < SBM_CT_ROWS; ++r)
-            if (i0 + r < N) sbm_jrow<CW>(i0 + r, Jp, w, acc[r]);
+        for (int c = 0; c < CW; ++c) {
+            // dense G, both states of the row pair in one 128-bit load (layout: SBM_GIDX in the model source)
+            const double2 g2 = *reinterpret_cast<const double2*>(Gw + SBM_GIDX(c * NE + i0));
+            acc[0][c] = g2.x;
+            acc[1][c] = g2.y;
+        }
+        sbm_jrow<CW>(i0, Jp, w, acc[0]);
+        if (two) sbm_jrow<CW>(i0 + 1, Jp, w, acc[1]);
 #pragma unroll
-        for (int r = 0; r < SBM_CT_ROWS; ++r) {
-            const int i = i0 + r;
-            if (i < N) {
+        for (int c = 0; c < CW; ++c) {
+            double v1a = 0.0, v1b = 0.0, v4a = 0.0, v4b = 0.0;
+            if (S == 4) sbm_st_wait(p1[c], v1a, v1b);
+            if (S >= 5) sbm_st_wait(p4[c], v4a, v4b);
+            double dummy2 = 0.0, dummy3 = 0.0;
+            sbm_ct_update<S>(acc[0][c], h, y[c][i0], v1a, s2[c][i0], s3[c][i0], v4a);
+            if (two) sbm_ct_update<S>(acc[1][c], h, y[c][i0 + 1], v1b, s2[c][i0 + 1], s3[c][i0 + 1], v4b);
+            else sbm_ct_update<S>(0.0, h, 0.0, v1b, dummy2, dummy3, v4b);
+            if (S == 4 || S == 7) sbm_st_store(st, 1, c * NE + i0, v1a, v1b);
+            if (S >= 4 && S <= 6) sbm_st_store(st, 4, c * NE + i0, v4a, v4b);
+            if (S == 7) {
 #pragma unroll
-                for (int c = 0; c < CW; ++c) {
-                    double v1 = 0.0, v4 = 0.0;
-                    if (S == 4) v1 = V1[(c * N + i) * 32];
-                    if (S >= 5) v4 = V4[(c * N + i) * 32];
-                    sbm_ct_update<S>(acc[r][c], h, y[c][i], v1, s2[c][i], s3[c][i], v4);
-                    if (S == 4 || S == 7) V1[(c * N + i) * 32] = v1;
-                    if (S >= 4 && S <= 6) V4[(c * N + i) * 32] = v4;
-                    if (S == 7) {
+                for (int r = 0; r < 2; ++r) {
+                    if (r == 0 || two) {
+                        const int i = i0 + r;
                         const double isk = sbm_rcp_fast(fma(rtol, fmax(fabs(y[c][i]), fabs(s3[c][i])), atol));
-                        const double q = v4 * isk;
+                        const double q = (r == 0 ? v4a : v4b) * isk;
                         sq = fma(q, q, sq);
                         if (anyinit) {
                             const double q0 = y[c][i] * isk, q1 = acc[r][c] * isk;
@@ -195,6 +272,7 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
             }
         }
     }
+    sbm_st_fence();
 }
 
 // start of a step for a block of CW sensitivity columns: apply the accept decision, write the Jacobian
@@ -203,7 +281,7 @@ template <int CW>
 __device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const int info, const int cflags,
                                                   const double h, const int col0, const int lane,
                                                   double (&y)[CW][SBM_N], const double (&s3)[CW][SBM_N],
-                                                  double* __restrict__ V1, const double* __restrict__ pb,
+                                                  const SbmCtStore& st, const double* __restrict__ pb,
                                                   const long long* __restrict__ trj, const int* __restrict__ ktb)
 {
     constexpr int N = SBM_N;
@@ -251,13 +329,21 @@ __device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const i
 #pragma unroll
             for (int i = 0; i < N; ++i) y[c][i] = 0.0;
     }
-    if (h == 0.0) {
-        // zero-length step (start-up, refresh after a rejection, idle lane): the stale k1 must not leak
-        // into the stage inputs (0 * Inf = NaN after a rejected non-finite trial)
+    if (__any_sync(0xffffffffu, h == 0.0)) {
+        // zero-length step (start-up, refresh after a rejection, idle lane): the stale k1 must not leak into the
+        // stage inputs (0 * Inf = NaN after a rejected non-finite trial).  Warp-uniform: TMEM transfers are collective.
+        constexpr int NE = N + (N & 1);
 #pragma unroll
         for (int c = 0; c < CW; ++c)
 #pragma unroll
-            for (int i = 0; i < N; ++i) V1[(c * N + i) * 32] = 0.0;
+            for (int ip = 0; ip < NE / 2; ++ip) {
+                SbmCtPair pv;
+                double va, vb;
+                sbm_st_issue(st, 1, c * NE + 2 * ip, pv);
+                sbm_st_wait(pv, va, vb);
+                sbm_st_store(st, 1, c * NE + 2 * ip, h == 0.0 ? 0.0 : va, h == 0.0 ? 0.0 : vb);
+            }
+        sbm_st_fence();
     }
 }
 
@@ -265,17 +351,17 @@ template <int CW>
 __device__ __forceinline__ void sbm_ct_cols_stage(const int s, const double h, const double* __restrict__ Jp,
                                                   const double* __restrict__ Gw,
                                                   double (&y)[CW][SBM_N], double (&s2)[CW][SBM_N],
-                                                  double (&s3)[CW][SBM_N], double* __restrict__ V1,
-                                                  double* __restrict__ V4, const double rtol, const double atol,
+                                                  double (&s3)[CW][SBM_N], const SbmCtStore& st,
+                                                  const double rtol, const double atol,
                                                   const bool anyinit, double& sq, double& d0, double& d1)
 {
     switch (s) {
-    case 2: sbm_ct_sens_stage<2, CW>(h, Jp, Gw, y, s2, s3, V1, V4, rtol, atol, anyinit, sq, d0, d1); break;
-    case 3: sbm_ct_sens_stage<3, CW>(h, Jp, Gw, y, s2, s3, V1, V4, rtol, atol, anyinit, sq, d0, d1); break;
-    case 4: sbm_ct_sens_stage<4, CW>(h, Jp, Gw, y, s2, s3, V1, V4, rtol, atol, anyinit, sq, d0, d1); break;
-    case 5: sbm_ct_sens_stage<5, CW>(h, Jp, Gw, y, s2, s3, V1, V4, rtol, atol, anyinit, sq, d0, d1); break;
-    case 6: sbm_ct_sens_stage<6, CW>(h, Jp, Gw, y, s2, s3, V1, V4, rtol, atol, anyinit, sq, d0, d1); break;
-    default: sbm_ct_sens_stage<7, CW>(h, Jp, Gw, y, s2, s3, V1, V4, rtol, atol, anyinit, sq, d0, d1); break;
+    case 2: sbm_ct_sens_stage<2, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 3: sbm_ct_sens_stage<3, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 4: sbm_ct_sens_stage<4, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 5: sbm_ct_sens_stage<5, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 6: sbm_ct_sens_stage<6, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    default: sbm_ct_sens_stage<7, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
     }
 }
 
@@ -289,8 +375,7 @@ struct SbmCtShared {
     double* Pb;          // [2][N][32]         partial stage values y + h sum_{j<S-1} a_Sj f_j, prepared one iteration ahead
     double* pb;          // [NP][32]           model parameters of each lane's trajectory
     double* sqb;         // [W+3][32]          partial sums of the squared error norm (per column warp), then the state
-                         //                    column's error / |y| / |f| sums; on start-up steps
-                         //                    the |y| and |f| partial sums are parked in the first two elements of each warp's S4
+                         //                    column's error / |y| / |f| sums
     double* hb;          // [32]               step of each lane (0: zero-length step / idle)
     double* cd;          // [SBM_CT_ND][32]    controller doubles
     unsigned long long* cnt;   // [4][32]      steps, rejects, rhs evaluations, trajectories
@@ -299,7 +384,9 @@ struct SbmCtShared {
     int* fl;             // [32]               per-lane flags of this step
     int* ktb;            // [32]               output-time index to emit
     int* cta;            // [32]               CTA-wide flags in cta[0]
-    double* V;           // S1 and S4 of the sensitivity columns: warp w at V + w*2*C*N*32
+    double* park;        // [2][W][32]         start-up norms |y|, |f| (per column warp)
+    double* V;           // S1 and S4 of the sensitivity columns when they live in shared memory (SBM_CT_TMEM = 0)
+    unsigned tmem_base;  // TMEM allocation (SBM_CT_TMEM = 1)
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -420,10 +507,8 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
                 // upper bound 100 h0 and let the controller (and, if needed, one rejection) settle it
 #pragma unroll
                 for (int w = 0; w < W; ++w) {
-                    const int cw = (w == W - 1) ? CL : C;
-                    const double* park = sh.V + ((w * 2 * C + cw) * N) * 32 + lane;    // that warp's S4
-                    q0 += park[0];
-                    q1 += park[32];
+                    q0 += sh.park[w * 32 + lane];
+                    q1 += sh.park[(W + w) * 32 + lane];
                 }
                 const double n0 = sqrt(q0 * inv_naug), n1 = sqrt(q1 * inv_naug);
                 const double h0 = (n0 < 1e-5 || n1 < 1e-5) ? 1e-6 : 0.01 * n0 / n1;
@@ -591,18 +676,30 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
 {
     constexpr int N = SBM_N, NT = (W + XW) * 32;
     const int col0 = warp * C;                     // first sensitivity column (free-parameter index) of this warp
-    double* V1 = sh.V + (warp * 2 * C * N) * 32 + lane;
-    double* V4 = V1 + CW * N * 32;
-    static_assert(CW * N >= 2, "start-up norms are parked in two elements of S4");
+    constexpr int NE = N + (N & 1);
+    SbmCtStore st;
+#if SBM_CT_TMEM
+    // this warp's TMEM window: its lane quadrant, 4*C*NE columns per warp of the quadrant (S1 then S4)
+    st.t1 = sh.tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 4 * C * NE);
+    st.t4 = st.t1 + 2u * CW * NE;
+#else
+    st.v1 = sh.V + (warp * 2 * C * NE) * 32 + lane;
+    st.v4 = st.v1 + CW * NE * 32;
+#endif
+    static_assert(CW * N >= 2, "at least one row pair per warp");
     double y[CW][N], s2[CW][N], s3[CW][N];
 #pragma unroll
     for (int c = 0; c < CW; ++c)
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            y[c][i] = 0.0; s2[c][i] = 0.0; s3[c][i] = 0.0;
-            V1[(c * N + i) * 32] = 0.0;
-            V4[(c * N + i) * 32] = 0.0;
+        for (int i = 0; i < N; ++i) { y[c][i] = 0.0; s2[c][i] = 0.0; s3[c][i] = 0.0; }
+#pragma unroll
+    for (int c = 0; c < CW; ++c)
+#pragma unroll
+        for (int ip = 0; ip < NE / 2; ++ip) {
+            sbm_st_store(st, 1, c * NE + 2 * ip, 0.0, 0.0);
+            sbm_st_store(st, 4, c * NE + 2 * ip, 0.0, 0.0);
         }
+    sbm_st_fence();
     const double rtol = a.rtol, atol = a.atol;
 
     for (;;) {
@@ -612,7 +709,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
         if (!(cflags & SBM_CT_ALIVE)) break;
         const int info = sh.fl[lane];
         const double h = sh.hb[lane];
-        sbm_ct_cols_begin<CW>(a, info, cflags, h, col0, lane, y, s3, V1, sh.pb, sh.trj, sh.ktb);
+        sbm_ct_cols_begin<CW>(a, info, cflags, h, col0, lane, y, s3, st, sh.pb, sh.trj, sh.ktb);
         const bool anyinit = (cflags & SBM_CT_ANYINIT) != 0;
         double sq = 0.0, d0 = 0.0, d1 = 0.0;
         // iteration s: stage s of this warp's columns (s >= 2) and its share of the model at the input of
@@ -622,7 +719,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
             if (s >= 2) {
                 const double* Jp = sh.Jb + (s & 1) * SBM_NJ * 32 + lane;
                 const double* Gw = sh.Gd + ((s & 1) * SBM_NF + col0) * (N + (N & 1)) * 32 + 2 * lane;
-                sbm_ct_cols_stage<CW>(s, h, Jp, Gw, y, s2, s3, V1, V4, rtol, atol, anyinit, sq, d0, d1);
+                sbm_ct_cols_stage<CW>(s, h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
             }
             if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
 #ifdef SBM_CT_PRIMAL_REPEAT
@@ -633,7 +730,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
 #endif
             else {
                 sh.sqb[warp * 32 + lane] = sq;
-                if (anyinit) { V4[0] = d0; V4[32] = d1; }      // S4 is dead once the error norm is formed
+                if (anyinit) { sh.park[warp * 32 + lane] = d0; sh.park[(W + warp) * 32 + lane] = d1; }
             }
             SBM_CT_BAR(NT);
         }
@@ -673,7 +770,7 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
 // CL = NF - (W-1)*C) plus XW warps without columns.  Shared-memory carve-up in doubles (sbm_api.cu computes the same
 // size on the host):
 //   2*NJ*32 + 2*NF*NE*32 + 7*N*32 + 2*N*32 + 2*N*32 + NP*32 + (W+3)*32 + 32 + ND*32 + 4*32 + 32 + (NI*32 + 3*32)/2
-//   + ((W-1)*C + CL)*2*N*32
+//   + 2*W*32 + (SBM_CT_TMEM ? 0 : W*2*C*NE*32)
 template <int W, int C, int XW>
 __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
 {
@@ -699,7 +796,9 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     sh.fl = sh.ci + SBM_CT_NI * 32;
     sh.ktb = sh.fl + 32;
     sh.cta = sh.ktb + 32;
-    sh.V = (double*)(sh.cta + 32);
+    sh.park = (double*)(sh.cta + 32);
+    sh.V = sh.park + 2 * W * 32;
+    sh.tmem_base = 0;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -723,14 +822,40 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
         sh.ktb[lane] = 0;
         sh.cta[lane] = 0;
     }
+    for (int q = threadIdx.x; q < 2 * W * 32; q += WT * 32) sh.park[q] = 0.0;
+#if SBM_CT_TMEM
+    // tensor memory for S1 / S4: ceil(W/4) warps per lane quadrant, 4*C*NE columns each (power of two >= 32)
+    constexpr int TM_NEED = ((W + 3) / 4) * 4 * C * (N + (N & 1));
+    constexpr int TM_COLS = TM_NEED <= 32 ? 32 : TM_NEED <= 64 ? 64 : TM_NEED <= 128 ? 128 : TM_NEED <= 256 ? 256 : 512;
+    static_assert(TM_NEED <= 512, "sensitivity columns do not fit in tensor memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((unsigned)__cvta_generic_to_shared(sh.cta + 1)), "r"(TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     SBM_CT_BAR(WT * 32);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    sh.tmem_base = (unsigned)sh.cta[1];
+#else
+    SBM_CT_BAR(WT * 32);
+#endif
 
     if (XW > 0 && warp >= W) sbm_ct_model_warp<W, C, XW>(a, sh, warp, lane);
     else if (warp == W - 1 && CL != C) sbm_ct_warp<W, C, CL, XW>(a, sh, warp, lane);
     else sbm_ct_warp<W, C, C, XW>(a, sh, warp, lane);
 
     // ---- counters: one atomic per CTA ----
+#if SBM_CT_TMEM
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#endif
     SBM_CT_BAR(WT * 32);
+#if SBM_CT_TMEM
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(sh.tmem_base), "r"(TM_COLS) : "memory");
+    }
+#endif
     if (warp == 0) {
         unsigned long long v[4];
 #pragma unroll

@@ -846,6 +846,12 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     L.append('#define SBM_CT_W %d' % W_ct)
     L.append('#define SBM_CT_C %d' % C_ct)
     L.append('#define SBM_CT_XW %d' % XW_ct)
+    # S1 / S4 of the sensitivity columns in tensor memory (1) or in shared memory (0)
+    NE_ct = N + (N & 1)
+    tmem = 1 if (W_ct and ((W_ct + 3) // 4) * 4 * C_ct * NE_ct <= 512) else 0
+    if 'SBM_CT_TMEM' in _os.environ:
+        tmem = int(_os.environ['SBM_CT_TMEM'])
+    L.append('#define SBM_CT_TMEM %d' % tmem)
     if W_ct:
         ysyms = [sp.Symbol('y[%d]' % i, real=True) for i in range(N)]
         _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct)
