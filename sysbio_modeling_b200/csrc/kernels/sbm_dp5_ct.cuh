@@ -123,78 +123,72 @@ __device__ __forceinline__ void sbm_ct_update(const double kk, const double h, c
 // -------------------------------------------------------------------------------------------------
 // Storage of the two vectors that do not fit in registers (S1 and S4 of every sensitivity column).
 //
-// SBM_CT_TMEM = 1 (default): Blackwell tensor memory used as a register-file extension.  TMEM is 128 lanes x 512
+// Blackwell tensor memory used as a register-file extension.  TMEM is 128 lanes x 512
 // 32-bit columns per SM; a warp reaches the 32 lanes of its quadrant (warp % 4) and with the 32x32b shape thread t
 // reads / writes lane t - i.e. every thread owns a private row, exactly what lane = trajectory needs.  An element
 // (a double) is two columns; a row pair of one column of S is one tcgen05.ld/st ...x4.  This takes 43 % of the
-// kernel's shared-memory bytes (which bound the stage: see DESIGN.md) off the shared-memory pipe.
-// SBM_CT_TMEM = 0: shared memory, [element][lane].
+// kernel's shared-memory bytes off the shared-memory pipe and frees 90 KB of shared memory (MAPK).
 // -------------------------------------------------------------------------------------------------
-#ifndef SBM_CT_TMEM
-#define SBM_CT_TMEM 1
-#endif
+struct SbmCtPair { unsigned r0, r1, r2, r3; };      // two doubles in flight (from TMEM) or at hand (registers)
 
-struct SbmCtPair { unsigned r0, r1, r2, r3; };      // two doubles in flight from TMEM (or already loaded from smem)
+// S1 / S4 in tensor memory
+struct SbmCtStoreTmem {
+    unsigned t1, t4;                                // TMEM addresses (lane quadrant | column) of S1[0] and S4[0]
+    __device__ __forceinline__ void issue(const int slot, const int e0, SbmCtPair& v) const
+    {
+        const unsigned ta = (slot == 1 ? t1 : t4) + 2u * e0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.r0), "=r"(v.r1), "=r"(v.r2), "=r"(v.r3) : "r"(ta));
+    }
+    __device__ __forceinline__ void wait(SbmCtPair& v, double& a, double& b) const
+    {
+        // the registers are valid only after the wait: tie them to it so nothing reads them earlier
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v.r0), "+r"(v.r1), "+r"(v.r2), "+r"(v.r3));
+        a = __hiloint2double((int)v.r1, (int)v.r0);
+        b = __hiloint2double((int)v.r3, (int)v.r2);
+    }
+    __device__ __forceinline__ void store(const int slot, const int e0, const double a, const double b)
+    {
+        const unsigned ta = (slot == 1 ? t1 : t4) + 2u * e0;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                     :: "r"(ta), "r"(__double2loint(a)), "r"(__double2hiint(a)), "r"(__double2loint(b)),
+                        "r"(__double2hiint(b)) : "memory");
+    }
+    __device__ __forceinline__ void fence() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+};
 
-#if SBM_CT_TMEM
-struct SbmCtStore { unsigned t1, t4; };             // TMEM addresses (lane quadrant | column) of S1[0] and S4[0]
-
-__device__ __forceinline__ void sbm_st_issue(const SbmCtStore& st, const int slot, const int e0, SbmCtPair& v)
-{
-    const unsigned ta = (slot == 1 ? st.t1 : st.t4) + 2u * e0;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.r0), "=r"(v.r1), "=r"(v.r2), "=r"(v.r3) : "r"(ta));
-}
-__device__ __forceinline__ void sbm_st_wait(SbmCtPair& v, double& a, double& b)
-{
-    // the registers are valid only after the wait: tie them to it so nothing reads them earlier
-    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v.r0), "+r"(v.r1), "+r"(v.r2), "+r"(v.r3));
-    a = __hiloint2double((int)v.r1, (int)v.r0);
-    b = __hiloint2double((int)v.r3, (int)v.r2);
-}
-__device__ __forceinline__ void sbm_st_store(const SbmCtStore& st, const int slot, const int e0, const double a,
-                                             const double b)
-{
-    const unsigned ta = (slot == 1 ? st.t1 : st.t4) + 2u * e0;
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                 :: "r"(ta), "r"(__double2loint(a)), "r"(__double2hiint(a)), "r"(__double2loint(b)),
-                    "r"(__double2hiint(b)) : "memory");
-}
-__device__ __forceinline__ void sbm_st_fence() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-#else
-struct SbmCtStore { double* v1; double* v4; };      // shared memory, element e at [e * 32]
-
-__device__ __forceinline__ void sbm_st_issue(const SbmCtStore& st, const int slot, const int e0, SbmCtPair& v)
-{
-    const double* p = (slot == 1 ? st.v1 : st.v4) + e0 * 32;
-    const double a = p[0], b = p[32];
-    v.r0 = (unsigned)__double2loint(a); v.r1 = (unsigned)__double2hiint(a);
-    v.r2 = (unsigned)__double2loint(b); v.r3 = (unsigned)__double2hiint(b);
-}
-__device__ __forceinline__ void sbm_st_wait(SbmCtPair& v, double& a, double& b)
-{
-    a = __hiloint2double((int)v.r1, (int)v.r0);
-    b = __hiloint2double((int)v.r3, (int)v.r2);
-}
-__device__ __forceinline__ void sbm_st_store(const SbmCtStore& st, const int slot, const int e0, const double a,
-                                             const double b)
-{
-    double* p = (slot == 1 ? st.v1 : st.v4) + e0 * 32;
-    p[0] = a;
-    p[32] = b;
-}
-__device__ __forceinline__ void sbm_st_fence() {}
-#endif
+// S1 / S4 in registers: small systems (one warp per CTA = one thread per trajectory) whose five vectors fit the
+// register file - every index is a compile-time constant after unrolling
+template <int NEL>
+struct SbmCtStoreReg {
+    double v1[NEL], v4[NEL];
+    __device__ __forceinline__ void issue(const int slot, const int e0, SbmCtPair& v) const
+    {
+        const double a = slot == 1 ? v1[e0] : v4[e0], b = slot == 1 ? v1[e0 + 1] : v4[e0 + 1];
+        v.r0 = (unsigned)__double2loint(a); v.r1 = (unsigned)__double2hiint(a);
+        v.r2 = (unsigned)__double2loint(b); v.r3 = (unsigned)__double2hiint(b);
+    }
+    __device__ __forceinline__ void wait(SbmCtPair& v, double& a, double& b) const
+    {
+        a = __hiloint2double((int)v.r1, (int)v.r0);
+        b = __hiloint2double((int)v.r3, (int)v.r2);
+    }
+    __device__ __forceinline__ void store(const int slot, const int e0, const double a, const double b)
+    {
+        if (slot == 1) { v1[e0] = a; v1[e0 + 1] = b; } else { v4[e0] = a; v4[e0 + 1] = b; }
+    }
+    __device__ __forceinline__ void fence() const {}
+};
 
 // -------------------------------------------------------------------------------------------------
 // one stage on CW sensitivity columns of 32 trajectories.  Gw points at this warp's first column of the
 // dense G buffer: the entry of (column c, state i) sits at Gw[SBM_GIDX(c*NE + i)], structural zeros hold 0.
 // -------------------------------------------------------------------------------------------------
-template <int S, int CW>
+template <int S, int CW, class ST>
 __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* __restrict__ Jp,
                                                   const double* __restrict__ Gw,
                                                   double (&y)[CW][SBM_N], double (&s2)[CW][SBM_N],
-                                                  double (&s3)[CW][SBM_N], const SbmCtStore& st,
+                                                  double (&s3)[CW][SBM_N], ST& st,
                                                   const double rtol, const double atol,
                                                   const bool anyinit, double& sq, double& d0, double& d1)
 {
@@ -206,13 +200,13 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
 #pragma unroll
         for (int c = 0; c < CW; ++c)
 #pragma unroll
-            for (int ip = 0; ip < NP2; ++ip) sbm_st_issue(st, 1, c * NE + 2 * ip, pv[c][ip]);
+            for (int ip = 0; ip < NP2; ++ip) st.issue(1, c * NE + 2 * ip, pv[c][ip]);
 #pragma unroll
         for (int c = 0; c < CW; ++c)
 #pragma unroll
             for (int ip = 0; ip < NP2; ++ip) {
                 double va, vb;
-                sbm_st_wait(pv[c][ip], va, vb);
+                st.wait(pv[c][ip], va, vb);
                 w[c][2 * ip] = sbm_ct_input<S>(h, y[c][2 * ip], va, s2[c][2 * ip], s3[c][2 * ip]);
                 if (2 * ip + 1 < N)
                     w[c][2 * ip + 1] = sbm_ct_input<S>(h, y[c][2 * ip + 1], vb, s2[c][2 * ip + 1], s3[c][2 * ip + 1]);
@@ -230,8 +224,8 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
         SbmCtPair p1[CW], p4[CW];
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
-            if (S == 4) sbm_st_issue(st, 1, c * NE + i0, p1[c]);       // k1, for the in-place conversion
-            if (S >= 5) sbm_st_issue(st, 4, c * NE + i0, p4[c]);       // error accumulator
+            if (S == 4) st.issue(1, c * NE + i0, p1[c]);       // k1, for the in-place conversion
+            if (S >= 5) st.issue(4, c * NE + i0, p4[c]);       // error accumulator
         }
         double acc[2][CW];
 #pragma unroll
@@ -246,14 +240,14 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
             double v1a = 0.0, v1b = 0.0, v4a = 0.0, v4b = 0.0;
-            if (S == 4) sbm_st_wait(p1[c], v1a, v1b);
-            if (S >= 5) sbm_st_wait(p4[c], v4a, v4b);
+            if (S == 4) st.wait(p1[c], v1a, v1b);
+            if (S >= 5) st.wait(p4[c], v4a, v4b);
             double dummy2 = 0.0, dummy3 = 0.0;
             sbm_ct_update<S>(acc[0][c], h, y[c][i0], v1a, s2[c][i0], s3[c][i0], v4a);
             if (two) sbm_ct_update<S>(acc[1][c], h, y[c][i0 + 1], v1b, s2[c][i0 + 1], s3[c][i0 + 1], v4b);
             else sbm_ct_update<S>(0.0, h, 0.0, v1b, dummy2, dummy3, v4b);
-            if (S == 4 || S == 7) sbm_st_store(st, 1, c * NE + i0, v1a, v1b);
-            if (S >= 4 && S <= 6) sbm_st_store(st, 4, c * NE + i0, v4a, v4b);
+            if (S == 4 || S == 7) st.store(1, c * NE + i0, v1a, v1b);
+            if (S >= 4 && S <= 6) st.store(4, c * NE + i0, v4a, v4b);
             if (S == 7) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -272,16 +266,16 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
             }
         }
     }
-    sbm_st_fence();
+    st.fence();
 }
 
 // start of a step for a block of CW sensitivity columns: apply the accept decision, write the Jacobian
 // rows of an output time, restart on a new trajectory, and clear k1 before a zero-length step
-template <int CW>
+template <int CW, class ST>
 __device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const int info, const int cflags,
                                                   const double h, const int col0, const int lane,
                                                   double (&y)[CW][SBM_N], const double (&s3)[CW][SBM_N],
-                                                  const SbmCtStore& st, const double* __restrict__ pb,
+                                                  ST& st, const double* __restrict__ pb,
                                                   const long long* __restrict__ trj, const int* __restrict__ ktb)
 {
     constexpr int N = SBM_N;
@@ -339,29 +333,29 @@ __device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const i
             for (int ip = 0; ip < NE / 2; ++ip) {
                 SbmCtPair pv;
                 double va, vb;
-                sbm_st_issue(st, 1, c * NE + 2 * ip, pv);
-                sbm_st_wait(pv, va, vb);
-                sbm_st_store(st, 1, c * NE + 2 * ip, h == 0.0 ? 0.0 : va, h == 0.0 ? 0.0 : vb);
+                st.issue(1, c * NE + 2 * ip, pv);
+                st.wait(pv, va, vb);
+                st.store(1, c * NE + 2 * ip, h == 0.0 ? 0.0 : va, h == 0.0 ? 0.0 : vb);
             }
-        sbm_st_fence();
+        st.fence();
     }
 }
 
-template <int CW>
+template <int CW, class ST>
 __device__ __forceinline__ void sbm_ct_cols_stage(const int s, const double h, const double* __restrict__ Jp,
                                                   const double* __restrict__ Gw,
                                                   double (&y)[CW][SBM_N], double (&s2)[CW][SBM_N],
-                                                  double (&s3)[CW][SBM_N], const SbmCtStore& st,
+                                                  double (&s3)[CW][SBM_N], ST& st,
                                                   const double rtol, const double atol,
                                                   const bool anyinit, double& sq, double& d0, double& d1)
 {
     switch (s) {
-    case 2: sbm_ct_sens_stage<2, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
-    case 3: sbm_ct_sens_stage<3, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
-    case 4: sbm_ct_sens_stage<4, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
-    case 5: sbm_ct_sens_stage<5, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
-    case 6: sbm_ct_sens_stage<6, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
-    default: sbm_ct_sens_stage<7, CW>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 2: sbm_ct_sens_stage<2, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 3: sbm_ct_sens_stage<3, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 4: sbm_ct_sens_stage<4, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 5: sbm_ct_sens_stage<5, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 6: sbm_ct_sens_stage<6, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    default: sbm_ct_sens_stage<7, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
     }
 }
 
@@ -385,8 +379,7 @@ struct SbmCtShared {
     int* ktb;            // [32]               output-time index to emit
     int* cta;            // [32]               CTA-wide flags in cta[0]
     double* park;        // [2][W][32]         start-up norms |y|, |f| (per column warp)
-    double* V;           // S1 and S4 of the sensitivity columns when they live in shared memory (SBM_CT_TMEM = 0)
-    unsigned tmem_base;  // TMEM allocation (SBM_CT_TMEM = 1)
+    unsigned tmem_base;  // TMEM allocation holding S1 and S4 of the sensitivity columns
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -677,14 +670,15 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
     constexpr int N = SBM_N, NT = (W + XW) * 32;
     const int col0 = warp * C;                     // first sensitivity column (free-parameter index) of this warp
     constexpr int NE = N + (N & 1);
-    SbmCtStore st;
-#if SBM_CT_TMEM
+#if SBM_CT_REGV
+    typedef SbmCtStoreReg<CW * NE> ST;
+    ST st;
+#else
+    typedef SbmCtStoreTmem ST;
+    ST st;
     // this warp's TMEM window: its lane quadrant, 4*C*NE columns per warp of the quadrant (S1 then S4)
     st.t1 = sh.tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 4 * C * NE);
     st.t4 = st.t1 + 2u * CW * NE;
-#else
-    st.v1 = sh.V + (warp * 2 * C * NE) * 32 + lane;
-    st.v4 = st.v1 + CW * NE * 32;
 #endif
     static_assert(CW * N >= 2, "at least one row pair per warp");
     double y[CW][N], s2[CW][N], s3[CW][N];
@@ -696,10 +690,10 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
     for (int c = 0; c < CW; ++c)
 #pragma unroll
         for (int ip = 0; ip < NE / 2; ++ip) {
-            sbm_st_store(st, 1, c * NE + 2 * ip, 0.0, 0.0);
-            sbm_st_store(st, 4, c * NE + 2 * ip, 0.0, 0.0);
+            st.store(1, c * NE + 2 * ip, 0.0, 0.0);
+            st.store(4, c * NE + 2 * ip, 0.0, 0.0);
         }
-    sbm_st_fence();
+    st.fence();
     const double rtol = a.rtol, atol = a.atol;
 
     for (;;) {
@@ -709,7 +703,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
         if (!(cflags & SBM_CT_ALIVE)) break;
         const int info = sh.fl[lane];
         const double h = sh.hb[lane];
-        sbm_ct_cols_begin<CW>(a, info, cflags, h, col0, lane, y, s3, st, sh.pb, sh.trj, sh.ktb);
+        sbm_ct_cols_begin<CW, ST>(a, info, cflags, h, col0, lane, y, s3, st, sh.pb, sh.trj, sh.ktb);
         const bool anyinit = (cflags & SBM_CT_ANYINIT) != 0;
         double sq = 0.0, d0 = 0.0, d1 = 0.0;
         // iteration s: stage s of this warp's columns (s >= 2) and its share of the model at the input of
@@ -719,7 +713,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
             if (s >= 2) {
                 const double* Jp = sh.Jb + (s & 1) * SBM_NJ * 32 + lane;
                 const double* Gw = sh.Gd + ((s & 1) * SBM_NF + col0) * (N + (N & 1)) * 32 + 2 * lane;
-                sbm_ct_cols_stage<CW>(s, h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
+                sbm_ct_cols_stage<CW, ST>(s, h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
             }
             if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
 #ifdef SBM_CT_PRIMAL_REPEAT
@@ -770,7 +764,7 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
 // CL = NF - (W-1)*C) plus XW warps without columns.  Shared-memory carve-up in doubles (sbm_api.cu computes the same
 // size on the host):
 //   2*NJ*32 + 2*NF*NE*32 + 7*N*32 + 2*N*32 + 2*N*32 + NP*32 + (W+3)*32 + 32 + ND*32 + 4*32 + 32 + (NI*32 + 3*32)/2
-//   + 2*W*32 + (SBM_CT_TMEM ? 0 : W*2*C*NE*32)
+//   + 2*W*32       (S1 and S4 of the sensitivity columns live in tensor memory)
 template <int W, int C, int XW>
 __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
 {
@@ -797,7 +791,6 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     sh.ktb = sh.fl + 32;
     sh.cta = sh.ktb + 32;
     sh.park = (double*)(sh.cta + 32);
-    sh.V = sh.park + 2 * W * 32;
     sh.tmem_base = 0;
 
     const int lane = threadIdx.x & 31;
@@ -823,7 +816,9 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
         sh.cta[lane] = 0;
     }
     for (int q = threadIdx.x; q < 2 * W * 32; q += WT * 32) sh.park[q] = 0.0;
-#if SBM_CT_TMEM
+#if SBM_CT_REGV
+    SBM_CT_BAR(WT * 32);
+#else
     // tensor memory for S1 / S4: ceil(W/4) warps per lane quadrant, 4*C*NE columns each (power of two >= 32)
     constexpr int TM_NEED = ((W + 3) / 4) * 4 * C * (N + (N & 1));
     constexpr int TM_COLS = TM_NEED <= 32 ? 32 : TM_NEED <= 64 ? 64 : TM_NEED <= 128 ? 128 : TM_NEED <= 256 ? 256 : 512;
@@ -837,8 +832,6 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     SBM_CT_BAR(WT * 32);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     sh.tmem_base = (unsigned)sh.cta[1];
-#else
-    SBM_CT_BAR(WT * 32);
 #endif
 
     if (XW > 0 && warp >= W) sbm_ct_model_warp<W, C, XW>(a, sh, warp, lane);
@@ -846,11 +839,11 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     else sbm_ct_warp<W, C, C, XW>(a, sh, warp, lane);
 
     // ---- counters: one atomic per CTA ----
-#if SBM_CT_TMEM
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-#endif
+#if SBM_CT_REGV
     SBM_CT_BAR(WT * 32);
-#if SBM_CT_TMEM
+#else
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    SBM_CT_BAR(WT * 32);
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(sh.tmem_base), "r"(TM_COLS) : "memory");

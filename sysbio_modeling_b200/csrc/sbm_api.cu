@@ -138,7 +138,7 @@ struct sbm_model {
     int G = 1, C = 1, block = 128, block_plain = 128;
     int dyn_smem = 0, dyn_smem_plain = 0;
     // CTA-transposed sensitivity kernel (kernels/sbm_dp5_ct.cuh): W sensitivity warps x C columns + 1 state warp
-    int ctW = 0, ctC = 0, ctCS = 0, ctXW = 0, ct_dyn_smem = 0, ct_ctas_per_sm = 0, sm_count = 0;
+    int ctW = 0, ctC = 0, ctCS = 0, ctXW = 0, ct_tmem_cols = 0, ct_dyn_smem = 0, ct_ctas_per_sm = 0, sm_count = 0;
     bool ct_ok = false;
     bool has_rodas = true;
     int layout = 0;              // 0 auto, 1 lane-per-column groups, 2 CTA-transposed
@@ -217,7 +217,7 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     m->layout = desc->sens_layout > 0 ? desc->sens_layout : 0;
     {
         const int N = desc->n_vars, NF = desc->n_free;
-        int NJ = 1, NG = 1, W = 0, C = 0, XW = 0, TM = 0;
+        int NJ = 1, NG = 1, W = 0, C = 0, XW = 0, TM = 0, RV = 0;
         const char* q;
         if ((q = strstr(model_src, "#define SBM_NJ "))) NJ = atoi(q + 15);
         if ((q = strstr(model_src, "#define SBM_NG "))) NG = atoi(q + 15);
@@ -225,16 +225,18 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
         if ((q = strstr(model_src, "#define SBM_CT_C "))) C = atoi(q + 17);
         if ((q = strstr(model_src, "#define SBM_CT_XW "))) XW = atoi(q + 18);
         if ((q = strstr(model_src, "#define SBM_CT_TMEM "))) TM = atoi(q + 20);
+        if ((q = strstr(model_src, "#define SBM_CT_REGV "))) RV = atoi(q + 20);
         (void)NG;
         if (W >= 1 && C >= 1 && NF >= 1) {
             const int CL = NF - (W - 1) * C;
             const long long bytes = 8ll * (2 * NJ * 32 + 2 * NF * (N + (N & 1)) * 32 + 7 * N * 32 + 2 * N * 32 + 2 * N * 32 + desc->n_params * 32 +
                                            (W + 3) * 32 + 32 + 6 * 32 + 4 * 32 + 32) +
-                                    4ll * (8 * 32 + 3 * 32) + 8ll * 2 * W * 32 +
-                                    (TM ? 0ll : 8ll * W * 2 * C * (N + (N & 1)) * 32);
+                                    4ll * (8 * 32 + 3 * 32) + 8ll * 2 * W * 32;
             const int tm_need = ((W + 3) / 4) * 4 * C * (N + (N & 1));
-            if (CL >= 1 && CL <= C && CL * N >= 2 && W + XW <= 32 && bytes <= 227 * 1024 && (!TM || tm_need <= 512)) {
+            if (CL >= 1 && CL <= C && CL * N >= 2 && W + XW <= 32 && bytes <= 227 * 1024 && ((TM == 1 && tm_need <= 512) || RV == 1)) {
                 m->ctW = W; m->ctC = C; m->ctCS = CL; m->ctXW = XW; m->ct_dyn_smem = (int)bytes; m->ct_ok = true;
+                // tensor-memory columns one CTA allocates (power of two >= 32): bounds the CTAs that can run on an SM
+                m->ct_tmem_cols = RV ? 0 : tm_need <= 32 ? 32 : tm_need <= 64 ? 64 : tm_need <= 128 ? 128 : tm_need <= 256 ? 256 : 512;
             }
         }
         if (m->layout == 2 && !m->ct_ok) { delete m; return fail(SBM_E_INVALID, "CTA-transposed layout does not fit this model"); }
@@ -342,6 +344,7 @@ static int ensure_loaded(sbm_model* m)
         RT(cudaGetDevice(&dev));
         RT(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev));
         DRV(driver().cuOccupancy_(&m->ct_ctas_per_sm, m->dp5_ct.fn, (m->ctW + m->ctXW) * 32, (size_t)m->ct_dyn_smem));
+        if (m->ct_tmem_cols > 0 && m->ct_ctas_per_sm > 512 / m->ct_tmem_cols) m->ct_ctas_per_sm = 512 / m->ct_tmem_cols;
         if (m->ct_ctas_per_sm < 1) m->ct_ok = false;
     }
     m->loaded = true;

@@ -846,12 +846,14 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     L.append('#define SBM_CT_W %d' % W_ct)
     L.append('#define SBM_CT_C %d' % C_ct)
     L.append('#define SBM_CT_XW %d' % XW_ct)
-    # S1 / S4 of the sensitivity columns in tensor memory (1) or in shared memory (0)
+    # S1 / S4 of the sensitivity columns live in tensor memory: ceil(W/4) warps per lane quadrant, 4*C*NE columns each
     NE_ct = N + (N & 1)
-    tmem = 1 if (W_ct and ((W_ct + 3) // 4) * 4 * C_ct * NE_ct <= 512) else 0
-    if 'SBM_CT_TMEM' in _os.environ:
-        tmem = int(_os.environ['SBM_CT_TMEM'])
-    L.append('#define SBM_CT_TMEM %d' % tmem)
+    # ... except for small systems run by one thread per trajectory, whose five vectors fit the register file
+    regv = 1 if (W_ct == 1 and C_ct * NE_ct <= 16) else 0
+    if 'SBM_CT_REGV' in _os.environ:
+        regv = int(_os.environ['SBM_CT_REGV']) if W_ct else 0
+    L.append('#define SBM_CT_REGV %d' % regv)
+    L.append('#define SBM_CT_TMEM %d' % (1 if (W_ct and not regv and ((W_ct + 3) // 4) * 4 * C_ct * NE_ct <= 512) else 0))
     if W_ct:
         ysyms = [sp.Symbol('y[%d]' % i, real=True) for i in range(N)]
         _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct)
