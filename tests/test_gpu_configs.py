@@ -335,3 +335,32 @@ def test_c5_egfr_scale_ssr_ensemble():
     for b in (0, 17, 511):
         ssr0 = oracle.sum_square_residuals(theta[b])
         assert abs(out['ssr'][b] - ssr0) <= 1e-6 * ssr0 + 1e-9, (b, out['ssr'][b], ssr0)
+
+
+def test_cta_transposed_kernel_failure_status_and_queue_refill():
+    """CTA-transposed sensitivity kernel: (1) a step budget that is too small gives status max_steps and NaN rows for
+    every trajectory; (2) more trajectories than one wave of persistent CTAs (lanes refill from the global queue):
+    every trajectory is integrated exactly once and matches a stand-alone solve."""
+    import sysbio_modeling_b200 as sb
+    from sysbio_modeling_b200 import model_files
+    mod = model_files.module('mapk_kholodenko')
+    y0 = np.array(mod.initial_conditions)
+    t = np.concatenate([[0.0], np.linspace(150, 3000, 20)])
+    om = sb.OdeModel.from_model_file(model_files.path('mapk_kholodenko'), max_steps=5)
+    assert om.compiled.info()['sens_layout'] == 2
+    nominal = np.array([mod.nominal[k] for k in om.param_order])
+    P = nominal * np.exp(0.25 * np.random.default_rng(12).standard_normal((45, 22)))
+    y, S = om.calc_jacobian_batch(P, t, y0)
+    assert (om.last_status == 1).all()                      # SBM_ERR_MAXSTEPS
+    assert np.isnan(y[:, 1:]).all() and np.isnan(S[:, 1:]).all()
+    # queue refill: 148 SMs x 32 lanes = 4,736 trajectories in flight; take more, at a loose tolerance
+    om = sb.OdeModel.from_model_file(model_files.path('mapk_kholodenko'), rtol=1e-6, atol=1e-6)
+    nb = 4736 + 1000 + 37
+    P = nominal * np.exp(0.25 * np.random.default_rng(13).standard_normal((nb, 22)))
+    y, S = om.calc_jacobian_batch(P, t, y0)
+    assert (om.last_status == 0).all()
+    assert om.last_counters['trajectories'] == nb
+    assert np.isfinite(y).all() and np.isfinite(S).all()
+    for b in (0, 31, 4735, 4736, nb - 1):
+        y1, S1 = om.calc_jacobian_batch(P[b:b + 1], t, y0)
+        assert np.array_equal(y1[0], y[b]) and np.array_equal(S1[0], S[b])      # same arithmetic, any lane
