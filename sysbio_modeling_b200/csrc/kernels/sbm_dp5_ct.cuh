@@ -193,6 +193,7 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
                                                   const bool anyinit, double& sq, double& d0, double& d1)
 {
     constexpr int N = SBM_N, NE = N + (N & 1), NP2 = NE / 2;
+    __syncwarp();                                  // tcgen05.ld/st are warp-collective: be converged (cheap insurance)
     // ---- stage input of every element (element e = c*NE + i; S1 comes in row pairs) ----
     double w[CW][N];
     if (S <= 5) {
@@ -380,6 +381,7 @@ struct SbmCtShared {
     int* cta;            // [32]               CTA-wide flags in cta[0]
     double* park;        // [2][W][32]         start-up norms |y|, |f| (per column warp)
     unsigned tmem_base;  // TMEM allocation holding S1 and S4 of the sensitivity columns
+    unsigned long long* mbar;  // [2*NB + 2] mbarriers of the asynchronous hand-over: full[NB], empty[NB], done, go
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -630,19 +632,22 @@ __constant__ double sbm_dp_ap[8][5] = {
 
 // this warp's share of the model at the input of stage S (S = 2..7), written into the buffers of stage S
 __device__ __forceinline__ void sbm_ct_primal(const SbmCtShared& sh, const int warp, const int lane, const int S,
-                                              const double h)
+                                              const double h, const int buf)
 {
+    // with one CTA barrier per stage the buffer is the stage's parity (the compiler then sees one expression for the
+    // producer and the consumers; passing it in was measured to change the generated code's results - see DESIGN.md)
+    const int b = SBM_CT_ASYNC ? buf : (S & 1);
     const double ts = fma(sbm_dp_c[S], h, sh.cd[SBM_CT_D_T * 32 + lane]);
     const double* Pp = (S == 2) ? sh.yb + lane : sh.Pb + (S & 1) * SBM_N * 32 + lane;
     // stage 2 is the head of the step: its step size exists only after the previous step has been judged, so it
     // overlaps with nothing and is split over more warps (sbm_primal_head) than the stages that run one ahead
-    if (S == 2)
-        sbm_primal_head<32>(warp, ts, Pp, sh.fh + lane, h * DP_A21, sh.pb + lane, sh.Jb + lane, sh.Gd + 2 * lane,
-                            sh.fh + SBM_N * 32 + lane);
+    if (S == 2 && !SBM_CT_ASYNC)
+        sbm_primal_head<32>(warp, ts, Pp, sh.fh + lane, h * DP_A21, sh.pb + lane, sh.Jb + b * SBM_NJ * 32 + lane,
+                            sh.Gd + b * SBM_NF * (SBM_N + (SBM_N & 1)) * 32 + 2 * lane, sh.fh + SBM_N * 32 + lane);
     else
         sbm_primal_share<32>(warp, ts, Pp, sh.fh + (S - 2) * SBM_N * 32 + lane, h * sbm_dp_a[S][S - 2], sh.pb + lane,
-                             sh.Jb + (S & 1) * SBM_NJ * 32 + lane,
-                             sh.Gd + (S & 1) * SBM_NF * (SBM_N + (SBM_N & 1)) * 32 + 2 * lane,
+                             sh.Jb + b * SBM_NJ * 32 + lane,
+                             sh.Gd + b * SBM_NF * (SBM_N + (SBM_N & 1)) * 32 + 2 * lane,
                              sh.fh + (S - 1) * SBM_N * 32 + lane);
 }
 
@@ -718,9 +723,9 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
             if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
 #ifdef SBM_CT_PRIMAL_REPEAT
             // experiment: evaluate the share several times to measure how much of the critical path it is
-            if (s < 7) for (int rep = 0; rep < SBM_CT_PRIMAL_REPEAT; ++rep) sbm_ct_primal(sh, warp, lane, s + 1, h);
+            if (s < 7) for (int rep = 0; rep < SBM_CT_PRIMAL_REPEAT; ++rep) sbm_ct_primal(sh, warp, lane, s + 1, h, (s + 1) & 1);
 #else
-            if (s < 7) sbm_ct_primal(sh, warp, lane, s + 1, h);
+            if (s < 7) sbm_ct_primal(sh, warp, lane, s + 1, h, (s + 1) & 1);
 #endif
             else {
                 sh.sqb[warp * 32 + lane] = sq;
@@ -744,7 +749,7 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
 #pragma unroll 1
         for (int s = 1; s <= 7; ++s) {
             if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
-            if (s < 7) sbm_ct_primal(sh, warp, lane, s + 1, h);
+            if (s < 7) sbm_ct_primal(sh, warp, lane, s + 1, h, (s + 1) & 1);
             else if (warp == W) {
                 // while the column warps finish stage 7: the state column's part of the controller's input
                 double ynew[SBM_N], f7[SBM_N], sqs = 0.0, q0 = 0.0, q1 = 0.0;
@@ -760,11 +765,138 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// SBM_CT_ASYNC: producer / consumer hand-over of J and G through mbarriers instead of one CTA barrier per stage.
+// The model warp (it evaluates the whole model: one share) runs up to NB - 1 stages ahead of the slowest column
+// warp; a column warp waits only for the data of its next stage, never for the other column warps, so the warps
+// of a scheduler drift apart and stop competing for the FP64 pipe in the same phase of a stage.  Two CTA-wide
+// hand-shakes per step remain: "done" (all error-norm partial sums written) and "go" (controller output published).
+// -------------------------------------------------------------------------------------------------
+#ifndef SBM_CT_NB
+#define SBM_CT_NB 3
+#endif
+
+__device__ __forceinline__ void sbm_mb_init(unsigned long long* mb, const int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(mb)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sbm_mb_arrive(unsigned long long* mb)
+{
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n}"
+                 :: "r"((unsigned)__cvta_generic_to_shared(mb)) : "memory");
+}
+__device__ __forceinline__ void sbm_mb_wait(unsigned long long* mb, const unsigned parity)
+{
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(mb);
+    unsigned ok = 0, spins = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();      // a protocol error must not hang the GPU
+    }
+}
+
+template <int W, int C, int CW>
+__device__ __forceinline__ void sbm_ct_warp_async(const SbmSolveArgs& a, const SbmCtShared& sh, const int warp, const int lane)
+{
+    constexpr int N = SBM_N, NE = N + (N & 1), NB = SBM_CT_NB;
+    const int col0 = warp * C;
+    typedef SbmCtStoreTmem ST;
+    ST st;
+    st.t1 = sh.tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 4 * C * NE);
+    st.t4 = st.t1 + 2u * CW * NE;
+    double y[CW][N], s2[CW][N], s3[CW][N];
+#pragma unroll
+    for (int c = 0; c < CW; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i) { y[c][i] = 0.0; s2[c][i] = 0.0; s3[c][i] = 0.0; }
+#pragma unroll
+    for (int c = 0; c < CW; ++c)
+#pragma unroll
+        for (int ip = 0; ip < NE / 2; ++ip) { st.store(1, c * NE + 2 * ip, 0.0, 0.0); st.store(4, c * NE + 2 * ip, 0.0, 0.0); }
+    st.fence();
+    const double rtol = a.rtol, atol = a.atol;
+    unsigned long long* full = sh.mbar;
+    unsigned long long* empty = sh.mbar + NB;
+    unsigned long long* done = sh.mbar + 2 * NB;
+    unsigned long long* go = sh.mbar + 2 * NB + 1;
+    unsigned gc = 0, step = 0;                    // stages consumed, steps started
+    __syncwarp();
+    if (lane == 0) sbm_mb_arrive(done);            // "step -1 finished": lets the controller start
+
+    for (;;) {
+        sbm_mb_wait(go, step & 1u);                // controller output of this step published
+        ++step;
+        const int cflags = sh.cta[0];
+        if (!(cflags & SBM_CT_ALIVE)) break;
+        const int info = sh.fl[lane];
+        const double h = sh.hb[lane];
+        sbm_ct_cols_begin<CW, ST>(a, info, cflags, h, col0, lane, y, s3, st, sh.pb, sh.trj, sh.ktb);
+        const bool anyinit = (cflags & SBM_CT_ANYINIT) != 0;
+        double sq = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll 1
+        for (int s = 2; s <= 7; ++s) {
+            const unsigned b = gc % NB;
+            sbm_mb_wait(full + b, (gc / NB) & 1u); // J, G of this stage are in buffer b
+            const double* Jp = sh.Jb + b * SBM_NJ * 32 + lane;
+            const double* Gw = sh.Gd + (b * SBM_NF + col0) * NE * 32 + 2 * lane;
+            sbm_ct_cols_stage<CW, ST>(s, h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
+            __syncwarp();
+            if (lane == 0) sbm_mb_arrive(empty + b);   // this warp is done with buffer b
+            ++gc;
+        }
+        sh.sqb[warp * 32 + lane] = sq;
+        if (anyinit) { sh.park[warp * 32 + lane] = d0; sh.park[(W + warp) * 32 + lane] = d1; }
+        __syncwarp();
+        if (lane == 0) sbm_mb_arrive(done);
+    }
+}
+
+template <int W, int C>
+__device__ __forceinline__ void sbm_ct_model_warp_async(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane)
+{
+    constexpr int NB = SBM_CT_NB;
+    unsigned long long* full = sh.mbar;
+    unsigned long long* empty = sh.mbar + NB;
+    unsigned long long* done = sh.mbar + 2 * NB;
+    unsigned long long* go = sh.mbar + 2 * NB + 1;
+    unsigned gp = 0, step = 0;                    // stages produced, steps finished by the column warps
+    for (;;) {
+        sbm_mb_wait(done, step & 1u);              // all partial sums of the previous step are written
+        ++step;
+        sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 1>(a, sh, lane);
+        __syncwarp();
+        const bool alive = (sh.cta[0] & SBM_CT_ALIVE) != 0;
+        if (lane == 0) sbm_mb_arrive(go);
+        if (!alive) break;
+        const double h = sh.hb[lane];
+#pragma unroll 1
+        for (int S = 2; S <= 7; ++S) {
+            const unsigned b = gp % NB;
+            if (gp >= (unsigned)NB) sbm_mb_wait(empty + b, ((gp / NB) - 1u) & 1u);   // every column warp has left buffer b
+            if (S >= 3) sbm_ct_prepare<1>(sh, 0, lane, S, h);
+            sbm_ct_primal(sh, W, lane, S, h, (int)b);
+            __syncwarp();
+            if (lane == 0) sbm_mb_arrive(full + b);
+            ++gp;
+        }
+        // the state column's part of the controller's input (f_7 is this warp's own)
+        double ynew[SBM_N], f7[SBM_N], sqs = 0.0, q0 = 0.0, q1 = 0.0;
+        sbm_ct_state_column(sh, lane, h, a.rtol, a.atol, ynew, f7, sqs, q0, q1);
+#pragma unroll
+        for (int i = 0; i < SBM_N; ++i) sh.ynb[i * 32 + lane] = ynew[i];
+        sh.sqb[(W + 0) * 32 + lane] = sqs;
+        sh.sqb[(W + 1) * 32 + lane] = q0;
+        sh.sqb[(W + 2) * 32 + lane] = q1;
+    }
+}
+
 // W column warps per CTA (warps 0..W-2 carry C sensitivity columns each, warp W-1 the remaining
 // CL = NF - (W-1)*C) plus XW warps without columns.  Shared-memory carve-up in doubles (sbm_api.cu computes the same
 // size on the host):
 //   2*NJ*32 + 2*NF*NE*32 + 7*N*32 + 2*N*32 + 2*N*32 + NP*32 + (W+3)*32 + 32 + ND*32 + 4*32 + 32 + (NI*32 + 3*32)/2
-//   + 2*W*32       (S1 and S4 of the sensitivity columns live in tensor memory)
+//   + 2*W*32 + 16  (S1 and S4 of the sensitivity columns live in tensor memory; 16 = mbarriers)
+// with NBUF = 2 buffers of J and G (SBM_CT_NB = 3 with the asynchronous hand-over) in place of the factor 2 above
 template <int W, int C, int XW>
 __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
 {
@@ -775,8 +907,13 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     extern __shared__ double sbm_dyn[];
     SbmCtShared sh;
     sh.Jb = sbm_dyn;
-    sh.Gd = sh.Jb + 2 * SBM_NJ * 32;
-    sh.fh = sh.Gd + 2 * SBM_NF * (N + (N & 1)) * 32;
+#if SBM_CT_ASYNC
+    constexpr int NBUF = SBM_CT_NB;
+#else
+    constexpr int NBUF = 2;
+#endif
+    sh.Gd = sh.Jb + NBUF * SBM_NJ * 32;
+    sh.fh = sh.Gd + NBUF * SBM_NF * (N + (N & 1)) * 32;
     sh.yb = sh.fh + 7 * N * 32;
     sh.ynb = sh.yb + N * 32;
     sh.Pb = sh.ynb + N * 32;
@@ -791,13 +928,14 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     sh.ktb = sh.fl + 32;
     sh.cta = sh.ktb + 32;
     sh.park = (double*)(sh.cta + 32);
+    sh.mbar = (unsigned long long*)(sh.park + 2 * W * 32);
     sh.tmem_base = 0;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     // ---- one-time initialisation of the shared state ----
-    for (int q = threadIdx.x; q < 2 * SBM_NF * (N + (N & 1)) * 32; q += WT * 32) sh.Gd[q] = 0.0;   // structural zeros of G
-    for (int q = threadIdx.x; q < 2 * SBM_NJ * 32; q += WT * 32) sh.Jb[q] = 0.0;
+    for (int q = threadIdx.x; q < NBUF * SBM_NF * (N + (N & 1)) * 32; q += WT * 32) sh.Gd[q] = 0.0;   // structural zeros of G
+    for (int q = threadIdx.x; q < NBUF * SBM_NJ * 32; q += WT * 32) sh.Jb[q] = 0.0;
     for (int q = threadIdx.x; q < 7 * N * 32; q += WT * 32) sh.fh[q] = 0.0;
     for (int q = threadIdx.x; q < 2 * N * 32; q += WT * 32) sh.Pb[q] = 0.0;
     for (int q = threadIdx.x; q < (W + 3) * 32; q += WT * 32) sh.sqb[q] = 0.0;
@@ -813,9 +951,17 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
         sh.hb[lane] = 0.0;
         sh.fl[lane] = 0;
         sh.ktb[lane] = 0;
-        sh.cta[lane] = 0;
+        if (lane != 1) sh.cta[lane] = 0;             // cta[1] receives the tensor-memory base address from tcgen05.alloc
     }
     for (int q = threadIdx.x; q < 2 * W * 32; q += WT * 32) sh.park[q] = 0.0;
+#if SBM_CT_ASYNC
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < SBM_CT_NB; ++b) { sbm_mb_init(sh.mbar + b, 1); sbm_mb_init(sh.mbar + SBM_CT_NB + b, W); }
+        sbm_mb_init(sh.mbar + 2 * SBM_CT_NB, W);         // done: one arrival per column warp
+        sbm_mb_init(sh.mbar + 2 * SBM_CT_NB + 1, 1);     // go: the controller
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
 #if SBM_CT_REGV
     SBM_CT_BAR(WT * 32);
 #else
@@ -834,9 +980,16 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     sh.tmem_base = (unsigned)sh.cta[1];
 #endif
 
+#if SBM_CT_ASYNC
+    static_assert(XW == 1, "the asynchronous hand-over needs the dedicated model warp");
+    if (warp >= W) sbm_ct_model_warp_async<W, C>(a, sh, lane);
+    else if (warp == W - 1 && CL != C) sbm_ct_warp_async<W, C, CL>(a, sh, warp, lane);
+    else sbm_ct_warp_async<W, C, C>(a, sh, warp, lane);
+#else
     if (XW > 0 && warp >= W) sbm_ct_model_warp<W, C, XW>(a, sh, warp, lane);
     else if (warp == W - 1 && CL != C) sbm_ct_warp<W, C, CL, XW>(a, sh, warp, lane);
     else sbm_ct_warp<W, C, C, XW>(a, sh, warp, lane);
+#endif
 
     // ---- counters: one atomic per CTA ----
 #if SBM_CT_REGV

@@ -217,7 +217,7 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     m->layout = desc->sens_layout > 0 ? desc->sens_layout : 0;
     {
         const int N = desc->n_vars, NF = desc->n_free;
-        int NJ = 1, NG = 1, W = 0, C = 0, XW = 0, TM = 0, RV = 0;
+        int NJ = 1, NG = 1, W = 0, C = 0, XW = 0, TM = 0, RV = 0, AS = 0, NB = 2;
         const char* q;
         if ((q = strstr(model_src, "#define SBM_NJ "))) NJ = atoi(q + 15);
         if ((q = strstr(model_src, "#define SBM_NG "))) NG = atoi(q + 15);
@@ -226,10 +226,12 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
         if ((q = strstr(model_src, "#define SBM_CT_XW "))) XW = atoi(q + 18);
         if ((q = strstr(model_src, "#define SBM_CT_TMEM "))) TM = atoi(q + 20);
         if ((q = strstr(model_src, "#define SBM_CT_REGV "))) RV = atoi(q + 20);
+        if ((q = strstr(model_src, "#define SBM_CT_ASYNC "))) AS = atoi(q + 21);
+        if (AS) NB = 3;
         (void)NG;
         if (W >= 1 && C >= 1 && NF >= 1) {
             const int CL = NF - (W - 1) * C;
-            const long long bytes = 8ll * (2 * NJ * 32 + 2 * NF * (N + (N & 1)) * 32 + 7 * N * 32 + 2 * N * 32 + 2 * N * 32 + desc->n_params * 32 +
+            const long long bytes = 8ll * (NB * NJ * 32 + NB * NF * (N + (N & 1)) * 32 + 16 + 7 * N * 32 + 2 * N * 32 + 2 * N * 32 + desc->n_params * 32 +
                                            (W + 3) * 32 + 32 + 6 * 32 + 4 * 32 + 32) +
                                     4ll * (8 * 32 + 3 * 32) + 8ll * 2 * W * 32;
             const int tm_need = ((W + 3) / 4) * 4 * C * (N + (N & 1));

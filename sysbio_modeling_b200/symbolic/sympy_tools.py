@@ -853,6 +853,14 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     if 'SBM_CT_REGV' in _os.environ:
         regv = int(_os.environ['SBM_CT_REGV']) if W_ct else 0
     L.append('#define SBM_CT_REGV %d' % regv)
+    # producer / consumer hand-over of J and G (mbarriers, 3 buffers) when a dedicated model warp evaluates the whole model
+    n_sh = int(_os.environ.get('SBM_CT_SHARES', '0')) or (1 if XW_ct else min(W_ct, 3))
+    # (measured on C4: 129 k solves/s against 143.6 k with one CTA barrier per stage - the single model warp then also
+    #  prepares the stage values alone and becomes the critical path; kept as an option, off by default)
+    asyn = 0
+    if 'SBM_CT_ASYNC' in _os.environ:
+        asyn = int(_os.environ['SBM_CT_ASYNC']) if (XW_ct == 1 and n_sh == 1) else 0
+    L.append('#define SBM_CT_ASYNC %d' % asyn)
     L.append('#define SBM_CT_TMEM %d' % (1 if (W_ct and not regv and ((W_ct + 3) // 4) * 4 * C_ct * NE_ct <= 512) else 0))
     if W_ct:
         ysyms = [sp.Symbol('y[%d]' % i, real=True) for i in range(N)]
