@@ -835,9 +835,9 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     L.append('}')
     W_ct, C_ct = ct_layout(N, NF, ct_cols)
     import os as _os
-    # one extra warp without columns (it only evaluates the model) when that keeps the register budget:
-    # 9..11 column warps + 1 = at most 12 warps = 168 registers per thread, as without it
-    XW_ct = 1 if 9 <= W_ct <= 11 else 0
+    # one extra warp without columns: it evaluates the whole model and runs the step controller, so that the column
+    # warps (the critical path) carry no share of the model.  At most 12 warps = 168 registers per thread.
+    XW_ct = 1 if 2 <= W_ct <= 11 else 0
     if 'SBM_CT_XW' in _os.environ:
         XW_ct = int(_os.environ['SBM_CT_XW']) if W_ct else 0
     L.append('// dense G of the CTA-transposed kernel: element e = parameter * NE + state (NE = N rounded up to even) lives')

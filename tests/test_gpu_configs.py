@@ -293,6 +293,22 @@ def test_cta_transposed_layout_matches_warp_group_layout():
         (y1, S1), (y2, S2) = out[1], out[2]
         assert np.all(np.abs(y1 - y2) <= 1e-8 * (1 + np.abs(y1)))
         assert np.all(np.abs(S1 - S2) <= 1e-7 * (1 + np.abs(S1)))
+    # other shapes of the same kernel on the reversible Michaelis-Menten model: 4 column warps x 1 column and
+    # 2 x 2 (each plus the model warp, S1 / S4 in tensor memory) against one thread per trajectory (registers)
+    mod = model_files.module('reversible_mm')
+    tgrid = np.concatenate([[0.0], np.linspace(0.25, 4, 16)])
+    res = {}
+    for cols in (0, 1, 2):
+        om = sb.OdeModel.from_model_file(model_files.path('reversible_mm'), sens_layout=2, cols_per_lane=cols)
+        info = om.compiled.info()
+        assert info['sens_layout'] == 2 and info['ct_warps'] == {0: 1, 1: 5, 2: 3}[cols]
+        nominal = np.array([mod.nominal[k] for k in om.param_order])
+        P = nominal * np.exp(0.3 * np.random.default_rng(14).standard_normal((100, 4)))
+        res[cols] = om.calc_jacobian_batch(P, tgrid, np.array(mod.initial_conditions))
+        assert (om.last_status == 0).all()
+    for cols in (1, 2):
+        assert np.all(np.abs(res[cols][0] - res[0][0]) <= 1e-9 * (1 + np.abs(res[0][0])))
+        assert np.all(np.abs(res[cols][1] - res[0][1]) <= 1e-8 * (1 + np.abs(res[0][1])))
 
 
 def test_c5_egfr_scale_ssr_ensemble():
