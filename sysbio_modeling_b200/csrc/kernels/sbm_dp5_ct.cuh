@@ -142,17 +142,17 @@ struct SbmCtStoreTmem {
     }
     __device__ __forceinline__ void wait(SbmCtPair& v, double& a, double& b) const
     {
-        // the registers are valid only after the wait: tie them to it so nothing reads them earlier
-        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v.r0), "+r"(v.r1), "+r"(v.r2), "+r"(v.r3));
-        a = __hiloint2double((int)v.r1, (int)v.r0);
-        b = __hiloint2double((int)v.r3, (int)v.r2);
+        // the 32-bit registers are valid only after the wait: the doubles are formed inside the same asm block, so
+        // nothing can read them earlier (and ptxas coalesces the moves of adjacent registers away)
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n\tmov.b64 %0, {%2, %3};\n\tmov.b64 %1, {%4, %5};"
+                     : "=d"(a), "=d"(b) : "r"(v.r0), "r"(v.r1), "r"(v.r2), "r"(v.r3));
     }
     __device__ __forceinline__ void store(const int slot, const int e0, const double a, const double b)
     {
         const unsigned ta = (slot == 1 ? t1 : t4) + 2u * e0;
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                     :: "r"(ta), "r"(__double2loint(a)), "r"(__double2hiint(a)), "r"(__double2loint(b)),
-                        "r"(__double2hiint(b)) : "memory");
+        asm volatile("{\n\t.reg .b32 q0, q1, q2, q3;\n\tmov.b64 {q0, q1}, %1;\n\tmov.b64 {q2, q3}, %2;\n\t"
+                     "tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {q0, q1, q2, q3};\n\t}"
+                     :: "r"(ta), "d"(a), "d"(b) : "memory");
     }
     __device__ __forceinline__ void fence() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 };
