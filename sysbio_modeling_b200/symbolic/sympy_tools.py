@@ -610,11 +610,23 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0, f
         if not head else []
     if not share_warps:
         share_warps = list(range(W, WT)) + [w for w in ct_share_warps(WT, n_shares + XW) if w < W][:max(n_shares - XW, 0)]
-    loads = []
+    colwork = []
     for w in range(WT):
         real = max(0, min(C, NF - w * C)) if w < W else 0
-        # head = the model at the input of stage 2, evaluated while the column warps have nothing else to do
-        base = 0.0 if head else ((float(nnzJ + real * (nnzJ + 12 * N)) if real else 0.0) + (60.0 if w == 0 else 0.0))
+        colwork.append((float(nnzJ + real * (nnzJ + 12 * N)) if real else 0.0) + (60.0 if (w == 0 and not XW) else 0.0))
+    loads = []
+    for w in range(WT):
+        if head:
+            # the model at the input of stage 2, evaluated while the column warps have nothing else to do
+            base = 0.0
+        elif XW:
+            # several shares with a model warp: balance the load of the schedulers (warp w runs on scheduler w % 4), not
+            # of the warps - the model warp's scheduler hosts one column warp fewer.  Measured on C4: 1 / 4 / 7 / 10
+            # shares = 141.8 / 124.5 / 118.9 / 123.1 k solves/s, i.e. ANY slice of the model on a column warp costs
+            # more than the balance gains (the column warps' own latency is the critical path): default 1 share.
+            base = sum(colwork[v] for v in range(w % 4, WT, 4)) + (80.0 if w >= W else 0.0)
+        else:
+            base = colwork[w]
         loads.append(base + (0.0 if w in share_warps else 1e9))
     have = [set() for _ in range(WT)]
     mine = [[] for _ in range(WT)]
