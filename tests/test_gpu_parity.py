@@ -207,3 +207,28 @@ def test_fp64_peak_microbenchmark():
     from sysbio_modeling_b200 import _lib
     tf, ms = _lib.fp64_peak()
     assert 5.0 < tf < 100.0
+
+
+def test_scipy_leastsq_through_the_gpu_backend(golden):
+    """Reference tests/test_Project.py:202-213, 351-357: scipy.optimize.leastsq driven by Project.residuals and
+    Project.calc_project_jacobian (the reference only smoke-tests the calls).  Here both callbacks go through the CUDA
+    path; from a perturbed start on the Michaelis-Menten 'sum' project the fit must bring the objective back down to
+    the grid-snapping floor (1.4e-6 at the generating parameters), and the result must agree with the CPU oracle."""
+    from scipy.optimize import leastsq
+    proj, oracle = project_mm_sum(golden)
+    g = golden['project_mm_sum']
+    mine = [n.split(' ')[0] for n in proj.get_ordered_project_params()]
+    th = theta_by_name(mine, g['project_order'], g['points'][0]['theta'])
+    pert = dict(zip(['vmax', 'km', 'k_synt_s', 'k_deg_s', 'k_deg_p'], [0.3, -0.2, 0.1, 0.25, -0.15]))
+    x0 = th + np.array([pert[n] for n in mine])
+    ssr0 = proj.calc_sum_square_residuals(x0)
+    assert ssr0 > 1e-3
+    x, ier = leastsq(lambda v: np.asarray(proj.residuals(v)), x0, Dfun=lambda v: proj.calc_project_jacobian(v).values,
+                     ftol=1e-3, maxfev=5000)
+    assert ier in (1, 2, 3, 4)
+    ssr = proj.calc_sum_square_residuals(x)
+    assert ssr < 1e-5 and ssr < 1e-2 * ssr0
+    xo = np.zeros_like(x)                     # every MM parameter is Global here: oracle index by parameter name
+    for name, v in zip(mine, x):
+        xo[oracle.project_param_idx[name]['Global']] = v
+    assert abs(ssr - oracle.sum_square_residuals(xo)) <= 1e-6 * ssr + 1e-11
