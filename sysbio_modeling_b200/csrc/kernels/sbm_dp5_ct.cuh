@@ -67,13 +67,39 @@
 #define SBM_CT_NI       8
 
 #define SBM_CT_BAR(nt) asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory")
+#define SBM_CT_EM 4           /* rows of one output time staged in shared memory (more rows take the slow path) */
 
-// reciprocal for error weights: hardware seed + one Newton step (relative error ~1e-10, plenty for a norm)
+#ifdef SBM_CT_PROF
+// experiment (-DSBM_CT_PROF=<column warp>): clocks of the eight barrier intervals of a step and the busy part of each
+// for the model warp and one column warp, printed by CTA 0.  The barrier is "deferred blocking": a clock read right after it
+// may execute before the barrier completes, so the read is made to depend on a shared-memory load issued after the barrier.
+__device__ __forceinline__ long long sbm_ct_clock_after_barrier(const int* cta)
+{
+    const int dep = *reinterpret_cast<const volatile int*>(cta);
+    long long t;
+    asm volatile("{\n\t.reg .b32 d;\n\tmov.b32 d, %1;\n\tmov.u64 %0, %%clock64;\n\t}" : "=l"(t) : "r"(dep) : "memory");
+    return t;
+}
+#endif
+
+// reciprocal for error weights: the hardware seed alone (relative error <= 1e-6, measured in tests/cuda/check_device_math.cu):
+// a weight of the error norm needs no more, and stage 7 of the column warps is on the critical path
 __device__ __forceinline__ double sbm_rcp_fast(const double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
+// max(|a|, |b|) for an error weight, decided by the upper 32 bits only: values that agree in sign-less exponent and
+// the upper 20 mantissa bits may give either one (a relative difference <= 2^-20 in the weight, nothing for a norm).
+// There is no FP64 max instruction: fmax(fabs(a), fabs(b)) expands to DSETP + two selects + ~5 moves per element; this is
+// 2 LOP3 + ISETP + 2 SEL on the integer pipe.  NaN propagates (its upper word is the largest).
+__device__ __forceinline__ double sbm_absmax_hi(const double a, const double b)
+{
+    const int ha = __double2hiint(a) & 0x7fffffff, hb = __double2hiint(b) & 0x7fffffff;
+    const bool ta = ha >= hb;
+    return __hiloint2double(ta ? ha : hb, ta ? __double2loint(a) : __double2loint(b));
 }
 
 // stage input from the vectors of one element
@@ -254,7 +280,7 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
                 for (int r = 0; r < 2; ++r) {
                     if (r == 0 || two) {
                         const int i = i0 + r;
-                        const double isk = sbm_rcp_fast(fma(rtol, fmax(fabs(y[c][i]), fabs(s3[c][i])), atol));
+                        const double isk = sbm_rcp_fast(fma(rtol, sbm_absmax_hi(y[c][i], s3[c][i]), atol));
                         const double q = (r == 0 ? v4a : v4b) * isk;
                         sq = fma(q, q, sq);
                         if (anyinit) {
@@ -270,14 +296,89 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
     st.fence();
 }
 
+// shared-memory views of one CTA
+struct SbmCtShared {
+    double* Jb;          // [2][NJ][32]        J of the stage being consumed / produced
+    double* Gd;          // [2][NF*NE/2][32][2] dense G (column-major per parameter, row pairs adjacent), zeros stay 0
+    double* fh;          // [7][N][32]         stage derivatives f_1..f_7 of the state column
+    double* yb;          // [N][32]            state y at the start of the step
+    double* ynb;         // [N][32]            5th-order state of the step just taken (prepared by the model warp)
+    double* Pb;          // [2][N][32]         partial stage values y + h sum_{j<S-1} a_Sj f_j, prepared one iteration ahead
+    double* pb;          // [NP][32]           model parameters of each lane's trajectory
+    double* sqb;         // [W+3][32]          partial sums of the squared error norm (per column warp), then the state
+                         //                    column's error / |y| / |f| sums
+    double* hb;          // [32]               step of each lane (0: zero-length step / idle)
+    double* cd;          // [SBM_CT_ND][32]    controller doubles
+    unsigned long long* cnt;   // [4][32]      steps, rejects, rhs evaluations, trajectories
+    long long* trj;      // [32]               trajectory id
+    int* ci;             // [SBM_CT_NI][32]    controller ints
+    int* fl;             // [32]               per-lane flags of this step
+    int* ktb;            // [32]               output-time index to emit
+    int* cta;            // [32]               CTA-wide flags in cta[0]
+    double* park;        // [2][W][32]         start-up norms |y|, |f| (per column warp)
+    unsigned long long* em_mask;  // [SBM_CT_EM][32]  rows of the output time being emitted: state mask ...
+    long long* em_off;   // [SBM_CT_EM][32]    ... and offset of the row in the Jacobian output (staged by the controller)
+    int* em_n;           // [32]               number of rows of that output time
+    int* pcb;            // [NP][32]           project column of each model parameter of the lane's experiment (-1: fixed)
+    unsigned tmem_base;  // TMEM allocation holding S1 and S4 of the sensitivity columns
+    unsigned long long* mbar;  // [2*NB + 2] mbarriers of the asynchronous hand-over: full[NB], empty[NB], done, go
+};
+
 // start of a step for a block of CW sensitivity columns: apply the accept decision, write the Jacobian
 // rows of an output time, restart on a new trajectory, and clear k1 before a zero-length step
+template <int CW>
+__device__ __forceinline__ void sbm_ct_pick_state(const int i, const double (&y)[CW][SBM_N], double (&acc)[CW])
+{
+    // acc[c] = y[c][i] for a run-time i: a jump table instead of N compare-and-select pairs per column
+#define SBM_CT_PICK(k) case k: if (k < SBM_N) { _Pragma("unroll") for (int c = 0; c < CW; ++c) acc[c] = y[c][k < SBM_N ? k : 0]; } break;
+    switch (i) {
+        SBM_CT_PICK(0) SBM_CT_PICK(1) SBM_CT_PICK(2) SBM_CT_PICK(3) SBM_CT_PICK(4) SBM_CT_PICK(5) SBM_CT_PICK(6) SBM_CT_PICK(7)
+        SBM_CT_PICK(8) SBM_CT_PICK(9) SBM_CT_PICK(10) SBM_CT_PICK(11) SBM_CT_PICK(12) SBM_CT_PICK(13) SBM_CT_PICK(14)
+        SBM_CT_PICK(15) SBM_CT_PICK(16) SBM_CT_PICK(17) SBM_CT_PICK(18) SBM_CT_PICK(19) SBM_CT_PICK(20) SBM_CT_PICK(21)
+        SBM_CT_PICK(22) SBM_CT_PICK(23)
+    default: break;
+    }
+#undef SBM_CT_PICK
+}
+
+// one observable row of an output time for CW columns: d(observable)/d(theta)
+// (mapping: project/utils.py:29-45, 71-89; chain rule + scatter: base_project.py:443-488)
+template <int CW>
+__device__ __forceinline__ void sbm_ct_emit_row(const SbmSolveArgs& a, const SbmCtShared& sh, const unsigned long long mask,
+                                                double* __restrict__ row, const bool poison, const int col0, const int lane,
+                                                const double (&y)[CW][SBM_N])
+{
+    constexpr int N = SBM_N;
+    double acc[CW];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) acc[c] = 0.0;
+    if ((mask & (mask - 1ull)) == 0ull) {
+        sbm_ct_pick_state<CW>(__ffsll((long long)mask) - 1, y, acc);           // 'direct' rows: one state
+    } else {
+#pragma unroll
+        for (int c = 0; c < CW; ++c)
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc[c] += ((mask >> i) & 1ull) ? y[c][i] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < CW; ++c) {
+        if (poison) acc[c] = __longlong_as_double(0x7ff8000000000000ll);
+        const int m = sbm_free_idx[col0 + c];
+        int pc;
+        double sc;
+        if (a.jac_raw) { pc = col0 + c; sc = 1.0; }
+        else { pc = sh.pcb[m * 32 + lane]; sc = sh.pb[m * 32 + lane]; }        // d/dtheta = p d/dp
+        if (pc >= 0) {
+            const double v = acc[c] * sc;
+            if (a.jac_atomic) atomicAdd(row + pc, v); else row[pc] = v;
+        }
+    }
+}
+
 template <int CW, class ST>
-__device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const int info, const int cflags,
-                                                  const double h, const int col0, const int lane,
-                                                  double (&y)[CW][SBM_N], const double (&s3)[CW][SBM_N],
-                                                  ST& st, const double* __restrict__ pb,
-                                                  const long long* __restrict__ trj, const int* __restrict__ ktb)
+__device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const SbmCtShared& sh, const int info,
+                                                  const int cflags, const double h, const int col0, const int lane,
+                                                  double (&y)[CW][SBM_N], const double (&s3)[CW][SBM_N], ST& st)
 {
     constexpr int N = SBM_N;
     if (info & SBM_CT_F_ACCEPT) {
@@ -286,38 +387,25 @@ __device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const i
 #pragma unroll
             for (int i = 0; i < N; ++i) y[c][i] = s3[c][i];
     }
+#ifndef SBM_WHATIF_NO_COL_EMIT   /* experiment: how much of a step is the emission of Jacobian rows (results are wrong without) */
     if (cflags & SBM_CT_ANYEMIT) {
         if (info & SBM_CT_F_EMIT) {
-            // observable rows of this output time: d(observable)/d(theta) for these columns
-            // (mapping: project/utils.py:29-45, 71-89; chain rule + scatter: base_project.py:443-488)
-            const long long traj = trj[lane];
-            const int e = (int)(traj % a.E);
-            const long long b = traj / a.E;
-            const int kt = ktb[lane];
+            // every column warp stalls the whole CTA while one of its lanes writes rows (one step in five on the MAPK
+            // benchmark has an emitting lane): masks and row positions come staged from the controller
             const bool poison = (info & SBM_CT_F_POISON) != 0;
-            const int r0 = a.orow_off[kt], r1 = a.orow_off[kt + 1];
-            for (int r = r0; r < r1; ++r) {
-                const unsigned long long mask = a.row_mask[r];
-                double* row = a.jac + (b * a.n_rows + a.row_jac[r]) * (long long)a.n_proj;
-#pragma unroll
-                for (int c = 0; c < CW; ++c) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int i = 0; i < N; ++i) acc += ((mask >> i) & 1ull) ? y[c][i] : 0.0;
-                    if (poison) acc = __longlong_as_double(0x7ff8000000000000ll);
-                    const int m = sbm_free_idx[col0 + c];
-                    int pc;
-                    double sc;
-                    if (a.jac_raw) { pc = col0 + c; sc = 1.0; }
-                    else { pc = a.pmap[e * SBM_NP + m]; sc = pb[m * 32 + lane]; }   // d/dtheta = p d/dp
-                    if (pc >= 0) {
-                        const double v = acc * sc;
-                        if (a.jac_atomic) atomicAdd(row + pc, v); else row[pc] = v;
-                    }
-                }
+            const int n = sh.em_n[lane];
+            for (int q = 0; q < n && q < SBM_CT_EM; ++q)
+                sbm_ct_emit_row<CW>(a, sh, sh.em_mask[q * 32 + lane], a.jac + sh.em_off[q * 32 + lane], poison, col0, lane, y);
+            if (n > SBM_CT_EM) {
+                const long long b = sh.trj[lane] / a.E;
+                const int r0 = a.orow_off[sh.ktb[lane]];
+                for (int r = r0 + SBM_CT_EM; r < r0 + n; ++r)
+                    sbm_ct_emit_row<CW>(a, sh, a.row_mask[r], a.jac + (b * a.n_rows + a.row_jac[r]) * (long long)a.n_proj,
+                                        poison, col0, lane, y);
             }
         }
     }
+#endif
     if (info & SBM_CT_F_RESET) {
 #pragma unroll
         for (int c = 0; c < CW; ++c)
@@ -360,30 +448,6 @@ __device__ __forceinline__ void sbm_ct_cols_stage(const int s, const double h, c
     }
 }
 
-// shared-memory views of one CTA
-struct SbmCtShared {
-    double* Jb;          // [2][NJ][32]        J of the stage being consumed / produced
-    double* Gd;          // [2][NF*NE/2][32][2] dense G (column-major per parameter, row pairs adjacent), zeros stay 0
-    double* fh;          // [7][N][32]         stage derivatives f_1..f_7 of the state column
-    double* yb;          // [N][32]            state y at the start of the step
-    double* ynb;         // [N][32]            5th-order state of the step just taken (prepared by the model warp)
-    double* Pb;          // [2][N][32]         partial stage values y + h sum_{j<S-1} a_Sj f_j, prepared one iteration ahead
-    double* pb;          // [NP][32]           model parameters of each lane's trajectory
-    double* sqb;         // [W+3][32]          partial sums of the squared error norm (per column warp), then the state
-                         //                    column's error / |y| / |f| sums
-    double* hb;          // [32]               step of each lane (0: zero-length step / idle)
-    double* cd;          // [SBM_CT_ND][32]    controller doubles
-    unsigned long long* cnt;   // [4][32]      steps, rejects, rhs evaluations, trajectories
-    long long* trj;      // [32]               trajectory id
-    int* ci;             // [SBM_CT_NI][32]    controller ints
-    int* fl;             // [32]               per-lane flags of this step
-    int* ktb;            // [32]               output-time index to emit
-    int* cta;            // [32]               CTA-wide flags in cta[0]
-    double* park;        // [2][W][32]         start-up norms |y|, |f| (per column warp)
-    unsigned tmem_base;  // TMEM allocation holding S1 and S4 of the sensitivity columns
-    unsigned long long* mbar;  // [2*NB + 2] mbarriers of the asynchronous hand-over: full[NB], empty[NB], done, go
-};
-
 // -------------------------------------------------------------------------------------------------
 // step controller, trajectory queue and the state column (warp 0, one lane per trajectory)
 // -------------------------------------------------------------------------------------------------
@@ -403,7 +467,7 @@ __device__ __forceinline__ void sbm_ct_state_column(const SbmCtShared& sh, const
         ynew[i] = fma(hdone, fma(DP_A76, f6, fma(DP_A75, f5, fma(DP_A74, f4, fma(DP_A73, f3, DP_A71 * f1)))), yi);
         const double er = hdone * fma(DP_E7, f7[i], fma(DP_E6, f6, fma(DP_E5, f5, fma(DP_E4, f4,
                                   fma(DP_E3, f3, DP_E1 * f1)))));
-        const double isk = sbm_rcp_fast(fma(rtol, fmax(fabs(yi), fabs(ynew[i])), atol));
+        const double isk = sbm_rcp_fast(fma(rtol, sbm_absmax_hi(yi, ynew[i]), atol));
         const double q = er * isk, u0 = yi * isk, u1 = f7[i] * isk;
         sq = fma(q, q, sq);
         q0 = fma(u0, u0, q0);
@@ -436,9 +500,15 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
     int info = 0, ktemit = 0;
     if (mode != SBM_CT_IDLE) {
         // ---- the state column of the step just taken: 5th-order solution, embedded error, norms ----
+        // (everything between the partial sums and the new step size is on the critical path of the whole CTA: the
+        //  column warps wait for it.  Hence four interleaved sums, no square root and no FP64 division below.)
         double sq = 0.0, q0 = 0.0, q1 = 0.0;
+        {
+            double part[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int w = 0; w < W; ++w) sq += sh.sqb[w * 32 + lane];
+            for (int w = 0; w < W; ++w) part[w & 3] += sh.sqb[w * 32 + lane];
+            sq = (part[0] + part[1]) + (part[2] + part[3]);
+        }
         double ynew[N], f7[N];
         if (PRE) {
             // prepared by the model warp while the column warps were busy with stage 7
@@ -452,25 +522,28 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
             sbm_ct_state_column(sh, lane, hdone, rtol, atol, ynew, f7, sqs, q0, q1);
             sq += sqs;
         }
-        const double err = sqrt(sq * inv_naug);
+        // err2 = err^2; the controller works on the square (half the exponents) in single precision: the step factor
+        // needs no more, and the result is rounded the same way for every lane and every launch
+        const double err2 = sq * inv_naug;
         bool fsal = false;
         if (mode == SBM_CT_NORMAL) {
             nstep_traj++;
             sh.cnt[0 * 32 + lane] += 1;
             sh.cnt[2 * 32 + lane] += 6;
-            if (err <= 1.0) {
-                // accept; PI controller (Hairer's DOPRI5: beta = 0.04, safe = 0.9, factor in [0.2, 10])
-                const float ferr = fmaxf((float)err, 1e-30f);
-                float fac = __powf(ferr, 0.2f - 0.04f * 0.75f) / __powf(facold, 0.04f);
-                fac = fmaxf(0.1f, fminf(5.0f, fac / 0.9f));
-                facold = fmaxf(ferr, 1e-4f);
+            if (err2 <= 1.0) {
+                // accept; PI controller (Hairer's DOPRI5: beta = 0.04, safe = 0.9, step factor in [0.2, 10]);
+                // facold holds the SQUARE of the previous error (floor 1e-4 ^ 2)
+                const float ferr2 = fmaxf((float)err2, 1e-37f);
+                float rfac = 0.9f * __fdividef(__powf(facold, 0.5f * 0.04f), __powf(ferr2, 0.5f * (0.2f - 0.04f * 0.75f)));
+                rfac = fminf(10.0f, fmaxf(0.2f, rfac));
+                facold = fmaxf(ferr2, 1e-8f);
                 t = clipped ? tk : t + h;
 #pragma unroll
                 for (int i = 0; i < N; ++i) sh.yb[i * 32 + lane] = ynew[i];
                 fsal = true;
-                double hnew = h / (double)fac;
-                if (lastrej) hnew = fmin(hnew, h);
-                if (clipped) hnew = fmax(hnew, hprop);     // a clipped step must not shrink the cruise step
+                if (lastrej) rfac = fminf(rfac, 1.0f);
+                double hnew = h * (double)rfac;
+                if (clipped && hnew < hprop) hnew = hprop;  // a clipped step must not shrink the cruise step
                 h = hnew;
                 lastrej = false;
                 info |= SBM_CT_F_ACCEPT;
@@ -479,9 +552,9 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
                 sh.cnt[2 * 32 + lane] += 1;                 // k1 of the sensitivity columns is re-evaluated
                 lastrej = true;
                 refresh = true;
-                if (err == err && err < 1e300) {
-                    const float ferr = (float)fmin(err, 1e30);
-                    h = h / (double)fminf(5.0f, __powf(ferr, 0.2f - 0.04f * 0.75f) / 0.9f);
+                if (err2 == err2 && err2 < 1e300) {
+                    const float ferr2 = (float)fmin(err2, 1e30);
+                    h = h * (double)fmaxf(0.2f, __fdividef(0.9f, __powf(ferr2, 0.5f * (0.2f - 0.04f * 0.75f))));
                 } else {
                     h *= 0.1;                                // NaN/Inf in the trial state: retreat hard
                     if (h < 1e-300) status = SBM_ERR_NONFINITE;
@@ -524,6 +597,7 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
             ktemit = kt;
             const long long b = traj / a.E;
             const int r0 = a.orow_off[kt], r1 = a.orow_off[kt + 1];
+            sh.em_n[lane] = r1 - r0;
             for (int r = r0; r < r1; ++r) {
                 const unsigned long long mask = a.row_mask[r];
                 double acc = 0.0;
@@ -531,6 +605,12 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
                 for (int i = 0; i < N; ++i) acc += ((mask >> i) & 1ull) ? sh.yb[i * 32 + lane] : 0.0;   // utils.py:10-26, 48-68
                 if (status != SBM_OK) acc = __longlong_as_double(0x7ff8000000000000ll);
                 a.sims[b * a.n_rows + a.row_sim[r]] = acc;
+                // the column warps write the Jacobian rows of this output time at the start of the next step: hand them
+                // the mask and the position of each row (they would otherwise all repeat these index computations)
+                if (r - r0 < SBM_CT_EM) {
+                    sh.em_mask[(r - r0) * 32 + lane] = mask;
+                    sh.em_off[(r - r0) * 32 + lane] = (b * a.n_rows + a.row_jac[r]) * (long long)a.n_proj;
+                }
             }
             kt++;
             if (kt >= kt1) {
@@ -556,6 +636,7 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
             for (int m = 0; m < SBM_NP; ++m) {
                 const int c = a.pmap[e * SBM_NP + m];        // base_project.py:343-363
                 sh.pb[m * 32 + lane] = (c >= 0) ? exp(a.theta[b * a.theta_sb + c * a.theta_sp]) : a.pfix[e * SBM_NP + m];
+                sh.pcb[m * 32 + lane] = c;
             }
 #pragma unroll
             for (int i = 0; i < N; ++i) sh.yb[i * 32 + lane] = a.y0[e * N + i];
@@ -565,7 +646,7 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
             sh.trj[lane] = traj;
             t = 0.0;
             status = SBM_OK;
-            facold = 1e-4f;
+            facold = 1e-8f;                                 // (1e-4)^2: the controller keeps squared errors
             lastrej = false;
             nstep_traj = 0;
             if (kt1 > kt) {
@@ -701,14 +782,24 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
     st.fence();
     const double rtol = a.rtol, atol = a.atol;
 
+#ifdef SBM_CT_PROF
+    long long cbusy[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ctprev = 0;
+#endif
     for (;;) {
         if (XW == 0 && warp == 0) sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 0>(a, sh, lane);
         SBM_CT_BAR(NT);                            // controller output published
+#ifdef SBM_CT_PROF
+        ctprev = sbm_ct_clock_after_barrier(sh.cta);
+        cbusy[8] += 1;
+#endif
         const int cflags = sh.cta[0];
         if (!(cflags & SBM_CT_ALIVE)) break;
         const int info = sh.fl[lane];
         const double h = sh.hb[lane];
-        sbm_ct_cols_begin<CW, ST>(a, info, cflags, h, col0, lane, y, s3, st, sh.pb, sh.trj, sh.ktb);
+        sbm_ct_cols_begin<CW, ST>(a, sh, info, cflags, h, col0, lane, y, s3, st);
+#ifdef SBM_CT_PROF
+        cbusy[0] += clock64() - ctprev;            // cols_begin alone
+#endif
         const bool anyinit = (cflags & SBM_CT_ANYINIT) != 0;
         double sq = 0.0, d0 = 0.0, d1 = 0.0;
         // iteration s: stage s of this warp's columns (s >= 2) and its share of the model at the input of
@@ -731,9 +822,21 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
                 sh.sqb[warp * 32 + lane] = sq;
                 if (anyinit) { sh.park[warp * 32 + lane] = d0; sh.park[(W + warp) * 32 + lane] = d1; }
             }
+#ifdef SBM_CT_PROF
+            cbusy[s] += clock64() - ctprev;
+#endif
             SBM_CT_BAR(NT);
+#ifdef SBM_CT_PROF
+            ctprev = sbm_ct_clock_after_barrier(sh.cta);
+#endif
         }
     }
+#ifdef SBM_CT_PROF
+    if (blockIdx.x == 0 && (warp == SBM_CT_PROF || warp == W - 1) && lane == 0)
+        printf("SBM_CT_PROF column warp %d busy: begin %lld s1 %lld s2 %lld s3 %lld s4 %lld s5 %lld s6 %lld s7 %lld\n", warp,
+               cbusy[0] / cbusy[8], cbusy[1] / cbusy[8], cbusy[2] / cbusy[8], cbusy[3] / cbusy[8], cbusy[4] / cbusy[8], cbusy[5] / cbusy[8],
+               cbusy[6] / cbusy[8], cbusy[7] / cbusy[8]);
+#endif
 }
 
 // a warp without columns: evaluates its share of the model, runs the step controller
@@ -741,11 +844,25 @@ template <int W, int C, int XW>
 __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const SbmCtShared& sh, const int warp, const int lane)
 {
     constexpr int NT = (W + XW) * 32;
+#ifdef SBM_CT_PROF
+    // [0] controller, [s] iteration s (columns: stage s; model: input of stage s+1), [8] steps
+    long long prof[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, busy[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define SBM_CT_MARK(i) { const long long tnow = sbm_ct_clock_after_barrier(sh.cta); prof[i] += tnow - tprev; tprev = tnow; }
+#define SBM_CT_BUSY(i) { busy[i] += clock64() - tprev; }
+#else
+#define SBM_CT_MARK(i)
+#define SBM_CT_BUSY(i)
+#endif
     for (;;) {
         if (warp == W) sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 1>(a, sh, lane);
+        SBM_CT_BUSY(0)
         SBM_CT_BAR(NT);
+        SBM_CT_MARK(0)
         if (!(sh.cta[0] & SBM_CT_ALIVE)) break;
         const double h = sh.hb[lane];
+#ifdef SBM_CT_PROF
+        prof[8] += 1;
+#endif
 #pragma unroll 1
         for (int s = 1; s <= 7; ++s) {
             if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
@@ -760,9 +877,21 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
                 sh.sqb[(W + 1) * 32 + lane] = q0;
                 sh.sqb[(W + 2) * 32 + lane] = q1;
             }
+            SBM_CT_BUSY(s)
             SBM_CT_BAR(NT);
+            SBM_CT_MARK(s)
         }
     }
+#ifdef SBM_CT_PROF
+    if (blockIdx.x == 0 && warp == W && lane == 0) {
+        printf("SBM_CT_PROF steps %lld clocks/step: ctl %lld s1 %lld s2 %lld s3 %lld s4 %lld s5 %lld s6 %lld s7 %lld\n", prof[8],
+               prof[0] / prof[8], prof[1] / prof[8], prof[2] / prof[8], prof[3] / prof[8], prof[4] / prof[8],
+               prof[5] / prof[8], prof[6] / prof[8], prof[7] / prof[8]);
+        printf("SBM_CT_PROF model warp busy: ctl %lld s1 %lld s2 %lld s3 %lld s4 %lld s5 %lld s6 %lld s7 %lld\n",
+               busy[0] / prof[8], busy[1] / prof[8], busy[2] / prof[8], busy[3] / prof[8], busy[4] / prof[8],
+               busy[5] / prof[8], busy[6] / prof[8], busy[7] / prof[8]);
+    }
+#endif
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -831,7 +960,7 @@ __device__ __forceinline__ void sbm_ct_warp_async(const SbmSolveArgs& a, const S
         if (!(cflags & SBM_CT_ALIVE)) break;
         const int info = sh.fl[lane];
         const double h = sh.hb[lane];
-        sbm_ct_cols_begin<CW, ST>(a, info, cflags, h, col0, lane, y, s3, st, sh.pb, sh.trj, sh.ktb);
+        sbm_ct_cols_begin<CW, ST>(a, sh, info, cflags, h, col0, lane, y, s3, st);
         const bool anyinit = (cflags & SBM_CT_ANYINIT) != 0;
         double sq = 0.0, d0 = 0.0, d1 = 0.0;
 #pragma unroll 1
@@ -929,6 +1058,10 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     sh.cta = sh.ktb + 32;
     sh.park = (double*)(sh.cta + 32);
     sh.mbar = (unsigned long long*)(sh.park + 2 * W * 32);
+    sh.em_mask = sh.mbar + 16;
+    sh.em_off = (long long*)(sh.em_mask + SBM_CT_EM * 32);
+    sh.em_n = (int*)(sh.em_off + SBM_CT_EM * 32);
+    sh.pcb = sh.em_n + 32;
     sh.tmem_base = 0;
 
     const int lane = threadIdx.x & 31;

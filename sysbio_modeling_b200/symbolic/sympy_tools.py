@@ -384,10 +384,10 @@ class _CudaPrinter(C99CodePrinter):
         return 'sbm_rcp(%s)' % self._print(expr.args[0])
 
     def _print_sbm_exp(self, expr):
-        return 'exp(%s)' % self._print(expr.args[0])
+        return 'sbm_exp(%s)' % self._print(expr.args[0])      # csrc/sbm_device_math.h
 
     def _print_sbm_log(self, expr):
-        return 'log(%s)' % self._print(expr.args[0])
+        return 'sbm_log(%s)' % self._print(expr.args[0])
 
     def _print_Pow(self, expr):
         base, ex = expr.base, expr.exp
@@ -879,7 +879,8 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
         _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct)
         # a second, wider split for the first stage of a step: its step size is only known once the previous step
         # has been judged, so nothing overlaps it and every warp is free to help
-        n_head = int(_os.environ.get('SBM_CT_HEAD_SHARES', '0')) or min(W_ct + XW_ct, 2)
+        # (measured on C4 with the model warp: 1 / 2 / 3 / 4 / 6 head shares = 144.2 / 141.7 / 145.1 / 144.5 / 142.9 k solves/s)
+        n_head = int(_os.environ.get('SBM_CT_HEAD_SHARES', '0')) or min(W_ct + XW_ct, 3)
         L.append('#define SBM_CT_HEAD_SHARES %d' % n_head)
         _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct, fname='sbm_primal_head',
                             n_shares=n_head, head=True)

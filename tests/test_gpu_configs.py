@@ -268,6 +268,16 @@ def test_device_reciprocal_accuracy(tmp_path):
     vals = dict(zip(out.split()[0::2], [float(v) for v in out.split()[1::2]]))
     assert vals['sbm_rcp_ulp'] <= 1.0
     assert vals['seed_relerr'] < 1e-5
+    # branch-free log / exp of the generated model code: within 2 ulp of libm (itself <= 1 ulp) on positive normal
+    # arguments; never a wrong finite number outside (NaN for log, Inf / 0 for exp)
+    assert vals['sbm_log_ulp'] <= 2.0 and vals['sbm_log_near1_ulp'] <= 2.0 and vals['sbm_exp_ulp'] <= 2.0
+    assert vals['pow_relerr'] < 5e-15
+    for k in ('log_zero', 'log_neg', 'log_inf', 'log_subnormal', 'exp_nan'):
+        assert np.isnan(vals[k]), k
+    assert vals['log_one'] == 0.0 and vals['exp_zero'] == 1.0
+    assert vals['exp_800'] == np.inf and vals['exp_1e12'] == np.inf
+    assert vals['exp_m800'] == 0.0 and vals['exp_m1e12'] == 0.0
+    assert abs(vals['exp_m740'] / np.exp(-740.0) - 1) < 1e-3         # subnormal result
 
 
 def test_cta_transposed_layout_matches_warp_group_layout():
