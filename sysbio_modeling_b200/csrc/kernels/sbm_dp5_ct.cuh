@@ -73,6 +73,7 @@
 // experiment (-DSBM_CT_PROF=<column warp>): clocks of the eight barrier intervals of a step and the busy part of each
 // for the model warp and one column warp, printed by CTA 0.  The barrier is "deferred blocking": a clock read right after it
 // may execute before the barrier completes, so the read is made to depend on a shared-memory load issued after the barrier.
+__shared__ long long sbm_ctl_prof[8];          // clocks of the parts of the controller (lane 0)
 __device__ __forceinline__ long long sbm_ct_clock_after_barrier(const int* cta)
 {
     const int dep = *reinterpret_cast<const volatile int*>(cta);
@@ -320,6 +321,7 @@ struct SbmCtShared {
     long long* em_off;   // [SBM_CT_EM][32]    ... and offset of the row in the Jacobian output (staged by the controller)
     int* em_n;           // [32]               number of rows of that output time
     int* pcb;            // [NP][32]           project column of each model parameter of the lane's experiment (-1: fixed)
+    long long* trow;     // [32]               first output row of the lane's parameter set (b * n_rows)
     unsigned tmem_base;  // TMEM allocation holding S1 and S4 of the sensitivity columns
     unsigned long long* mbar;  // [2*NB + 2] mbarriers of the asynchronous hand-over: full[NB], empty[NB], done, go
 };
@@ -397,10 +399,10 @@ __device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const S
             for (int q = 0; q < n && q < SBM_CT_EM; ++q)
                 sbm_ct_emit_row<CW>(a, sh, sh.em_mask[q * 32 + lane], a.jac + sh.em_off[q * 32 + lane], poison, col0, lane, y);
             if (n > SBM_CT_EM) {
-                const long long b = sh.trj[lane] / a.E;
+                const long long rowbase = sh.trow[lane];
                 const int r0 = a.orow_off[sh.ktb[lane]];
                 for (int r = r0 + SBM_CT_EM; r < r0 + n; ++r)
-                    sbm_ct_emit_row<CW>(a, sh, a.row_mask[r], a.jac + (b * a.n_rows + a.row_jac[r]) * (long long)a.n_proj,
+                    sbm_ct_emit_row<CW>(a, sh, a.row_mask[r], a.jac + (rowbase + a.row_jac[r]) * (long long)a.n_proj,
                                         poison, col0, lane, y);
             }
         }
@@ -485,6 +487,12 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
     const double inv_naug = 1.0 / (double)(N * (SBM_NF + 1));
     unsigned long long* queue = a.counters + SBM_CNT_QUEUE;
 
+#ifdef SBM_CT_PROF
+    long long cp0 = clock64();
+#define SBM_CTL_MARK(i) { const long long tn = clock64(); if (lane == 0) sbm_ctl_prof[i] += tn - cp0; cp0 = tn; }
+#else
+#define SBM_CTL_MARK(i)
+#endif
     double t = sh.cd[SBM_CT_D_T * 32 + lane], h = sh.cd[SBM_CT_D_H * 32 + lane];
     double hprop = sh.cd[SBM_CT_D_HPROP * 32 + lane], tk = sh.cd[SBM_CT_D_TK * 32 + lane];
     double tend = sh.cd[SBM_CT_D_TEND * 32 + lane];
@@ -525,40 +533,38 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
         // err2 = err^2; the controller works on the square (half the exponents) in single precision: the step factor
         // needs no more, and the result is rounded the same way for every lane and every launch
         const double err2 = sq * inv_naug;
+        SBM_CTL_MARK(0)                            // state and partial sums loaded
         bool fsal = false;
         if (mode == SBM_CT_NORMAL) {
+            // PI controller (Hairer's DOPRI5: beta = 0.04, safe = 0.9, step factor in [0.2, 10]); facold holds the SQUARE
+            // of the previous accepted error (floor 1e-4 ^ 2).  Accepted and rejected lanes share one instruction stream
+            // (selects, predicated stores): only the clean-up after a rejection is a branch.
             nstep_traj++;
+            const bool acc = err2 <= 1.0;                                      // false for NaN
+            const bool finite = (err2 == err2) && (err2 < 1e300);
+            const float ferr2 = fmaxf((float)err2, 1e-37f);                    // +Inf when err2 exceeds the float range
+            const float e17 = __powf(ferr2, 0.5f * (0.2f - 0.04f * 0.75f));    // err ^ 0.17
+            float ra = fminf(10.0f, fmaxf(0.2f, 0.9f * __fdividef(__powf(facold, 0.5f * 0.04f), e17)));
+            if (lastrej) ra = fminf(ra, 1.0f);
+            const float rr = finite ? fmaxf(0.2f, __fdividef(0.9f, e17)) : 0.1f;   // NaN/Inf in the trial state: retreat hard
+            double hnew = h * (double)(acc ? ra : rr);
+            if (acc && clipped && hnew < hprop) hnew = hprop;                  // a clipped step must not shrink the cruise step
+            t = acc ? (clipped ? tk : t + h) : t;
+            facold = acc ? fmaxf(ferr2, 1e-8f) : facold;
+            h = hnew;
             sh.cnt[0 * 32 + lane] += 1;
-            sh.cnt[2 * 32 + lane] += 6;
-            if (err2 <= 1.0) {
-                // accept; PI controller (Hairer's DOPRI5: beta = 0.04, safe = 0.9, step factor in [0.2, 10]);
-                // facold holds the SQUARE of the previous error (floor 1e-4 ^ 2)
-                const float ferr2 = fmaxf((float)err2, 1e-37f);
-                float rfac = 0.9f * __fdividef(__powf(facold, 0.5f * 0.04f), __powf(ferr2, 0.5f * (0.2f - 0.04f * 0.75f)));
-                rfac = fminf(10.0f, fmaxf(0.2f, rfac));
-                facold = fmaxf(ferr2, 1e-8f);
-                t = clipped ? tk : t + h;
+            sh.cnt[2 * 32 + lane] += acc ? 6 : 7;               // after a rejection k1 of the sensitivity columns is re-evaluated
+            if (acc) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) sh.yb[i * 32 + lane] = ynew[i];
-                fsal = true;
-                if (lastrej) rfac = fminf(rfac, 1.0f);
-                double hnew = h * (double)rfac;
-                if (clipped && hnew < hprop) hnew = hprop;  // a clipped step must not shrink the cruise step
-                h = hnew;
-                lastrej = false;
                 info |= SBM_CT_F_ACCEPT;
-            } else {
+            }
+            fsal = acc;
+            lastrej = !acc;
+            if (!acc) {
                 sh.cnt[1 * 32 + lane] += 1;
-                sh.cnt[2 * 32 + lane] += 1;                 // k1 of the sensitivity columns is re-evaluated
-                lastrej = true;
                 refresh = true;
-                if (err2 == err2 && err2 < 1e300) {
-                    const float ferr2 = (float)fmin(err2, 1e30);
-                    h = h * (double)fmaxf(0.2f, __fdividef(0.9f, __powf(ferr2, 0.5f * (0.2f - 0.04f * 0.75f))));
-                } else {
-                    h *= 0.1;                                // NaN/Inf in the trial state: retreat hard
-                    if (h < 1e-300) status = SBM_ERR_NONFINITE;
-                }
+                if (!finite && h < 1e-300) status = SBM_ERR_NONFINITE;
                 // stage derivatives of the rejected trial may be non-finite: they must not meet the zero
                 // coefficients of the refresh step (0 * Inf)
 #pragma unroll
@@ -586,30 +592,37 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
                 sh.cnt[2 * 32 + lane] += 1;
             }
         }
+        SBM_CTL_MARK(1)                            // decision and step size
         if (fsal) {
 #pragma unroll
             for (int i = 0; i < N; ++i) sh.fh[(0 * N + i) * 32 + lane] = f7[i];
         }
+        SBM_CTL_MARK(2)
         // arrived at an output time (or failed: flush the remaining rows as NaN, one time per pass)
         if (!refresh && (t >= tk || status != SBM_OK)) {
             info |= SBM_CT_F_EMIT;
             if (status != SBM_OK) info |= SBM_CT_F_POISON;
             ktemit = kt;
-            const long long b = traj / a.E;
-            const int r0 = a.orow_off[kt], r1 = a.orow_off[kt + 1];
+            // (this block stalls the whole CTA once in five steps on the MAPK benchmark: read-only table loads through the
+            //  L1 path, issued before they are needed; the row base of the parameter set was kept at fetch time)
+            const long long rowbase = sh.trow[lane];
+            const int r0 = __ldg(a.orow_off + kt), r1 = __ldg(a.orow_off + kt + 1);
+            const double tknext = (kt + 1 < kt1) ? __ldg(a.tout + kt + 1) : tk;
             sh.em_n[lane] = r1 - r0;
+#pragma unroll 2
             for (int r = r0; r < r1; ++r) {
-                const unsigned long long mask = a.row_mask[r];
+                const unsigned long long mask = __ldg(a.row_mask + r);
+                const int rs = __ldg(a.row_sim + r), rj = __ldg(a.row_jac + r);
                 double acc = 0.0;
 #pragma unroll
                 for (int i = 0; i < N; ++i) acc += ((mask >> i) & 1ull) ? sh.yb[i * 32 + lane] : 0.0;   // utils.py:10-26, 48-68
                 if (status != SBM_OK) acc = __longlong_as_double(0x7ff8000000000000ll);
-                a.sims[b * a.n_rows + a.row_sim[r]] = acc;
+                a.sims[rowbase + rs] = acc;
                 // the column warps write the Jacobian rows of this output time at the start of the next step: hand them
                 // the mask and the position of each row (they would otherwise all repeat these index computations)
                 if (r - r0 < SBM_CT_EM) {
                     sh.em_mask[(r - r0) * 32 + lane] = mask;
-                    sh.em_off[(r - r0) * 32 + lane] = (b * a.n_rows + a.row_jac[r]) * (long long)a.n_proj;
+                    sh.em_off[(r - r0) * 32 + lane] = (rowbase + rj) * (long long)a.n_proj;
                 }
             }
             kt++;
@@ -618,7 +631,7 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
                 sh.cnt[3 * 32 + lane] += 1;
                 mode = SBM_CT_IDLE;
             } else {
-                tk = a.tout[kt];
+                tk = tknext;
             }
         }
     } else if (!exhausted) {
@@ -644,6 +657,7 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
             kt = a.tout_off[e];
             kt1 = a.tout_off[e + 1];
             sh.trj[lane] = traj;
+            sh.trow[lane] = b * a.n_rows;
             t = 0.0;
             status = SBM_OK;
             facold = 1e-8f;                                 // (1e-4)^2: the controller keeps squared errors
@@ -664,6 +678,7 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
             exhausted = true;
         }
     }
+    SBM_CTL_MARK(3)                                // output time / new trajectory
     // ---- next step of this lane ----
     double hstep = 0.0;
     if (mode != SBM_CT_IDLE) {
@@ -699,6 +714,12 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
     sh.ci[SBM_CT_I_BITS * 32 + lane] = (lastrej ? 1 : 0) | (clipped ? 2 : 0) | (refresh ? 4 : 0) | (initf ? 8 : 0) |
                                        (exhausted ? 16 : 0);
     sh.ci[SBM_CT_I_NSTEP * 32 + lane] = (int)nstep_traj;
+    SBM_CTL_MARK(4)                                // clipping, flags, state saved
+#ifdef SBM_CT_PROF
+    if (lane == 0 && blockIdx.x == 0 && !(sh.cta[0] & SBM_CT_ALIVE))
+        printf("SBM_CT_PROF controller clocks (total over steps): load %lld decide %lld fsal %lld emit/fetch %lld finish %lld\n",
+               sbm_ctl_prof[0], sbm_ctl_prof[1], sbm_ctl_prof[2], sbm_ctl_prof[3], sbm_ctl_prof[4]);
+#endif
 }
 
 // Tableau rows without their last entry: the stage value of stage S is prepared one iteration ahead as
@@ -1062,7 +1083,11 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     sh.em_off = (long long*)(sh.em_mask + SBM_CT_EM * 32);
     sh.em_n = (int*)(sh.em_off + SBM_CT_EM * 32);
     sh.pcb = sh.em_n + 32;
+    sh.trow = (long long*)(sh.pcb + SBM_NP * 32 + (SBM_NP & 1) * 32);
     sh.tmem_base = 0;
+#ifdef SBM_CT_PROF
+    if (threadIdx.x < 8) sbm_ctl_prof[threadIdx.x] = 0;
+#endif
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -1118,6 +1143,19 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     if (warp >= W) sbm_ct_model_warp_async<W, C>(a, sh, lane);
     else if (warp == W - 1 && CL != C) sbm_ct_warp_async<W, C, CL>(a, sh, warp, lane);
     else sbm_ct_warp_async<W, C, C>(a, sh, warp, lane);
+#elif defined(SBM_CT_REGSPLIT)
+    // experiment: 16 warps = 4 warp groups launched with 128 registers per thread; the last warp group (model shares only)
+    // gives registers back, the other three (column warps and the main model warp) take them: 3 x 128 x 152 + 128 x 56 = 64 K
+    static_assert(WT == 16 && W <= 12 && W >= 9, "register split: three warp groups of column warps + one of model warps");
+    if (warp >= 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+        sbm_ct_model_warp<W, C, XW>(a, sh, warp, lane);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;" ::: "memory");
+        if (warp >= W) sbm_ct_model_warp<W, C, XW>(a, sh, warp, lane);
+        else if (warp == W - 1 && CL != C) sbm_ct_warp<W, C, CL, XW>(a, sh, warp, lane);
+        else sbm_ct_warp<W, C, C, XW>(a, sh, warp, lane);
+    }
 #else
     if (XW > 0 && warp >= W) sbm_ct_model_warp<W, C, XW>(a, sh, warp, lane);
     else if (warp == W - 1 && CL != C) sbm_ct_warp<W, C, CL, XW>(a, sh, warp, lane);

@@ -4,8 +4,9 @@
 // branches to a slow-path subroutine.  The generated right-hand sides contain a reciprocal per rate law
 // (13 in the MAPK model) and the error norm one per state, so those branches cut the code into ~20 basic
 // blocks per stage and the scheduler cannot overlap the independent rate-law chains.  sbm_rcp() has no
-// branch: hardware seed (rcp.approx.ftz.f64, relative error <= 2^-20) + three Newton-Raphson steps in
-// FMA form -> within 1 ulp for normal arguments.  Zero, subnormal, Inf and NaN arguments give Inf/NaN/0
+// branch: hardware seed (rcp.approx.ftz.f64, relative error <= 2^-20) + two Newton-Raphson steps in
+// FMA form (error 2^-20 -> 2^-40 -> 2^-80: the result is the rounding of the last FMA) -> within 1 ulp for normal arguments
+// (tests/cuda/check_device_math.cu: identical to IEEE division on 4 M random arguments; a third step changes nothing).  Zero, subnormal, Inf and NaN arguments give Inf/NaN/0
 // without special handling (a trajectory that produces them is rejected by the step controller anyway).
 #ifndef SBM_DEVICE_MATH_H
 #define SBM_DEVICE_MATH_H
@@ -15,8 +16,6 @@ __device__ __forceinline__ double sbm_rcp(const double x)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
@@ -32,7 +31,7 @@ __device__ __forceinline__ double sbm_rcp(const double x)
 //   sbm_log: fdlibm's e_log algorithm (x = 2^k m, m in [sqrt(1/2), sqrt(2)), s = f / (2 + f), degree-14 minimax in s),
 //            < 1 ulp for positive normal x; zero, negative, subnormal, Inf and NaN arguments all give NaN (the step
 //            controller rejects the trajectory), never a wrong finite number.
-//   sbm_exp: k = rint(x / ln 2), Cody-Waite reduction in FMA form, degree-13 Taylor polynomial on |r| <= ln2 / 2,
+//   sbm_exp: k = rint(x / ln 2), Cody-Waite reduction in FMA form, degree-13 Taylor polynomial on |r| <= ln2 / 2 (Estrin's scheme),
 //            scaling by 2^k in two factors (overflow -> Inf, underflow -> 0 through subnormals), < 1 ulp.
 // Both measured against libm on the device: tests/cuda/check_device_math.cu.
 // ---------------------------------------------------------------------------------------------------------
@@ -76,11 +75,14 @@ __device__ __forceinline__ double sbm_exp(const double x)
     const double dk = t - C[13];                                        // rint(x / ln 2)
     double r = fma(dk, C[14], x);
     r = fma(dk, C[15], r);
-    double p = C[11];
-#pragma unroll
-    for (int n = 10; n >= 0; --n) p = fma(p, r, C[n]);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    // exp(r) = 1 + (r + r^2 q(r)), q of degree 11 by Estrin's scheme: 6 dependent operations instead of 13 (the single model
+    // warp of sbm_dp5_ct is bound by the latency of its longest chain, ~8 clocks per dependent FP64 instruction)
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double e0 = fma(fma(C[3], r, C[2]), r2, fma(C[1], r, C[0]));
+    const double e1 = fma(fma(C[7], r, C[6]), r2, fma(C[5], r, C[4]));
+    const double e2 = fma(fma(C[11], r, C[10]), r2, fma(C[9], r, C[8]));
+    const double q = fma(r8, e2, fma(r4, e1, e0));
+    const double p = 1.0 + fma(r2, q, r);
     int k = __double2int_rn(dk);                                        // saturates; NaN -> 0 (p is NaN then)
     k = max(-2044, min(2044, k));
     const int k1 = k >> 1, k2 = k - k1;

@@ -617,8 +617,10 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0, f
     loads = []
     for w in range(WT):
         if head:
-            # the model at the input of stage 2, evaluated while the column warps have nothing else to do
-            base = 0.0
+            # the model at the input of stage 2, evaluated while the column warps have nothing else to do - except the
+            # start of their step (accept copy, Jacobian rows of an output time: ~1,000 clocks measured, about a
+            # third of the whole model), so the model warp takes the largest cluster (the longest dependent chain)
+            base = float(_os.environ.get('SBM_CT_HEAD_COLBASE', '150')) if w < W else 0.0
         elif XW:
             # several shares with a model warp: balance the load of the schedulers (warp w runs on scheduler w % 4), not
             # of the warps - the model warp's scheduler hosts one column warp fewer.  Measured on C4: 1 / 4 / 7 / 10
