@@ -171,6 +171,19 @@ int sbm_jacobian_host(sbm_plan* p, const sbm_solver_opts_t* opts, int loss_kind,
                       double* grad_host, double* sf_host, double* sims_host, int* status_host,
                       unsigned long long* counters_host, void* stream);
 
+/* ---- batched Levenberg-Marquardt step (the consumer of residuals + Jacobian) ---------------------------
+ * Replaces the inner linear algebra of scipy.optimize.leastsq(proj.residuals, x0, Dfun=proj.calc_project_jacobian)
+ * (reference call sites tests/test_Project.py:202-213, 351-357) for B parameter sets at once, on the device:
+ *   (J^T J + lambda D) delta = -J^T r,  pred = 0.5 delta^T (lambda D delta - J^T r),
+ *   D_j = max(dscale_j, (J^T J)_jj) written back to dscale (MINPACK's running column scaling; 1 where still zero)
+ *   jac    device [B][n_rows][n_proj]  (as written by sbm_loss)      resid  device [B][n_rows]
+ *   lambda device [B]                   dscale device [B][n_proj] in/out, zero before the first step (NULL: no memory)
+ *   delta  device [B][n_proj]           pred, gmax device [B]   (gmax = max |J^T r|)
+ *   info   device int [B]: 0 ok, 1 system not positive definite or input not finite (delta = 0: raise lambda)
+ * n_proj <= 32.                                                                                            */
+int sbm_lm_step(long long B, int n_rows, int n_proj, const double* jac, const double* resid, const double* lambda,
+                double* dscale, double* delta, double* pred, double* gmax, int* info, void* stream);
+
 /* ---- utilities ----------------------------------------------------------------------------------------- */
 /* DFMA-throughput microbenchmark on the current device: the measured FP64 roofline denominator. */
 int         sbm_fp64_peak(int iters, double* tflops_out, double* ms_out);

@@ -428,3 +428,74 @@ def central_difference(fun, x, rel=None):
         xm[j] -= h
         out[:, j] = (np.atleast_1d(fun(xp)) - np.atleast_1d(fun(xm))) / (2 * h)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Levenberg-Marquardt.  The reference has no LM of its own: its tests hand
+# Project.residuals / calc_project_jacobian to scipy.optimize.leastsq (MINPACK lmder; tests/test_Project.py:202-213,
+# 351-357).  MINPACK is a third-party dependency of SciPy (unpinned by the reference); the restatement below is the
+# textbook Marquardt-scaled step with Nielsen's damping update (Madsen, Nielsen, Tingleff, "Methods for non-linear
+# least squares problems", 2004, algorithm 3.16), the one csrc/sbm_lm.cuh and Project.lm_fit_batch implement.  It is pinned
+# by identities (tests/test_lm.py: Gauss-Newton limit = lstsq, predicted = actual reduction on linear problems) and,
+# for whole fits, by agreeing with scipy.optimize.leastsq on the reference's own fixture projects.
+# ---------------------------------------------------------------------------------------------------------
+def lm_step(J, r, lam, dscale=None):
+    """(delta, pred, gmax, info) of one damped step: (J^T J + lam D) delta = -J^T r with D_j = max(dscale_j, (J^T J)_jj)
+    (1 where still 0); ``dscale`` (None: no memory) is updated in place - MINPACK's running column scaling."""
+    J = np.asarray(J, dtype=np.float64)
+    r = np.asarray(r, dtype=np.float64)
+    A = J.T.dot(J)
+    g = J.T.dot(r)
+    D = np.diag(A).copy()
+    if dscale is not None:
+        D = np.where(dscale > D, dscale, D)
+        ok = np.isfinite(D) & (D < 1e300)
+        dscale[ok] = D[ok]
+    D[~(D > 0)] = 1.0
+    gmax = np.max(np.abs(g)) if g.size else 0.0
+    if not (np.all(np.isfinite(A)) and np.all(np.isfinite(g)) and np.isfinite(lam)):
+        return np.zeros(J.shape[1]), 0.0, gmax, 1
+    try:
+        L = np.linalg.cholesky(A + lam * np.diag(D))
+    except np.linalg.LinAlgError:
+        return np.zeros(J.shape[1]), 0.0, gmax, 1
+    y = np.linalg.solve(L, -g)
+    delta = np.linalg.solve(L.T, y)
+    pred = 0.5 * delta.dot(lam * D * delta - g)
+    return delta, pred, gmax, 0
+
+
+def lm_fit(residuals, jacobian, theta0, max_iter=100, lam0=1e-3, ftol=1e-12, xtol=1e-10, gtol=0.0, max_log_step=3.0):
+    """One start vector of Project.lm_fit_batch, same rules, on the CPU.  Returns (theta, ssr, n_iter, converged)."""
+    th = np.asarray(theta0, dtype=np.float64).copy()
+    r, J = np.asarray(residuals(th)), np.asarray(jacobian(th))
+    ssr = 0.5 * np.sum(r ** 2)
+    lam, nu = float(lam0), 2.0
+    dscale = np.zeros(th.shape)
+    if not np.isfinite(ssr):
+        return th, ssr, 0, False
+    for it in range(1, int(max_iter) + 1):
+        delta, pred, gmax, info = lm_step(J, r, lam, dscale)
+        step_ok = info == 0 and bool(np.max(np.abs(delta)) <= max_log_step)
+        accept = False
+        if step_ok:
+            r1 = np.asarray(residuals(th + delta))
+            ssr1 = 0.5 * np.sum(r1 ** 2)
+            accept = bool(np.isfinite(ssr1) and ssr1 < ssr and pred > 0)
+        small = step_ok and bool(np.all(np.abs(delta) <= xtol * (np.abs(th) + xtol)))
+        done = (accept and (ssr - ssr1) <= ftol * ssr) or small or gmax <= gtol
+        if accept:
+            rho = (ssr - ssr1) / pred
+            lam *= max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3)
+            nu = 2.0
+            th = th + delta
+            r, ssr = r1, ssr1
+            J = np.asarray(jacobian(th))
+        else:
+            lam *= nu
+            nu *= 2.0
+        if done:
+            return th, ssr, it, True
+        if not lam < 1e16:
+            return th, ssr, it, False
+    return th, ssr, int(max_iter), False

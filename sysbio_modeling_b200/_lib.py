@@ -65,7 +65,7 @@ class SolverOpts(ctypes.Structure):
 
 
 EXPORTS = ['sbm_model_compile', 'sbm_model_info', 'sbm_model_log', 'sbm_model_destroy', 'sbm_plan_create',
-           'sbm_plan_destroy', 'sbm_solve', 'sbm_loss', 'sbm_residuals_host', 'sbm_jacobian_host',
+           'sbm_plan_destroy', 'sbm_solve', 'sbm_loss', 'sbm_residuals_host', 'sbm_jacobian_host', 'sbm_lm_step',
            'sbm_fp64_peak', 'sbm_device_count', 'sbm_last_error', 'sbm_version']
 
 _lib = None
@@ -95,6 +95,7 @@ def lib():
     L.sbm_loss.argtypes = [vp, ci, ci, ll, vp, ll, ll, vp, vp, vp, vp, vp, vp, vp, vp]
     L.sbm_residuals_host.argtypes = [vp, ctypes.POINTER(SolverOpts), ci, ll, vp, vp, vp, vp, vp, vp, vp, vp]
     L.sbm_jacobian_host.argtypes = [vp, ctypes.POINTER(SolverOpts), ci, ci, ll, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sbm_lm_step.argtypes = [ll, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.sbm_fp64_peak.argtypes = [ci, _DP, _DP]
     _lib = L
     return L

@@ -26,6 +26,7 @@
 #include "../../include/sbm_b200.h"
 #include "sbm_kernel_args.h"
 #include "sbm_epilogue.cuh"
+#include "sbm_lm.cuh"
 
 // generated at build time from sbm_kernel_args.h + kernels/sbm_ode_kernels.cuh
 extern const char* sbm_embedded_args_header;
@@ -548,6 +549,25 @@ extern "C" int sbm_loss(sbm_plan* p, int loss_kind, int flags, long long B,
     a.B = B; a.n_rows = p->d.n_rows; a.n_proj = p->d.n_proj; a.n_groups = p->d.n_groups;
     a.loss_kind = loss_kind; a.flags = flags;
     sbm_launch_loss(a, (cudaStream_t)stream);
+    RT(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched Levenberg-Marquardt step
+// ------------------------------------------------------------------------------------------------
+extern "C" int sbm_lm_step(long long B, int n_rows, int n_proj, const double* jac, const double* resid, const double* lambda,
+                           double* dscale, double* delta, double* pred, double* gmax, int* info, void* stream)
+{
+    if (!jac || !resid || !lambda || !delta || !pred || !gmax || !info) return fail(SBM_E_INVALID, "sbm_lm_step: null argument");
+    if (B <= 0 || n_rows <= 0 || n_proj <= 0) return fail(SBM_E_INVALID, "sbm_lm_step: B, n_rows, n_proj must be positive");
+    if (n_proj > 32) return fail(SBM_E_INVALID, "sbm_lm_step: n_proj > 32 is not supported");
+    int rc = require_device();
+    if (rc) return rc;
+    SbmLmArgs a;
+    a.jac = jac; a.resid = resid; a.lambda = lambda; a.dscale = dscale; a.delta = delta; a.pred = pred; a.gmax = gmax; a.info = info;
+    a.B = B; a.n_rows = n_rows; a.n_proj = n_proj;
+    if (sbm_launch_lm_step(a, (cudaStream_t)stream)) return fail(SBM_E_INVALID, "sbm_lm_step: unsupported shape");
     RT(cudaGetLastError());
     return 0;
 }

@@ -191,3 +191,28 @@ class DevicePlan(object):
         _lib.check(_lib.lib().sbm_loss(
             self._h, LOSSES[loss], int(flags), B, dp(theta), theta.stride(0), theta.stride(1),
             dp(sims), dp(jac), dp(resid), dp(ssr), dp(sf), dp(sfgrad), dp(grad), ctypes.c_void_p(st)))
+
+
+def lm_step_device(jac, resid, lam, dscale=None, delta=None, pred=None, gmax=None, info=None, stream=None):
+    """Batched Levenberg-Marquardt step on device tensors (C ABI ``sbm_lm_step``, csrc/sbm_lm.cuh):
+    ``(J^T J + lam D) delta = -J^T r`` for every parameter set, ``D = max(dscale, diag(J^T J))`` written back to
+    ``dscale`` [B, n_proj] (zero before the first step; None: this step's diagonal only).  jac [B, n_rows, n_proj],
+    resid [B, n_rows], lam [B] (CUDA float64, contiguous).  Returns (delta [B, n_proj], pred [B], gmax [B], info [B] int32)."""
+    import torch
+    B, R, P = jac.shape
+    f64 = dict(dtype=torch.float64, device=jac.device)
+    delta = torch.empty((B, P), **f64) if delta is None else delta
+    pred = torch.empty((B,), **f64) if pred is None else pred
+    gmax = torch.empty((B,), **f64) if gmax is None else gmax
+    info = torch.empty((B,), dtype=torch.int32, device=jac.device) if info is None else info
+    for x in (jac, resid, lam, delta, pred, gmax, info) + ((dscale,) if dscale is not None else ()):
+        if not x.is_contiguous():
+            raise ValueError('lm_step_device needs contiguous tensors')
+    st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    vp = ctypes.c_void_p
+    _lib.check(_lib.lib().sbm_lm_step(B, R, P, vp(jac.data_ptr()), vp(resid.data_ptr()), vp(lam.data_ptr()),
+                                      vp(dscale.data_ptr() if dscale is not None else None),
+                                      vp(delta.data_ptr()), vp(pred.data_ptr()), vp(gmax.data_ptr()),
+                                      vp(info.data_ptr()), vp(st)))
+    return delta, pred, gmax, info
+

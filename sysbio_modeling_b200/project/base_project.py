@@ -626,6 +626,69 @@ class Project(object):
         plan.loss_device(theta, sims, jac, resid, ssr, sf, sfgrad, grad, loss=self._loss_name(), flags=self._flags())
         return o
 
+    def lm_fit_batch(self, thetas, max_iter=100, lam0=1e-3, ftol=1e-12, xtol=1e-10, gtol=0.0, max_log_step=3.0):
+        """Batched multistart Levenberg-Marquardt on the device: the consumer the reference drives through
+        ``scipy.optimize.leastsq(proj.residuals, x0, Dfun=proj.calc_project_jacobian)`` (tests/test_Project.py:202-213,
+        351-357), for B start vectors at once.  Every iteration is one fused evaluation (integrator + loss epilogue) of
+        all trial points and one ``sbm_lm_step`` launch; parameters, residuals and Jacobians never leave the GPU.
+
+        The step solves ``(J^T J + lam D) delta = -J^T r`` with Marquardt's ``D = diag(J^T J)`` kept at its running
+        maximum over the iterations (MINPACK's column scaling: a parameter drifting into a flat direction keeps its
+        damping); ``lam`` follows
+        Nielsen's gain-ratio rule (accepted: ``lam *= max(1/3, 1 - (2 rho - 1)^3)``; rejected: ``lam *= nu, nu *= 2``).
+        A set stops when an accepted step reduces SSR by less than ``ftol`` (relative), its step is below ``xtol``
+        (relative, per parameter), ``max |J^T r| <= gtol`` or ``lam`` overflows.  A step that would change a log-parameter
+        by more than ``max_log_step`` is not tried (its damping is raised instead): a nearly undamped first step can land
+        where the model is extremely stiff, and the whole batch would wait for those trajectories.  J and r are exactly what the reference's
+        callbacks return (the scaled Jacobian is not divided by sigma), so the fixed points are scipy's.
+
+        Returns a dict of numpy arrays: theta [B, n_proj], ssr [B], n_iter [B], converged [B], lam [B]."""
+        import torch
+        _lib.require_gpu()
+        dev = torch.device('cuda')
+        th = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(thetas), dtype=np.float64)).to(dev)
+        B, P = th.shape
+        if P != self.n_project_params:
+            raise ValueError('expected %d project parameters, got %d' % (self.n_project_params, P))
+        f64 = dict(dtype=torch.float64, device=dev)
+        cur, tri = {}, {}
+        self.evaluate_device(th, True, out=cur)
+        lam = torch.full((B,), float(lam0), **f64)
+        nu = torch.full((B,), 2.0, **f64)
+        dscale = torch.zeros((B, P), **f64)
+        active = torch.isfinite(cur['ssr'])
+        converged = torch.zeros((B,), dtype=torch.bool, device=dev)
+        n_iter = torch.zeros((B,), dtype=torch.int64, device=dev)
+        step = None
+        keys = ('sims', 'resid', 'ssr', 'sf', 'jac', 'sfgrad', 'grad', 'status')
+        for it in range(int(max_iter)):
+            step = engine.lm_step_device(cur['jac'], cur['resid'], lam, dscale, *(step or ()))
+            delta, pred, gmax, info = step
+            step_ok = active & (info == 0) & (delta.abs().amax(dim=1) <= max_log_step)
+            th_try = torch.where(step_ok[:, None], th + delta, th)
+            self.evaluate_device(th_try, True, out=tri)
+            ssr0, ssr1 = cur['ssr'], tri['ssr']
+            accept = step_ok & torch.isfinite(ssr1) & (ssr1 < ssr0) & (pred > 0)
+            rho = torch.where(accept, (ssr0 - ssr1) / torch.where(pred > 0, pred, torch.ones_like(pred)), torch.zeros_like(pred))
+            small = (delta.abs() <= xtol * (th.abs() + xtol)).all(dim=1)
+            done = (accept & ((ssr0 - ssr1) <= ftol * ssr0)) | (step_ok & small) | (active & (gmax <= gtol))
+            lam_new = torch.where(accept, lam * torch.clamp(1.0 - (2.0 * rho - 1.0) ** 3, min=1.0 / 3.0), lam * nu)
+            nu = torch.where(accept, torch.full_like(nu, 2.0), nu * 2.0)
+            lam = torch.where(active, lam_new, lam)
+            th = torch.where(accept[:, None], th_try, th)
+            for k in keys:
+                if k in cur and k in tri:
+                    m = accept.reshape((B,) + (1,) * (cur[k].dim() - 1))
+                    cur[k].copy_(torch.where(m, tri[k], cur[k]))
+            n_iter += active.to(torch.int64)
+            converged |= active & done
+            active = active & ~done & (lam < 1e16)
+            if (it % 4 == 3 or it == max_iter - 1) and not bool(active.any()):
+                break
+        self._last_lm = {'theta': th.cpu().numpy(), 'ssr': cur['ssr'].cpu().numpy(), 'n_iter': n_iter.cpu().numpy(),
+                         'converged': converged.cpu().numpy(), 'lam': lam.cpu().numpy()}
+        return self._last_lm
+
     # ------------------------------------------------------------------------------------------
     # dict <-> vector helpers (reference :898-972)
     # ------------------------------------------------------------------------------------------
