@@ -413,6 +413,34 @@ class OracleProject(object):
         J = self.jacobian(theta)
         return (J.T * r).sum(axis=1)
 
+    def scale_factors_entropy(self, theta, temperature=1.0):
+        """base_project.py:854-872 -> abstract_loss_function.py:122-134 -> linear_scale_factor.py:13-18, 63-80: for every
+        scale-factor group T * log of the SloppyCell integral over the log scale factor (QUADPACK over the whole line in
+        the reference; the finite window below holds the integrand down to exp(-72) of its peaks)."""
+        from scipy.integrate import quad
+        sims, _ = self.sim_experiments(theta)
+        entropy = 0.0
+        for g in self.sf_groups:
+            rows = self.group_rows[g]
+            s, d, sg_ = sims[rows], self.meas_mean[rows], self.meas_std[rows]
+            sde, sds = np.sum(s * d / sg_ ** 2), np.sum(s * s / sg_ ** 2)
+            B = sde / sds
+            lB = np.log(B)
+            if g not in self.sf_priors:
+                raise TypeError('scale-factor entropy needs a log prior (as in the reference)')
+            mu, sig = self.sf_priors[g]
+
+            def integrand(u):                                # linear_scale_factor.py:13-18
+                return np.exp(-sds / (2 * temperature) * (np.exp(u) * B - B) ** 2 - (u + lB - mu) ** 2 / (2 * sig ** 2))
+            w = max(np.sqrt(temperature / (sds * B * B)), sig)
+            pts = sorted([0.0, mu - lB])
+            ans, _ = quad(integrand, pts[0] - 12 * w, pts[1] + 12 * w, points=pts, limit=1000, epsabs=0, epsrel=1e-12)
+            entropy += temperature * np.log(ans)             # abstract_loss_function.py:132
+        return entropy
+
+    def free_energy(self, theta, temperature=1.0):
+        return self.sum_square_residuals(theta) - self.scale_factors_entropy(theta, temperature)    # :874-892
+
 
 def central_difference(fun, x, rel=None):
     """Central finite differences with the step rule of statsmodels' ``approx_fprime(centered=True)``
@@ -499,3 +527,43 @@ def lm_fit(residuals, jacobian, theta0, max_iter=100, lam0=1e-3, ftol=1e-12, xto
         if not lam < 1e16:
             return th, ssr, it, False
     return th, ssr, int(max_iter), False
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Metropolis ensemble sampler: restatement of project/Ensembles.py:55-178 with
+# _sampling_matrix (:226-264), _trial_move (:266-270), _accept_move (:193-198) for ONE walker fed with given random
+# numbers, with the two defects SURVEY.md lists fixed as in the product (curr_F follows accepted moves; Hessian = J^T J).
+# ---------------------------------------------------------------------------------------------------------
+def sampling_matrix(hessian, cutoff=0, temperature=1, step_scale=1):
+    u, sing_vals, vh = np.linalg.svd(0.5 * np.asarray(hessian, dtype=np.float64))          # :229
+    cutoff_sing_val = cutoff * max(sing_vals)                                                # :236
+    D = 1.0 / np.maximum(sing_vals, cutoff_sing_val)                                         # :238
+    samp_mat = np.transpose(vh) * np.sqrt(D)                                                 # :243
+    cutoff_vals = np.compress(sing_vals < cutoff_sing_val, sing_vals)                        # :247
+    if len(cutoff_vals):
+        scale = np.sqrt(len(sing_vals) - len(cutoff_vals) + sum(cutoff_vals) / cutoff_sing_val)
+    else:
+        scale = np.sqrt(len(sing_vals))
+    samp_mat = samp_mat / scale                                                              # :254
+    samp_mat = samp_mat * step_scale                                                         # :255
+    samp_mat = samp_mat * np.sqrt(temperature)                                               # :256
+    return samp_mat
+
+
+def ensemble_walker(free_energy, params, samp_mat, normals, uniforms, temperature=1.0, skip_elems=0):
+    """One walker: normals f8[steps, n], uniforms f8[steps].  Returns (ens, ens_fes, ratio)."""
+    cur = np.asarray(params, dtype=np.float64).copy()
+    curF = free_energy(cur)
+    ens, fes, accepted = [cur.copy()], [curF], 0
+    for it in range(len(normals)):
+        nxt = cur + samp_mat.dot(normals[it])                                                # :266-270, :134
+        nxtF = free_energy(nxt)
+        if not np.isfinite(nxtF):
+            nxtF = np.inf
+        if uniforms[it] < np.exp(-(nxtF - curF) / temperature):                              # :193-198
+            cur, curF = nxt, nxtF
+            accepted += 1
+        if (it + 1) % (skip_elems + 1) == 0:
+            ens.append(cur.copy())
+            fes.append(curF)
+    return np.array(ens), np.array(fes), accepted / max(len(normals), 1)
