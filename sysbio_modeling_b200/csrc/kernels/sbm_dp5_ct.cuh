@@ -67,6 +67,9 @@
 #define SBM_CT_NI       8
 
 #define SBM_CT_BAR(nt) asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory")
+#ifndef SBM_CT_ACCEPT_AT_BEGIN
+#define SBM_CT_ACCEPT_AT_BEGIN 0
+#endif
 #define SBM_CT_EM 4           /* rows of one output time staged in shared memory (more rows take the slow path) */
 
 #ifdef SBM_CT_PROF
@@ -383,12 +386,19 @@ __device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const S
                                                   double (&y)[CW][SBM_N], const double (&s3)[CW][SBM_N], ST& st)
 {
     constexpr int N = SBM_N;
+#if SBM_CT_ACCEPT_AT_BEGIN
     if (info & SBM_CT_F_ACCEPT) {
 #pragma unroll
         for (int c = 0; c < CW; ++c)
 #pragma unroll
             for (int i = 0; i < N; ++i) y[c][i] = s3[c][i];
     }
+    const double (&ynow)[CW][SBM_N] = y;
+#else
+    // a lane emits only right after an accepted step (the controller raises EMIT in the pass that advanced t) or to flush
+    // NaN rows of a failed trajectory: the rows are those of the accepted solution, still in s3 (copied into y at stage 2)
+    const double (&ynow)[CW][SBM_N] = s3;
+#endif
 #ifndef SBM_WHATIF_NO_COL_EMIT   /* experiment: how much of a step is the emission of Jacobian rows (results are wrong without) */
     if (cflags & SBM_CT_ANYEMIT) {
         if (info & SBM_CT_F_EMIT) {
@@ -397,13 +407,13 @@ __device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const S
             const bool poison = (info & SBM_CT_F_POISON) != 0;
             const int n = sh.em_n[lane];
             for (int q = 0; q < n && q < SBM_CT_EM; ++q)
-                sbm_ct_emit_row<CW>(a, sh, sh.em_mask[q * 32 + lane], a.jac + sh.em_off[q * 32 + lane], poison, col0, lane, y);
+                sbm_ct_emit_row<CW>(a, sh, sh.em_mask[q * 32 + lane], a.jac + sh.em_off[q * 32 + lane], poison, col0, lane, ynow);
             if (n > SBM_CT_EM) {
                 const long long rowbase = sh.trow[lane];
                 const int r0 = a.orow_off[sh.ktb[lane]];
                 for (int r = r0 + SBM_CT_EM; r < r0 + n; ++r)
                     sbm_ct_emit_row<CW>(a, sh, a.row_mask[r], a.jac + (rowbase + a.row_jac[r]) * (long long)a.n_proj,
-                                        poison, col0, lane, y);
+                                        poison, col0, lane, ynow);
             }
         }
     }
@@ -433,7 +443,7 @@ __device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const S
 }
 
 template <int CW, class ST>
-__device__ __forceinline__ void sbm_ct_cols_stage(const int s, const double h, const double* __restrict__ Jp,
+__device__ __forceinline__ void sbm_ct_cols_stage(const int s, const int info, const double h, const double* __restrict__ Jp,
                                                   const double* __restrict__ Gw,
                                                   double (&y)[CW][SBM_N], double (&s2)[CW][SBM_N],
                                                   double (&s3)[CW][SBM_N], ST& st,
@@ -441,7 +451,18 @@ __device__ __forceinline__ void sbm_ct_cols_stage(const int s, const double h, c
                                                   const bool anyinit, double& sq, double& d0, double& d1)
 {
     switch (s) {
-    case 2: sbm_ct_sens_stage<2, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 2:
+#if !SBM_CT_ACCEPT_AT_BEGIN
+        // the accept decision (y = the 5th-order solution of the step just taken) is applied here, not at the start of
+        // the step: there the head shares wait for it, here the column warps wait for the model warp anyway
+        if (info & SBM_CT_F_ACCEPT) {
+#pragma unroll
+            for (int c = 0; c < CW; ++c)
+#pragma unroll
+                for (int i = 0; i < SBM_N; ++i) y[c][i] = s3[c][i];
+        }
+#endif
+        sbm_ct_sens_stage<2, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
     case 3: sbm_ct_sens_stage<3, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
     case 4: sbm_ct_sens_stage<4, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
     case 5: sbm_ct_sens_stage<5, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
@@ -830,7 +851,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
             if (s >= 2) {
                 const double* Jp = sh.Jb + (s & 1) * SBM_NJ * 32 + lane;
                 const double* Gw = sh.Gd + ((s & 1) * SBM_NF + col0) * (N + (N & 1)) * 32 + 2 * lane;
-                sbm_ct_cols_stage<CW, ST>(s, h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
+                sbm_ct_cols_stage<CW, ST>(s, info, h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
             }
             if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
 #ifdef SBM_CT_PRIMAL_REPEAT
@@ -990,7 +1011,7 @@ __device__ __forceinline__ void sbm_ct_warp_async(const SbmSolveArgs& a, const S
             sbm_mb_wait(full + b, (gc / NB) & 1u); // J, G of this stage are in buffer b
             const double* Jp = sh.Jb + b * SBM_NJ * 32 + lane;
             const double* Gw = sh.Gd + (b * SBM_NF + col0) * NE * 32 + 2 * lane;
-            sbm_ct_cols_stage<CW, ST>(s, h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
+            sbm_ct_cols_stage<CW, ST>(s, info, h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
             __syncwarp();
             if (lane == 0) sbm_mb_arrive(empty + b);   // this warp is done with buffer b
             ++gc;
