@@ -18,11 +18,14 @@ from .. import _lib
 
 
 def autocorrelation(series):
-    """Normalised autocorrelation of a series through the FFT (reference ``Ensembles.py:14-29``)."""
+    """Normalised autocorrelation of a series through the FFT (reference ``Ensembles.py:14-29``, same calls: FFTPACK's
+    packed real transform, whose real and imaginary parts the reference squares SEPARATELY before transforming back -
+    kept, so that the numbers are the reference's)."""
+    import scipy.fftpack
     x = np.asarray(series, dtype=np.float64)
     n = len(x)
-    f = np.fft.rfft(x - x.mean(), n=2 * n)
-    ac = np.fft.irfft(np.abs(f) ** 2)[:n]
+    f = scipy.fftpack.rfft(x - np.mean(x), n=2 * n)
+    ac = scipy.fftpack.irfft(abs(f) ** 2)[:n]
     ac *= n / (n - 1.0 * np.arange(n))
     return ac / ac[0]
 

@@ -84,3 +84,44 @@ def test_device_generator_and_stationarity_smoke():
     assert a[0].shape == (7, 64, 3) and np.all(np.isfinite(a[1]))
     assert np.array_equal(a[0], b[0]) and not np.array_equal(a[0], c[0])
     assert 0.02 < a[2].mean() < 0.98
+
+
+# ---- pinned against the real reference (tests/golden/make_golden_ensembles.py ran its function sources here) ----
+def _golden_ens():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_golden_ensembles.json')))
+
+
+def test_sampling_matrix_and_autocorrelation_match_the_reference():
+    from sysbio_modeling_b200.project import ensembles
+    g = _golden_ens()
+    for case in g['sampling_matrix']:
+        H, ref = np.array(case['hessian']), np.array(case['samp_mat'])
+        for fn in (O.sampling_matrix, ensembles.sampling_matrix):
+            S = fn(H, case['cutoff'], case['temperature'], case['step_scale'])
+            assert np.allclose(S, ref, rtol=1e-10, atol=1e-13 * np.abs(ref).max())
+    ac = g['autocorrelation']
+    assert np.allclose(ensembles.autocorrelation(ac['series']), ac['ac'], rtol=1e-10, atol=1e-12)
+
+
+def test_scale_factor_entropy_matches_the_reference():
+    """linear_scale_factor.py:63-80 (QUADPACK over the whole line in the reference): the restatement's windowed QUADPACK
+    call, the product's host rule (composite Gauss-Legendre) and - on a GPU, test below - the torch rule."""
+    from sysbio_modeling_b200.project.loss_functions.squared_loss.linear_scale_factor import LinearScaleFactor
+    from scipy.integrate import quad
+    for case in _golden_ens()['entropy']:
+        s, d, sg = np.array(case['sim']), np.array(case['data']), np.array(case['std'])
+        sds, sde = np.sum(s * s / sg ** 2), np.sum(s * d / sg ** 2)
+        T, mu, sig = case['temperature'], case['log_prior'], case['log_prior_sigma']
+        h = LinearScaleFactor(mu, sig)
+        ent = h.calc_scale_factor_entropy(sds, sde, T)
+        assert abs(ent - case['entropy']) <= 1e-8 * max(1.0, abs(case['entropy'])), (case['temperature'], ent, case['entropy'])
+        B = sde / sds
+        assert abs(B - case['sf']) <= 1e-12 * abs(B)
+        lB = np.log(B)
+        w = max(np.sqrt(T / (sds * B * B)), sig)
+        pts = sorted([0.0, mu - lB])
+        ans, _ = quad(lambda u: np.exp(-sds / (2 * T) * (np.exp(u) * B - B) ** 2 - (u + lB - mu) ** 2 / (2 * sig ** 2)),
+                      pts[0] - 12 * w, pts[1] + 12 * w, points=pts, limit=1000, epsabs=0, epsrel=1e-12)
+        assert abs(np.log(ans) - case['entropy']) <= 1e-8 * max(1.0, abs(case['entropy']))
