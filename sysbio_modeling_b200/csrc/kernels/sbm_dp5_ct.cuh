@@ -527,6 +527,7 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
     const double hdone = sh.hb[lane];
 
     int info = 0, ktemit = 0;
+    bool fetched = false;
     if (mode != SBM_CT_IDLE) {
         // ---- the state column of the step just taken: 5th-order solution, embedded error, norms ----
         // (everything between the partial sums and the new step size is on the critical path of the whole CTA: the
@@ -665,13 +666,9 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
         const long long nt = (long long)base + __popc(want & ((1u << lane) - 1u));
         if (nt < ntraj) {
             traj = nt;
+            fetched = true;                                 // its model parameters are gathered by the whole warp below
             const int e = (int)(traj % a.E);
             const long long b = traj / a.E;
-            for (int m = 0; m < SBM_NP; ++m) {
-                const int c = a.pmap[e * SBM_NP + m];        // base_project.py:343-363
-                sh.pb[m * 32 + lane] = (c >= 0) ? exp(a.theta[b * a.theta_sb + c * a.theta_sp]) : a.pfix[e * SBM_NP + m];
-                sh.pcb[m * 32 + lane] = c;
-            }
 #pragma unroll
             for (int i = 0; i < N; ++i) sh.yb[i * 32 + lane] = a.y0[e * N + i];
             for (int q = 0; q < 7 * N; ++q) sh.fh[q * 32 + lane] = 0.0;
@@ -697,6 +694,20 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
             }
         } else {
             exhausted = true;
+        }
+    }
+    // ---- model parameters of the new trajectories: exp(theta) for optimised, the raw value for fixed parameters
+    //      (base_project.py:343-363).  One parameter per lane instead of a loop of NP exponentials in the one lane that
+    //      fetched (the whole CTA waits for this code) ----
+    for (unsigned need = __ballot_sync(FULL, fetched); need; need &= need - 1u) {
+        const int L = __ffs(need) - 1;
+        const long long trajL = __shfl_sync(FULL, traj, L);
+        const int e = (int)(trajL % a.E);
+        const long long b = trajL / a.E;
+        for (int m = lane; m < SBM_NP; m += 32) {
+            const int c = a.pmap[e * SBM_NP + m];
+            sh.pb[m * 32 + L] = (c >= 0) ? exp(a.theta[b * a.theta_sb + c * a.theta_sp]) : a.pfix[e * SBM_NP + m];
+            sh.pcb[m * 32 + L] = c;
         }
     }
     SBM_CTL_MARK(3)                                // output time / new trajectory
