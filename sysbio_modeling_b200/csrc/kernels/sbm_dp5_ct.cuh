@@ -7,27 +7,31 @@
 //
 //   lane = trajectory     32 trajectories per CTA, each with its own t, h and accept/reject decision
 //   warp = column group   warp w owns C sensitivity columns S_j = dy/dp_j (the last warp CL <= C) of ALL 32
-//                         trajectories, and one SHARE of the model's primal part
+//                         trajectories
+//   model warp(s)         XW warps without columns evaluate the model's primal part and run the step controller
+//                         (default: one; small systems run everything in one warp, XW = 0)
 //
 // Why: with lane = column (sbm_dp5_sens) every lane of a group re-evaluates the model's primal part
 // (f, J = df/dy, G = df/dp: rate laws, reciprocals, exp/log) - measured to be more than half of the FP64
-// instructions.  Here the primal part is evaluated ONCE per trajectory and stage, split by the emitter
-// (symbolic/sympy_tools.py:_emit_primal_shares) into W straight-line shares of balanced cost; every thread
-// (= trajectory) runs the share of its warp and stores the results in shared memory ([entry][lane],
-// conflict-free), from where all warps read J and their own columns of G for  dS_j/dt = J S_j + G_j.
+// instructions.  Here the primal part is evaluated ONCE per trajectory and stage: the emitter
+// (symbolic/sympy_tools.py:_emit_primal_shares) splits it into straight-line shares (one for the model warp in the
+// default layout; at the head of a step, where nothing else can run, three); the results go to shared memory
+// ([entry][lane], conflict-free), from where the column warps read J and their own columns of G for
+// dS_j/dt = J S_j + G_j.
 //
-// The state column y does not depend on the sensitivities, so the model runs ONE STAGE AHEAD: while a warp
-// works on stage s of its columns it also evaluates its share of the model at the input of stage s+1
-// (double-buffered J and G) - one CTA barrier per stage.  For that the state column lives in shared memory
-// in "pull" form (y and the stage derivatives f_1..f_7), so that every share can form the stage values of
-// exactly the states it depends on.
+// The state column y does not depend on the sensitivities, so the model runs ONE STAGE AHEAD: while the column warps
+// work on stage s, the model warp evaluates the model at the input of stage s+1 (double-buffered J and G) - one
+// CTA barrier per stage.  For that the state column lives in shared memory in "pull" form (y and the stage
+// derivatives f_1..f_7); the partial stage values are prepared one iteration ahead by the column warps.
+// A step is eight barrier intervals: controller | head (model at the input of stage 2; column warps: rows of an
+// output time) | stages 2..7.  Where the clocks go: DESIGN.md section 6, -DSBM_CT_PROF.
 //
 // Storage per (trajectory, sensitivity column): the 5 vectors  y, S1..S4  of a "push" formulation
 //   stages 2-4 pull   Y_s = y + h sum a_sj k_j           (k1..k3 live in S1..S3)
 //   after k4          S1 <- Y5, S2 <- Y6 - h a65 k5, S3 <- Y7 - h (a75 k5 + a76 k6), S4 <- h (e1 k1 + e3 k3 + e4 k4)
 //   stages 5-7 push   k5, k6, k7 are added into S2, S3, S4 as soon as they exist; S1 <- k7 (FSAL)
-// which needs two vectors fewer than keeping k1..k6.  y, S2, S3 live in registers, S1 and S4 in shared
-// memory ([element][lane]).  Full trajectories never exist; only the observable rows go to HBM.
+// which needs two vectors fewer than keeping k1..k6.  y, S2, S3 live in registers, S1 and S4 in tensor memory
+// (registers for small systems).  Full trajectories never exist; only the observable rows go to HBM.
 //
 // A rejected step has destroyed k1 of the sensitivity columns (S1 holds k7 of the rejected trial), so the
 // next "step" of that lane is a zero-length step, which re-evaluates F(y) in every stage and leaves k1 in S1
