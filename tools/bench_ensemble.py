@@ -9,8 +9,13 @@ import sysbio_modeling_b200 as sb
 from sysbio_modeling_b200 import model_files
 from sysbio_modeling_b200.project import ensembles
 
-W = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
+W = int(sys.argv[1]) if len(sys.argv) > 1 else 131072            # walkers PER GPU (weak scaling under torchrun)
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+if world > 1:
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    dist.init_process_group('nccl')
 mod = model_files.module('egfr_signalling')
 om = sb.OdeModel.from_model_file(model_files.path('egfr_signalling'))
 nominal = np.array([mod.nominal[k] for k in om.param_order])
@@ -28,11 +33,22 @@ th0 = np.log(nominal)
 hess = np.eye(len(th0)) * 2.0e4
 ensembles.ensemble_log_params_batch(proj, th0, hess=hess, steps=1, n_walkers=1024, seeds=1)      # warm-up
 torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
 t0 = time.time()
-ens, fes, ratio = ensembles.ensemble_log_params_batch(proj, th0, hess=hess, steps=steps, n_walkers=W, seeds=2,
+# independent walkers: every rank runs its own shard with its own random stream, no data-path collective
+ens, fes, ratio = ensembles.ensemble_log_params_batch(proj, th0, hess=hess, steps=steps, n_walkers=W, seeds=2 + rank,
                                                       skip_elems=steps - 1)
 torch.cuda.synchronize()
-dt = time.time() - t0
-print(json.dumps({'walkers': W, 'steps': steps, 'wall_s': dt, 'walker_steps_per_s': W * (steps + 1) / dt,
-                  'acceptance_mean': float(ratio.mean()), 'free_energy_finite': bool(np.isfinite(fes).all()),
-                  'free_energy_start': float(fes[0].mean()), 'free_energy_end': float(fes[-1].mean())}))
+dt = torch.tensor([time.time() - t0], dtype=torch.float64, device='cuda')
+acc = torch.tensor([float(ratio.mean())], dtype=torch.float64, device='cuda')
+if world > 1:
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    acc /= world
+if rank == 0:
+    print(json.dumps({'n_gpus': world, 'walkers_per_gpu': W, 'steps': steps, 'wall_s_max_over_ranks': float(dt),
+                      'walker_steps_per_s': world * W * (steps + 1) / float(dt), 'acceptance_mean': float(acc),
+                      'free_energy_finite_rank0': bool(np.isfinite(fes).all())}))
+if world > 1:
+    dist.destroy_process_group()
