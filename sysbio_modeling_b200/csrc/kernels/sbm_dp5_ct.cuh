@@ -74,6 +74,9 @@
 #ifndef SBM_CT_ACCEPT_AT_BEGIN
 #define SBM_CT_ACCEPT_AT_BEGIN 0
 #endif
+#ifndef SBM_CT_NO_STAGE_ROWS
+#define SBM_CT_NO_STAGE_ROWS 0
+#endif
 #define SBM_CT_EM 4           /* rows of one output time staged in shared memory (more rows take the slow path) */
 
 #ifdef SBM_CT_PROF
@@ -329,6 +332,10 @@ struct SbmCtShared {
     int* em_n;           // [32]               number of rows of that output time
     int* pcb;            // [NP][32]           project column of each model parameter of the lane's experiment (-1: fixed)
     long long* trow;     // [32]               first output row of the lane's parameter set (b * n_rows)
+    long long* em_soff;  // [SBM_CT_EM][32]    rows staged ahead by the model warp: position of the observable ...
+    double* em_val;      // [SBM_CT_EM][32]    ... and its value at the trial state
+    double* em_tk;       // [32]               the output time after the staged one
+    int* em_kt;          // [32]               output-time index the staging belongs to (-1: none)
     unsigned tmem_base;  // TMEM allocation holding S1 and S4 of the sensitivity columns
     unsigned long long* mbar;  // [2*NB + 2] mbarriers of the asynchronous hand-over: full[NB], empty[NB], done, go
 };
@@ -502,6 +509,31 @@ __device__ __forceinline__ void sbm_ct_state_column(const SbmCtShared& sh, const
     }
 }
 
+// Rows of the output time a clipped step lands on, prepared from the TRIAL state while the column warps are still busy
+// with stage 7 (the model warp idles there): if the controller accepts the step it only has to store them.
+__device__ __forceinline__ void sbm_ct_stage_rows(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane,
+                                                  const double (&ynew)[SBM_N])
+{
+    constexpr int N = SBM_N;
+    const int kt = sh.ci[SBM_CT_I_KT * 32 + lane], kt1 = sh.ci[SBM_CT_I_KT1 * 32 + lane];
+    const long long rowbase = sh.trow[lane];
+    const int r0 = __ldg(a.orow_off + kt), r1 = __ldg(a.orow_off + kt + 1);
+    sh.em_tk[lane] = (kt + 1 < kt1) ? __ldg(a.tout + kt + 1) : 0.0;
+    sh.em_n[lane] = r1 - r0;
+    for (int r = r0; r < r1 && r - r0 < SBM_CT_EM; ++r) {
+        const unsigned long long mask = __ldg(a.row_mask + r);
+        const int rs = __ldg(a.row_sim + r), rj = __ldg(a.row_jac + r);
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc += ((mask >> i) & 1ull) ? ynew[i] : 0.0;                  // utils.py:10-26, 48-68
+        sh.em_mask[(r - r0) * 32 + lane] = mask;
+        sh.em_off[(r - r0) * 32 + lane] = (rowbase + rj) * (long long)a.n_proj;
+        sh.em_soff[(r - r0) * 32 + lane] = rowbase + rs;
+        sh.em_val[(r - r0) * 32 + lane] = acc;
+    }
+    sh.em_kt[lane] = kt;
+}
+
 template <int W, int C, int CL, int PRE>
 __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane)
 {
@@ -632,11 +664,28 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
             // (this block stalls the whole CTA once in five steps on the MAPK benchmark: read-only table loads through the
             //  L1 path, issued before they are needed; the row base of the parameter set was kept at fetch time)
             const long long rowbase = sh.trow[lane];
-            const int r0 = __ldg(a.orow_off + kt), r1 = __ldg(a.orow_off + kt + 1);
-            const double tknext = (kt + 1 < kt1) ? __ldg(a.tout + kt + 1) : tk;
-            sh.em_n[lane] = r1 - r0;
+            double tknext;
+            int rfirst, r1;
+            if (PRE && status == SBM_OK && sh.em_kt[lane] == kt) {
+                // staged from the trial state during stage 7 (sbm_ct_stage_rows): store the observables, done
+                const int n = sh.em_n[lane];
+                for (int q = 0; q < n && q < SBM_CT_EM; ++q) a.sims[sh.em_soff[q * 32 + lane]] = sh.em_val[q * 32 + lane];
+                tknext = sh.em_tk[lane];
+                rfirst = r1 = 0;
+                if (n > SBM_CT_EM) {                                   // rows beyond the staging take the loop below
+                    r1 = __ldg(a.orow_off + kt) + n;
+                    rfirst = r1 - n + SBM_CT_EM;
+                }
+            } else {
+                rfirst = __ldg(a.orow_off + kt);
+                r1 = __ldg(a.orow_off + kt + 1);
+                tknext = (kt + 1 < kt1) ? __ldg(a.tout + kt + 1) : tk;
+                sh.em_n[lane] = r1 - rfirst;
+            }
+            sh.em_kt[lane] = -1;
+            const int r0 = r1 - sh.em_n[lane];
 #pragma unroll 2
-            for (int r = r0; r < r1; ++r) {
+            for (int r = rfirst; r < r1; ++r) {
                 const unsigned long long mask = __ldg(a.row_mask + r);
                 const int rs = __ldg(a.row_sim + r), rj = __ldg(a.row_jac + r);
                 double acc = 0.0;
@@ -933,6 +982,11 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
                 sh.sqb[(W + 0) * 32 + lane] = sqs;
                 sh.sqb[(W + 1) * 32 + lane] = q0;
                 sh.sqb[(W + 2) * 32 + lane] = q1;
+#if !SBM_CT_NO_STAGE_ROWS
+                // a clipped step ends on an output time: prepare its rows now, off the controller's critical path
+                if (sh.ci[SBM_CT_I_MODE * 32 + lane] == SBM_CT_NORMAL && (sh.ci[SBM_CT_I_BITS * 32 + lane] & 2))
+                    sbm_ct_stage_rows(a, sh, lane, ynew);
+#endif
             }
             SBM_CT_BUSY(s)
             SBM_CT_BAR(NT);
@@ -1120,6 +1174,10 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     sh.em_n = (int*)(sh.em_off + SBM_CT_EM * 32);
     sh.pcb = sh.em_n + 32;
     sh.trow = (long long*)(sh.pcb + SBM_NP * 32 + (SBM_NP & 1) * 32);
+    sh.em_soff = sh.trow + 32;
+    sh.em_val = (double*)(sh.em_soff + SBM_CT_EM * 32);
+    sh.em_tk = sh.em_val + SBM_CT_EM * 32;
+    sh.em_kt = (int*)(sh.em_tk + 32);
     sh.tmem_base = 0;
 #ifdef SBM_CT_PROF
     if (threadIdx.x < 8) sbm_ctl_prof[threadIdx.x] = 0;
@@ -1142,6 +1200,7 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
         for (int q = 0; q < SBM_CT_NI; ++q) sh.ci[q * 32 + lane] = 0;
         for (int q = 0; q < 4; ++q) sh.cnt[q * 32 + lane] = 0ull;
         sh.trj[lane] = -1;
+        sh.em_kt[lane] = -1;
         sh.hb[lane] = 0.0;
         sh.fl[lane] = 0;
         sh.ktb[lane] = 0;

@@ -235,7 +235,8 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
             const long long bytes = 8ll * (NB * NJ * 32 + NB * NF * (N + (N & 1)) * 32 + 16 + 7 * N * 32 + 2 * N * 32 + 2 * N * 32 + desc->n_params * 32 +
                                            (W + 3) * 32 + 32 + 6 * 32 + 4 * 32 + 32) +
                                     4ll * (8 * 32 + 3 * 32) + 8ll * 2 * W * 32 +
-                                    8ll * (2 * 4 * 32 + 32) + 4ll * (32 + (desc->n_params + (desc->n_params & 1)) * 32);   // staged rows (SBM_CT_EM = 4), row base, project columns
+                                    8ll * (2 * 4 * 32 + 32) + 4ll * (32 + (desc->n_params + (desc->n_params & 1)) * 32) +
+                                    8ll * (2 * 4 * 32 + 32) + 4ll * 32;   // rows staged ahead by the model warp: offsets, values, next time, index   // staged rows (SBM_CT_EM = 4), row base, project columns
             const int tm_need = ((W + 3) / 4) * 4 * C * (N + (N & 1));
             if (CL >= 1 && CL <= C && CL * N >= 2 && W + XW <= 32 && bytes <= 227 * 1024 && ((TM == 1 && tm_need <= 512) || RV == 1)) {
                 m->ctW = W; m->ctC = C; m->ctCS = CL; m->ctXW = XW; m->ct_dyn_smem = (int)bytes; m->ct_ok = true;
