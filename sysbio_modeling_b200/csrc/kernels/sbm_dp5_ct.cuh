@@ -534,8 +534,15 @@ __device__ __forceinline__ void sbm_ct_stage_rows(const SbmSolveArgs& a, const S
     sh.em_kt[lane] = kt;
 }
 
+// what the model warp has computed for the controller while the column warps finished stage 7; stays in registers across
+// the barrier (PRE == 2), so the controller - on the critical path of the whole CTA - starts with no loads for it
+struct SbmCtCarry {
+    double ynew[SBM_N], f7[SBM_N], sqs, q0, q1;
+};
+
 template <int W, int C, int CL, int PRE>
-__device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane)
+__device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane,
+                                               const SbmCtCarry& cy)
 {
     constexpr int N = SBM_N;
     constexpr unsigned FULL = 0xffffffffu;
@@ -576,7 +583,13 @@ __device__ __forceinline__ void sbm_ct_control(const SbmSolveArgs& a, const SbmC
             sq = (part[0] + part[1]) + (part[2] + part[3]);
         }
         double ynew[N], f7[N];
-        if (PRE) {
+        if (PRE == 2) {
+            sq += cy.sqs;
+            q0 = cy.q0;
+            q1 = cy.q1;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { ynew[i] = cy.ynew[i]; f7[i] = cy.f7[i]; }
+        } else if (PRE) {
             // prepared by the model warp while the column warps were busy with stage 7
             sq += sh.sqb[(W + 0) * 32 + lane];
             q0 = sh.sqb[(W + 1) * 32 + lane];
@@ -892,7 +905,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
     long long cbusy[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ctprev = 0;
 #endif
     for (;;) {
-        if (XW == 0 && warp == 0) sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 0>(a, sh, lane);
+        if (XW == 0 && warp == 0) { SbmCtCarry none; sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 0>(a, sh, lane, none); }
         SBM_CT_BAR(NT);                            // controller output published
 #ifdef SBM_CT_PROF
         ctprev = sbm_ct_clock_after_barrier(sh.cta);
@@ -959,8 +972,12 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
 #define SBM_CT_MARK(i)
 #define SBM_CT_BUSY(i)
 #endif
+    SbmCtCarry cy;
+#pragma unroll
+    for (int i = 0; i < SBM_N; ++i) { cy.ynew[i] = 0.0; cy.f7[i] = 0.0; }
+    cy.sqs = cy.q0 = cy.q1 = 0.0;
     for (;;) {
-        if (warp == W) sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 1>(a, sh, lane);
+        if (warp == W) sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 2>(a, sh, lane, cy);
         SBM_CT_BUSY(0)
         SBM_CT_BAR(NT);
         SBM_CT_MARK(0)
@@ -975,17 +992,12 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
             if (s < 7) sbm_ct_primal(sh, warp, lane, s + 1, h, (s + 1) & 1);
             else if (warp == W) {
                 // while the column warps finish stage 7: the state column's part of the controller's input
-                double ynew[SBM_N], f7[SBM_N], sqs = 0.0, q0 = 0.0, q1 = 0.0;
-                sbm_ct_state_column(sh, lane, h, a.rtol, a.atol, ynew, f7, sqs, q0, q1);
-#pragma unroll
-                for (int i = 0; i < SBM_N; ++i) sh.ynb[i * 32 + lane] = ynew[i];
-                sh.sqb[(W + 0) * 32 + lane] = sqs;
-                sh.sqb[(W + 1) * 32 + lane] = q0;
-                sh.sqb[(W + 2) * 32 + lane] = q1;
+                cy.sqs = cy.q0 = cy.q1 = 0.0;
+                sbm_ct_state_column(sh, lane, h, a.rtol, a.atol, cy.ynew, cy.f7, cy.sqs, cy.q0, cy.q1);
 #if !SBM_CT_NO_STAGE_ROWS
                 // a clipped step ends on an output time: prepare its rows now, off the controller's critical path
                 if (sh.ci[SBM_CT_I_MODE * 32 + lane] == SBM_CT_NORMAL && (sh.ci[SBM_CT_I_BITS * 32 + lane] & 2))
-                    sbm_ct_stage_rows(a, sh, lane, ynew);
+                    sbm_ct_stage_rows(a, sh, lane, cy.ynew);
 #endif
             }
             SBM_CT_BUSY(s)
@@ -1104,7 +1116,7 @@ __device__ __forceinline__ void sbm_ct_model_warp_async(const SbmSolveArgs& a, c
     for (;;) {
         sbm_mb_wait(done, step & 1u);              // all partial sums of the previous step are written
         ++step;
-        sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 1>(a, sh, lane);
+        { SbmCtCarry none; sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 1>(a, sh, lane, none); }
         __syncwarp();
         const bool alive = (sh.cta[0] & SBM_CT_ALIVE) != 0;
         if (lane == 0) sbm_mb_arrive(go);
