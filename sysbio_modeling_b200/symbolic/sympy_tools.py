@@ -620,7 +620,7 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0, f
             # the model at the input of stage 2, evaluated while the column warps have nothing else to do - except the
             # start of their step (accept copy, Jacobian rows of an output time: ~1,000 clocks measured, about a
             # third of the whole model), so the model warp takes the largest cluster (the longest dependent chain)
-            base = float(_os.environ.get('SBM_CT_HEAD_COLBASE', '150')) if w < W else 0.0
+            base = float(_os.environ.get('SBM_CT_HEAD_COLBASE', '200')) if w < W else 0.0
         elif XW:
             # several shares with a model warp: balance the load of the schedulers (warp w runs on scheduler w % 4), not
             # of the warps - the model warp's scheduler hosts one column warp fewer.  Measured on C4: 1 / 4 / 7 / 10
@@ -881,8 +881,9 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
         _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct)
         # a second, wider split for the first stage of a step: its step size is only known once the previous step
         # has been judged, so nothing overlaps it and every warp is free to help
-        # (measured on C4 with the model warp: 1 / 2 / 3 / 4 / 6 head shares = 144.2 / 141.7 / 145.1 / 144.5 / 142.9 k solves/s)
-        n_head = int(_os.environ.get('SBM_CT_HEAD_SHARES', '0')) or min(W_ct + XW_ct, 3)
+        # (measured on C4 with the model warp: 1 / 2 / 3 / 4 / 6 head shares = 144.2 / 141.7 / 145.1 / 144.5 / 142.9 k solves/s;
+        #  final build, (shares, column base load): (3, 150) 157.3, (3, 200) 157.9, (4, 100) 157.7, (4, 200) 158.8, (5, 150) 157.2 k)
+        n_head = int(_os.environ.get('SBM_CT_HEAD_SHARES', '0')) or min(W_ct + XW_ct, 4)
         L.append('#define SBM_CT_HEAD_SHARES %d' % n_head)
         _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct, fname='sbm_primal_head',
                             n_shares=n_head, head=True)
