@@ -417,6 +417,9 @@ __device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const S
             // benchmark has an emitting lane): masks and row positions come staged from the controller
             const bool poison = (info & SBM_CT_F_POISON) != 0;
             const int n = sh.em_n[lane];
+#ifdef SBM_CT_EMIT_UNROLL
+#pragma unroll SBM_CT_EMIT_UNROLL
+#endif
             for (int q = 0; q < n && q < SBM_CT_EM; ++q)
                 sbm_ct_emit_row<CW>(a, sh, sh.em_mask[q * 32 + lane], a.jac + sh.em_off[q * 32 + lane], poison, col0, lane, ynow);
             if (n > SBM_CT_EM) {
