@@ -41,6 +41,9 @@ extern "C" {
                                      default 0 reproduces the reference, whose rows stay zero because
                                      base_project.py:519-530 is never called by :764-771            */
 
+#define SBM_FLAG_LOSS_GENERIC    2 /* force the CTA-per-set loss kernel (J stays in global memory) even when the
+                                     warp-per-set kernel with the TMA-staged tile fits (tests compare the two)        */
+
 /* row kinds in sbm_plan_desc_t.row_kind */
 #define SBM_ROW_MEASUREMENT 0
 #define SBM_ROW_PARAM_PRIOR 1 /* row_aux = project column (base_project.py:427-437)                 */
@@ -156,6 +159,29 @@ int sbm_loss(sbm_plan* p, int loss_kind, int flags, long long B,
              const double* theta, long long theta_sb, long long theta_sp,
              double* sims, double* jac, double* resid, double* ssr, double* sf, double* sfgrad,
              double* grad, void* stream);
+
+/* ---- the loss epilogue in two halves: the hook of the EXPERIMENT shard (experiments of one parameter set spread over
+ * several GPUs).  A scale factor couples the rows of its group across all experiments (abstract_loss_function.py:62-91),
+ * so every rank forms the group sums of ITS rows, the sums are all-reduced, and every rank finishes its rows with the
+ * global sums.  sums is device [B][n_groups][3 + 2 n_proj]:
+ *   linear_scale_factor.py:27-42   p1 = sum s d / sigma^2, p2 = sum s^2 / sigma^2, (p3 unused),
+ *                                  j1[c] = sum J_c d / sigma^2, j2[c] = sum J_c s / sigma^2
+ *   log_scale_factor.py:17-36      p1 = sum 1/sr^2, p2 = sum log(d)/sr^2, p3 = sum log(s)/sr^2, j1[c] = sum J_c/(s sr^2)
+ * sbm_loss == sbm_loss_sums + sbm_loss_finish without the exchange.  jac may be NULL (residual path: p1..p3 only).   */
+int sbm_loss_sums(sbm_plan* p, int loss_kind, int flags, long long B,
+                  const double* theta, long long theta_sb, long long theta_sp,
+                  double* sims, double* jac, double* sums, void* stream);
+int sbm_loss_finish(sbm_plan* p, int loss_kind, int flags, long long B,
+                    const double* theta, long long theta_sb, long long theta_sp,
+                    double* sims, double* jac, const double* sums, double* resid, double* ssr, double* sf,
+                    double* sfgrad, double* grad, void* stream);
+
+/* ---- per-set normal equations: what the Jacobian-block gather of the multi-GPU path ships ("normally
+ * only J^T J / J^T r [22 x 22 + 22] per set are needed") and what scipy.optimize.leastsq's consumer forms from
+ * Project.calc_project_jacobian / residuals (tests/test_Project.py:202-213).
+ *   out device [B][n_proj (n_proj + 1) / 2 + n_proj + 1]: lower triangle of J^T J (row-major), J^T r, r^T r.  n_proj <= 32. */
+int sbm_normal_equations(long long B, int n_rows, int n_proj, const double* jac, const double* resid, double* out,
+                         void* stream);
 
 /* ---- fused objective calls with HOST buffers (what a reference-side binding calls) ---------------------
  * Project.residuals / calc_sum_square_residuals (base_project.py:708-729, 807-827) and

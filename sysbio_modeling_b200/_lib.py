@@ -13,6 +13,7 @@ CACHE_DIR = os.path.join(_HERE, '_cache')
 SBM_SOLVER_DP5, SBM_SOLVER_RODAS4 = 0, 1
 SBM_LOSS_SQUARE, SBM_LOSS_LOG, SBM_LOSS_NORMALIZED = 0, 1, 2
 SBM_FLAG_PRIOR_JAC_UNIT = 1
+SBM_FLAG_LOSS_GENERIC = 2
 SBM_ROW_MEASUREMENT, SBM_ROW_PARAM_PRIOR, SBM_ROW_SF_PRIOR, SBM_ROW_PLAIN = 0, 1, 2, 3
 SBM_N_COUNTERS = 8
 STATUS_NAMES = {0: 'ok', 1: 'max_steps', 2: 'step_underflow', 3: 'non_finite'}
@@ -65,7 +66,8 @@ class SolverOpts(ctypes.Structure):
 
 
 EXPORTS = ['sbm_model_compile', 'sbm_model_info', 'sbm_model_log', 'sbm_model_destroy', 'sbm_plan_create',
-           'sbm_plan_destroy', 'sbm_solve', 'sbm_loss', 'sbm_residuals_host', 'sbm_jacobian_host', 'sbm_lm_step',
+           'sbm_plan_destroy', 'sbm_solve', 'sbm_loss', 'sbm_loss_sums', 'sbm_loss_finish', 'sbm_normal_equations',
+           'sbm_residuals_host', 'sbm_jacobian_host', 'sbm_lm_step',
            'sbm_fp64_peak', 'sbm_device_count', 'sbm_last_error', 'sbm_version']
 
 _lib = None
@@ -93,6 +95,9 @@ def lib():
     L.sbm_plan_destroy.restype = None
     L.sbm_solve.argtypes = [vp, ctypes.POINTER(SolverOpts), ll, vp, ll, ll, vp, vp, vp, vp, vp]
     L.sbm_loss.argtypes = [vp, ci, ci, ll, vp, ll, ll, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sbm_loss_sums.argtypes = [vp, ci, ci, ll, vp, ll, ll, vp, vp, vp, vp]
+    L.sbm_loss_finish.argtypes = [vp, ci, ci, ll, vp, ll, ll, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sbm_normal_equations.argtypes = [ll, ci, ci, vp, vp, vp, vp]
     L.sbm_residuals_host.argtypes = [vp, ctypes.POINTER(SolverOpts), ci, ll, vp, vp, vp, vp, vp, vp, vp, vp]
     L.sbm_jacobian_host.argtypes = [vp, ctypes.POINTER(SolverOpts), ci, ci, ll, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.sbm_lm_step.argtypes = [ll, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]

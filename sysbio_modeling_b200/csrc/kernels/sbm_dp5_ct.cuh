@@ -194,6 +194,19 @@ struct SbmCtStoreTmem {
     __device__ __forceinline__ void fence() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 };
 
+// experiment (-DSBM_WHATIF_NO_TMEM): no storage at all for S1 / S4 - what the tensor-memory transfers cost (results are wrong)
+struct SbmCtStoreNone {
+    unsigned t1, t4;
+    __device__ __forceinline__ void issue(const int, const int, SbmCtPair& v) const { v.r0 = 0u; v.r1 = 0x39b4484bu; v.r2 = 0u; v.r3 = 0x39b4484bu; }
+    __device__ __forceinline__ void wait(SbmCtPair& v, double& a, double& b) const
+    {
+        a = __hiloint2double((int)v.r1, (int)v.r0);
+        b = __hiloint2double((int)v.r3, (int)v.r2);
+    }
+    __device__ __forceinline__ void store(const int, const int, const double, const double) {}
+    __device__ __forceinline__ void fence() const {}
+};
+
 // S1 / S4 in registers: small systems (one warp per CTA = one thread per trajectory) whose five vectors fit the
 // register file - every index is a compile-time constant after unrolling
 template <int NEL>
@@ -231,6 +244,16 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
 {
     constexpr int N = SBM_N, NE = N + (N & 1), NP2 = NE / 2;
     __syncwarp();                                  // tcgen05.ld/st are warp-collective: be converged (cheap insurance)
+    // Tensor-memory transfers are pipelined by hand: tcgen05.wait::ld waits for EVERY outstanding load of the thread, so
+    // the vectors a row pair needs in its update (k1 in stage 4, the error accumulator from stage 5 on) are requested one
+    // row pair ahead - right AFTER the wait for the current one - and their latency hides behind the FMA chains of the
+    // current row pair (measured with -DSBM_WHATIF_NO_TMEM: exposed TMEM latency was 1,700 clocks of stage 4's 4,150).
+    constexpr int USLOT = (S == 4) ? 1 : 4;        // vector read by the updates of this stage (S >= 4)
+    SbmCtPair pu[2][CW];                           // [row pair parity][column]
+    if (S >= 4) {
+#pragma unroll
+        for (int c = 0; c < CW; ++c) st.issue(USLOT, c * NE, pu[0][c]);       // joins the batch of the stage inputs
+    }
     // ---- stage input of every element (element e = c*NE + i; S1 comes in row pairs) ----
     double w[CW][N];
     if (S <= 5) {
@@ -259,27 +282,37 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
 #pragma unroll
     for (int i0 = 0; i0 < N; i0 += 2) {
         const bool two = (i0 + 1 < N);
-        SbmCtPair p1[CW], p4[CW];
-#pragma unroll
-        for (int c = 0; c < CW; ++c) {
-            if (S == 4) st.issue(1, c * NE + i0, p1[c]);       // k1, for the in-place conversion
-            if (S >= 5) st.issue(4, c * NE + i0, p4[c]);       // error accumulator
-        }
+        const int par = (i0 >> 1) & 1;
         double acc[2][CW];
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
+#ifdef SBM_WHATIF_NO_G         /* experiment: no loads of G (results are wrong) */
+            acc[0][c] = 1e-30;
+            acc[1][c] = 2e-30;
+#else
             // dense G, both states of the row pair in one 128-bit load (layout: SBM_GIDX in the model source)
             const double2 g2 = *reinterpret_cast<const double2*>(Gw + SBM_GIDX(c * NE + i0));
             acc[0][c] = g2.x;
             acc[1][c] = g2.y;
+#endif
         }
         sbm_jrow<CW>(i0, Jp, w, acc[0]);
         if (two) sbm_jrow<CW>(i0 + 1, Jp, w, acc[1]);
+        double ua[CW], ub[CW];
+#pragma unroll
+        for (int c = 0; c < CW; ++c) {
+            ua[c] = 0.0; ub[c] = 0.0;
+            if (S >= 4) st.wait(pu[par][c], ua[c], ub[c]);
+        }
+        if (S >= 4 && i0 + 2 < N) {
+#pragma unroll
+            for (int c = 0; c < CW; ++c) st.issue(USLOT, c * NE + i0 + 2, pu[par ^ 1][c]);
+        }
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
             double v1a = 0.0, v1b = 0.0, v4a = 0.0, v4b = 0.0;
-            if (S == 4) st.wait(p1[c], v1a, v1b);
-            if (S >= 5) st.wait(p4[c], v4a, v4b);
+            if (S == 4) { v1a = ua[c]; v1b = ub[c]; }
+            if (S >= 5) { v4a = ua[c]; v4b = ub[c]; }
             double dummy2 = 0.0, dummy3 = 0.0;
             sbm_ct_update<S>(acc[0][c], h, y[c][i0], v1a, s2[c][i0], s3[c][i0], v4a);
             if (two) sbm_ct_update<S>(acc[1][c], h, y[c][i0 + 1], v1b, s2[c][i0 + 1], s3[c][i0 + 1], v4b);
@@ -882,7 +915,11 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
     typedef SbmCtStoreReg<CW * NE> ST;
     ST st;
 #else
+#ifdef SBM_WHATIF_NO_TMEM
+    typedef SbmCtStoreNone ST;
+#else
     typedef SbmCtStoreTmem ST;
+#endif
     ST st;
     // this warp's TMEM window: its lane quadrant, 4*C*NE columns per warp of the quadrant (S1 then S4)
     st.t1 = sh.tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 4 * C * NE);
@@ -928,11 +965,13 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
         // stage s+1 (s <= 6) - the model runs one stage ahead; one barrier per iteration
 #pragma unroll 1
         for (int s = 1; s <= 7; ++s) {
+#ifndef SBM_WHATIF_COLS_SKIP   /* experiment: the model warp alone (results are wrong) */
             if (s >= 2) {
                 const double* Jp = sh.Jb + (s & 1) * SBM_NJ * 32 + lane;
                 const double* Gw = sh.Gd + ((s & 1) * SBM_NF + col0) * (N + (N & 1)) * 32 + 2 * lane;
                 sbm_ct_cols_stage<CW, ST>(s, info, h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
             }
+#endif
             if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
 #ifdef SBM_CT_PRIMAL_REPEAT
             // experiment: evaluate the share several times to measure how much of the critical path it is

@@ -148,6 +148,7 @@ struct sbm_model {
     std::vector<char> cubin;
     bool from_cache = false;
     bool loaded = false;
+    int device = -1;             // device whose context holds `mod` (one module per model; see ensure_loaded)
     CUmodule mod = nullptr;
     KernelSlot dp5_plain, dp5_sens, dp5_ct, rodas4;
     std::mutex mu;
@@ -333,25 +334,42 @@ static int slot_load(sbm_model* m, KernelSlot& s, const char* name)
 static int ensure_loaded(sbm_model* m)
 {
     std::lock_guard<std::mutex> lk(m->mu);
-    if (m->loaded) return 0;
     int rc = require_device();
     if (rc) return rc;
-    DRV(driver().cuModuleLoadData_(&m->mod, m->cubin.data()));
-    if ((rc = slot_load(m, m->dp5_plain, "sbm_dp5_plain"))) return rc;
-    if ((rc = slot_load(m, m->dp5_sens, "sbm_dp5_sens"))) return rc;
-    if (m->has_rodas && (rc = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return rc;
-    DRV(driver().cuFuncSetAttribute_(m->dp5_sens.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
-    DRV(driver().cuFuncSetAttribute_(m->dp5_plain.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_plain));
-    if (m->ct_ok) {
-        if ((rc = slot_load(m, m->dp5_ct, "sbm_dp5_ct"))) return rc;
-        DRV(driver().cuFuncSetAttribute_(m->dp5_ct.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->ct_dyn_smem));
-        int dev = 0;
-        RT(cudaGetDevice(&dev));
-        RT(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DRV(driver().cuOccupancy_(&m->ct_ctas_per_sm, m->dp5_ct.fn, (m->ctW + m->ctXW) * 32, (size_t)m->ct_dyn_smem));
-        if (m->ct_tmem_cols > 0 && m->ct_ctas_per_sm > 512 / m->ct_tmem_cols) m->ct_ctas_per_sm = 512 / m->ct_tmem_cols;
-        if (m->ct_ctas_per_sm < 1) m->ct_ok = false;
+    int dev = 0;
+    RT(cudaGetDevice(&dev));
+    if (m->loaded) {
+        // the CUmodule lives in the context of the device that was current at first use (one process per GPU is the
+        // deployment model): launching it from another device's context would use a foreign handle
+        if (dev != m->device)
+            return fail(SBM_E_INVALID, "model was loaded on CUDA device " + std::to_string(m->device) + " but device " +
+                        std::to_string(dev) + " is current (compile one model per device / process)");
+        return 0;
     }
+    DRV(driver().cuModuleLoadData_(&m->mod, m->cubin.data()));
+    rc = [&]() -> int {
+        int r;
+        if ((r = slot_load(m, m->dp5_plain, "sbm_dp5_plain"))) return r;
+        if ((r = slot_load(m, m->dp5_sens, "sbm_dp5_sens"))) return r;
+        if (m->has_rodas && (r = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return r;
+        DRV(driver().cuFuncSetAttribute_(m->dp5_sens.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
+        DRV(driver().cuFuncSetAttribute_(m->dp5_plain.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_plain));
+        RT(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev));
+        if (m->ct_ok) {
+            if ((r = slot_load(m, m->dp5_ct, "sbm_dp5_ct"))) return r;
+            DRV(driver().cuFuncSetAttribute_(m->dp5_ct.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->ct_dyn_smem));
+            DRV(driver().cuOccupancy_(&m->ct_ctas_per_sm, m->dp5_ct.fn, (m->ctW + m->ctXW) * 32, (size_t)m->ct_dyn_smem));
+            if (m->ct_tmem_cols > 0 && m->ct_ctas_per_sm > 512 / m->ct_tmem_cols) m->ct_ctas_per_sm = 512 / m->ct_tmem_cols;
+            if (m->ct_ctas_per_sm < 1) m->ct_ok = false;
+        }
+        return 0;
+    }();
+    if (rc) {                               // do not leak the module on a failed load (it is loaded again on retry)
+        driver().cuModuleUnload_(m->mod);
+        m->mod = nullptr;
+        return rc;
+    }
+    m->device = dev;
     m->loaded = true;
     return 0;
 }
@@ -414,6 +432,11 @@ struct sbm_plan {
     double *pfix = nullptr, *y0 = nullptr, *tout = nullptr, *data = nullptr, *sigma = nullptr;
     unsigned long long* row_mask = nullptr;
     std::vector<void*> owned;
+    bool jac_full = false;        // the integrator writes EVERY entry of jac (no memset needed before the launch)
+    int sm_count = 0;
+    std::mutex mu;                // the *_host entry points share the workspaces below: one call at a time per plan
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // grow-only workspaces of the *_host entry points
     DevBuf w_theta, w_sims, w_jac, w_resid, w_ssr, w_sf, w_sfgrad, w_grad, w_status, w_counters;
 };
@@ -437,6 +460,8 @@ extern "C" void sbm_plan_destroy(sbm_plan* p)
     for (void* q : p->owned) cudaFree(q);
     p->w_theta.release(); p->w_sims.release(); p->w_jac.release(); p->w_resid.release(); p->w_ssr.release();
     p->w_sf.release(); p->w_sfgrad.release(); p->w_grad.release(); p->w_status.release(); p->w_counters.release();
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    for (int i = 0; i < 2; ++i) { if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]); if (p->ev_free[i]) cudaEventDestroy(p->ev_free[i]); }
     delete p;
 }
 
@@ -465,6 +490,29 @@ extern "C" int sbm_plan_create(sbm_model* m, const sbm_plan_desc_t* d, sbm_plan*
         UP(grp_rows, n_gr)
     }
 #undef UP
+    {
+        int dev = 0;
+        RT(cudaGetDevice(&dev));
+        RT(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // Does the integrator write every entry of the Jacobian?  True when every row is an observable row of some output
+    // time and every project column is fed by a free parameter of the experiment that owns the row (C4: one experiment,
+    // 22 global parameters).  Then sbm_solve skips the memset of [B][n_rows][n_proj] (461 MB per call on C4).
+    if (m && !d->jac_atomic && d->n_rows > 0 && d->n_proj > 0 && (long long)d->n_rows * d->n_proj <= (1ll << 24)) {
+        const int NP = m->desc.n_params;
+        std::vector<char> covered((size_t)d->n_rows * d->n_proj, 0);
+        for (int e = 0; e < d->E; ++e)
+            for (int kt = d->tout_off[e]; kt < d->tout_off[e + 1]; ++kt)
+                for (int r = d->orow_off[kt]; r < d->orow_off[kt + 1]; ++r)
+                    for (int q = 0; q < NP; ++q) {
+                        const int c = d->pmap[(size_t)e * NP + q];
+                        if (c >= 0 && c < d->n_proj && d->row_jac[r] >= 0 && d->row_jac[r] < d->n_rows)
+                            covered[(size_t)d->row_jac[r] * d->n_proj + c] = 1;
+                    }
+        bool all = true;
+        for (char c : covered) if (!c) { all = false; break; }
+        p->jac_full = all;
+    }
     *out = p;
     return 0;
 }
@@ -501,7 +549,10 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
     if (o->jac_raw && jac && p->d.n_proj != m->desc.n_free) return fail(SBM_E_INVALID, "jac_raw needs a plan with n_proj == n_free");
     a.rtol = o->rtol; a.atol = o->atol; a.h0 = o->h0;
 
-    if (jac) RT(cudaMemsetAsync(jac, 0, (size_t)B * p->d.n_rows * p->d.n_proj * sizeof(double), st));
+    // (pmap of a fixed model parameter is -1, so a column is "covered" only through a free parameter; with jac_raw the
+    //  columns are the model's free parameters themselves)
+    if (jac && !(p->jac_full && !o->jac_raw))
+        RT(cudaMemsetAsync(jac, 0, (size_t)B * p->d.n_rows * p->d.n_proj * sizeof(double), st));
 
     const long long ntraj = B * p->d.E;
     KernelSlot* ks;
@@ -529,16 +580,20 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
 // ------------------------------------------------------------------------------------------------
 // loss epilogue
 // ------------------------------------------------------------------------------------------------
-extern "C" int sbm_loss(sbm_plan* p, int loss_kind, int flags, long long B,
-                        const double* theta, long long theta_sb, long long theta_sp,
-                        double* sims, double* jac, double* resid, double* ssr, double* sf, double* sfgrad,
-                        double* grad, void* stream)
+static int loss_common(sbm_plan* p, int loss_kind, int flags, int phase, long long B,
+                       const double* theta, long long theta_sb, long long theta_sp,
+                       double* sims, double* jac, double* sums, double* resid, double* ssr, double* sf, double* sfgrad,
+                       double* grad, void* stream, const char* who)
 {
-    if (!p || !theta || !sims || !resid || !ssr) return fail(SBM_E_INVALID, "sbm_loss: null argument");
-    if (p->d.n_groups > 0 && !sf) return fail(SBM_E_INVALID, "sbm_loss: sf buffer required when scale-factor groups exist");
-    if (jac && p->d.n_groups > 0 && !sfgrad) return fail(SBM_E_INVALID, "sbm_loss: sfgrad workspace required with jac");
-    if (loss_kind < 0 || loss_kind > 2) return fail(SBM_E_INVALID, "sbm_loss: unknown loss");
-    if (B <= 0) return fail(SBM_E_INVALID, "sbm_loss: B must be positive");
+    if (!p || !theta || !sims) return fail(SBM_E_INVALID, std::string(who) + ": null argument");
+    if (phase != SBM_LOSS_PHASE_SUMS) {
+        if (!resid || !ssr) return fail(SBM_E_INVALID, std::string(who) + ": null argument");
+        if (p->d.n_groups > 0 && !sf) return fail(SBM_E_INVALID, std::string(who) + ": sf buffer required when scale-factor groups exist");
+        if (jac && p->d.n_groups > 0 && !sfgrad) return fail(SBM_E_INVALID, std::string(who) + ": sfgrad workspace required with jac");
+    }
+    if (phase != SBM_LOSS_PHASE_ALL && p->d.n_groups > 0 && !sums) return fail(SBM_E_INVALID, std::string(who) + ": sums buffer required");
+    if (loss_kind < 0 || loss_kind > 2) return fail(SBM_E_INVALID, std::string(who) + ": unknown loss");
+    if (B <= 0) return fail(SBM_E_INVALID, std::string(who) + ": B must be positive");
     int rc = require_device();
     if (rc) return rc;
     SbmLossArgs a;
@@ -546,11 +601,53 @@ extern "C" int sbm_loss(sbm_plan* p, int loss_kind, int flags, long long B,
     a.data = p->data; a.sigma = p->sigma; a.row_group = p->row_group; a.row_kind = p->row_kind; a.row_aux = p->row_aux;
     a.grp_off = p->grp_off; a.grp_rows = p->grp_rows;
     a.theta = theta; a.theta_sb = theta_sb; a.theta_sp = theta_sp;
-    a.sims = sims; a.jac = jac; a.resid = resid; a.ssr = ssr; a.sf = sf; a.sfgrad = sfgrad; a.grad = grad;
+    a.sims = sims; a.jac = jac; a.resid = resid; a.ssr = ssr; a.sf = sf; a.sfgrad = sfgrad; a.grad = grad; a.sums = sums;
     a.B = B; a.n_rows = p->d.n_rows; a.n_proj = p->d.n_proj; a.n_groups = p->d.n_groups;
-    a.loss_kind = loss_kind; a.flags = flags;
-    sbm_launch_loss(a, (cudaStream_t)stream);
-    RT(cudaGetLastError());
+    a.loss_kind = loss_kind; a.flags = flags; a.phase = phase;
+    RT(sbm_launch_loss(a, (cudaStream_t)stream, p->sm_count));
+    return 0;
+}
+
+extern "C" int sbm_loss(sbm_plan* p, int loss_kind, int flags, long long B,
+                        const double* theta, long long theta_sb, long long theta_sp,
+                        double* sims, double* jac, double* resid, double* ssr, double* sf, double* sfgrad,
+                        double* grad, void* stream)
+{
+    return loss_common(p, loss_kind, flags, SBM_LOSS_PHASE_ALL, B, theta, theta_sb, theta_sp, sims, jac, nullptr, resid, ssr, sf,
+                       sfgrad, grad, stream, "sbm_loss");
+}
+
+extern "C" int sbm_loss_sums(sbm_plan* p, int loss_kind, int flags, long long B,
+                             const double* theta, long long theta_sb, long long theta_sp,
+                             double* sims, double* jac, double* sums, void* stream)
+{
+    return loss_common(p, loss_kind, flags, SBM_LOSS_PHASE_SUMS, B, theta, theta_sb, theta_sp, sims, jac, sums, nullptr, nullptr,
+                       nullptr, nullptr, nullptr, stream, "sbm_loss_sums");
+}
+
+extern "C" int sbm_loss_finish(sbm_plan* p, int loss_kind, int flags, long long B,
+                               const double* theta, long long theta_sb, long long theta_sp,
+                               double* sims, double* jac, const double* sums, double* resid, double* ssr, double* sf,
+                               double* sfgrad, double* grad, void* stream)
+{
+    return loss_common(p, loss_kind, flags, SBM_LOSS_PHASE_FINISH, B, theta, theta_sb, theta_sp, sims, jac,
+                       const_cast<double*>(sums), resid, ssr, sf, sfgrad, grad, stream, "sbm_loss_finish");
+}
+
+extern "C" int sbm_normal_equations(long long B, int n_rows, int n_proj, const double* jac, const double* resid, double* out,
+                                    void* stream)
+{
+    if (!jac || !resid || !out) return fail(SBM_E_INVALID, "sbm_normal_equations: null argument");
+    if (B <= 0 || n_rows <= 0 || n_proj <= 0) return fail(SBM_E_INVALID, "sbm_normal_equations: B, n_rows, n_proj must be positive");
+    if (n_proj > 32) return fail(SBM_E_INVALID, "sbm_normal_equations: n_proj > 32 is not supported");
+    int rc = require_device();
+    if (rc) return rc;
+    int dev = 0, sms = 0;
+    RT(cudaGetDevice(&dev));
+    RT(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SbmGramArgs a;
+    a.jac = jac; a.resid = resid; a.out = out; a.B = B; a.n_rows = n_rows; a.n_proj = n_proj;
+    RT(sbm_launch_gram(a, (cudaStream_t)stream, sms));
     return 0;
 }
 

@@ -1,16 +1,32 @@
 // sbm_epilogue.cuh - model-independent device code compiled statically into libsbm_b200.so:
 //   * the loss epilogue: optimal scale factors and their gradients, residuals, SSR, scaled Jacobian
 //     and J^T r  (reference project/loss_functions/**; formulas cited at each step);
+//   * per-set normal equations J^T J / J^T r (what the optimisers and the Jacobian-block gather consume);
 //   * the DFMA-throughput microbenchmark that gives the measured FP64 roofline denominator.
 //
-// One CTA per parameter set: a scale factor couples every row of its group across all experiments of
-// that parameter set, so the reduction cannot live inside the per-trajectory integrator.  The pass is
-// HBM-bound (reads the model Jacobian twice, writes it once); its traffic is stated in DESIGN.md.
+// A scale factor couples every row of its group across all experiments of a parameter set, so the reduction
+// cannot live inside the per-trajectory integrator.  Two kernels, same arithmetic:
+//
+//   sbm_loss_tile_kernel  one WARP per parameter set.  The model Jacobian of the set ([n_rows][n_proj], contiguous)
+//                         is staged in shared memory by one TMA bulk copy (cp.async.bulk, completion on an mbarrier),
+//                         double-buffered per warp; the scaled Jacobian goes back by a TMA bulk store.  HBM traffic:
+//                         J read ONCE and written once (the previous kernel read it twice).  Used whenever the tile
+//                         fits (C4: 40 x 22 doubles = 7 KB), and for residual-only evaluations (no tile at all).
+//   sbm_loss_kernel       one CTA per parameter set, J stays in global memory (two reads, one write): any shape
+//                         (C2: 65,536 rows x 16,384 project columns per set).
+//
+// Both can stop after the group sums (SBM_LOSS_PHASE_SUMS) or start from given sums (SBM_LOSS_PHASE_FINISH): that is
+// the hook of the experiment shard (distributed.py), which all-reduces the sums over ranks in between
+// (abstract_loss_function.py:62-91, linear_scale_factor.py:27-42).
 #ifndef SBM_EPILOGUE_CUH
 #define SBM_EPILOGUE_CUH
 
 #include <cuda_runtime.h>
 #include "../../include/sbm_b200.h"
+
+#define SBM_LOSS_PHASE_ALL    0
+#define SBM_LOSS_PHASE_SUMS   1   /* write sums[b][g][3 + 2 n_proj] and stop                     */
+#define SBM_LOSS_PHASE_FINISH 2   /* read the (reduced) sums instead of forming them              */
 
 struct SbmLossArgs {
     const double* data;
@@ -29,16 +45,278 @@ struct SbmLossArgs {
     double* sf;
     double* sfgrad;
     double* grad;
+    double* sums;          // [B][n_groups][3 + 2 n_proj]: p1, p2, p3, j1[n_proj], j2[n_proj] (phases SUMS / FINISH)
     long long B;
-    int n_rows, n_proj, n_groups, loss_kind, flags;
+    int n_rows, n_proj, n_groups, loss_kind, flags, phase;
 };
 
 #define SBM_LOSS_THREADS 128
+#define SBM_INF_BITS 0x7ff0000000000000ll
 
-__device__ __forceinline__ double sbm_block_sum(double v, double* red)
+// ---- the arithmetic shared by both kernels -----------------------------------------------------------------
+// weights of one row of a scale-factor group
+//   linear (linear_scale_factor.py:27-42):  w = 1/sigma^2;  p1 += s d w, p2 += s s w;  j1 += J d w, j2 += J s w
+//   log    (log_scale_factor.py:17-36), sigma rescaled by the data (sr = sigma / d):  w = 1/sr^2;
+//          p1 += w, p2 += log(d) w, p3 += log(s) w;  j1 += J / (s sr^2)
+__device__ __forceinline__ void sbm_sf_terms(const bool is_log, const double s, const double d, const double sg,
+                                             double& p1, double& p2, double& p3)
+{
+    if (!is_log) {
+        const double w = 1.0 / (sg * sg);
+        p1 += s * d * w;
+        p2 += s * s * w;
+    } else {
+        const double sr = sg / d;
+        const double w = 1.0 / (sr * sr);
+        p1 += w;
+        p2 += log(d) * w;
+        p3 += log(s) * w;
+    }
+}
+
+__device__ __forceinline__ void sbm_sfgrad_terms(const bool is_log, const double J, const double s, const double d,
+                                                 const double sg, double& j1, double& j2)
+{
+    if (!is_log) {
+        const double w = 1.0 / (sg * sg);
+        j1 += J * d * w;           // jac_dot_exp
+        j2 += J * s * w;           // jac_dot_sim
+    } else {
+        const double sr = sg / d;
+        j1 += J / (s * sr * sr);
+    }
+}
+
+__device__ __forceinline__ double sbm_sf_value(const bool is_log, const double p1, const double p2, const double p3)
+{
+    return is_log ? exp(p2 / p1) * exp(-p3 / p1) : p1 / p2;
+}
+
+// dB/dtheta_c: linear_scale_factor.py:33-42 (note the factor 2), log_scale_factor.py:29-36
+__device__ __forceinline__ double sbm_sfgrad_value(const bool is_log, const double B, const double p1, const double p2,
+                                                   const double j1, const double j2)
+{
+    return is_log ? B * (-1.0 / p1) * j1 : j1 / p2 - 2.0 * p1 * j2 / (p2 * p2);
+}
+
+// scaled Jacobian entry (squared_loss_function.py:58-80, log_squared_loss_function.py:66-98; prior rows:
+// abstract_loss_function.py:107-120, linear_scale_factor.py:44-53, base_project.py:519-530)
+__device__ __forceinline__ double sbm_scaled_entry(const SbmLossArgs& a, const bool is_log, const int r, const int c,
+                                                   const int kind, double J, const double s,
+                                                   const double* __restrict__ sfv, const double* __restrict__ sfg)
+{
+    if (kind == SBM_ROW_MEASUREMENT) {
+        const int g = a.row_group[r];
+        if (g >= 0) {
+            const double gB = sfg[g * a.n_proj + c];
+            J = is_log ? (J / s + gB / sfv[g]) : (J * sfv[g] + s * gB);
+        } else if (is_log) {
+            J = J / s;
+        }
+    } else if (kind == SBM_ROW_SF_PRIOR) {
+        const int g = a.row_aux[r];
+        J = sfg[g * a.n_proj + c] / sfv[g];
+    } else if (kind == SBM_ROW_PARAM_PRIOR && (a.flags & SBM_FLAG_PRIOR_JAC_UNIT)) {
+        J = (a.row_aux[r] == c) ? 1.0 : 0.0;
+    }
+    return J;
+}
+
+__device__ __forceinline__ double sbm_warp_sum(double v)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- TMA bulk copies (1-D) and mbarriers ----------------------------------------------------------------------
+__device__ __forceinline__ unsigned sbm_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void sbm_mbar_init(unsigned long long* mb, const int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(sbm_smem_addr(mb)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sbm_mbar_expect_tx(unsigned long long* mb, const unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sbm_smem_addr(mb)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sbm_mbar_wait(unsigned long long* mb, const unsigned parity)
+{
+    const unsigned addr = sbm_smem_addr(mb);
+    unsigned ok = 0, spins = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 28)) __trap();          // a lost copy must not hang the GPU
+    }
+}
+__device__ __forceinline__ void sbm_tma_load(void* dst_smem, const void* src_gmem, const unsigned bytes, unsigned long long* mb)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(sbm_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(sbm_smem_addr(mb)) : "memory");
+}
+__device__ __forceinline__ void sbm_tma_store(void* dst_gmem, const void* src_smem, const unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst_gmem), "r"(sbm_smem_addr(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// =================================================================================================================
+// warp-per-set kernel.  Dynamic shared memory per warp (doubles): 2 * tile | sims[n_rows] | resid[n_rows] |
+// sf[G] | p1[G] | p2[G] | sfgrad[G * n_proj] ; then 2 mbarriers per warp at the end of the CTA's block.
+// =================================================================================================================
+template <bool HAS_JAC>
+__global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a, const int tile_doubles, const int warp_doubles)
+{
+    extern __shared__ __align__(16) double dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double* base = dyn + (size_t)warp * warp_doubles;
+    double* tile0 = base;
+    double* s_sims = base + 2 * tile_doubles;
+    double* s_res = s_sims + a.n_rows;
+    double* s_sf = s_res + a.n_rows;
+    double* s_p1 = s_sf + a.n_groups;
+    double* s_p2 = s_p1 + a.n_groups;
+    double* s_sfg = s_p2 + a.n_groups;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(dyn + (size_t)nwarps * warp_doubles) + 2 * warp;
+    const bool is_log = (a.loss_kind == SBM_LOSS_LOG);
+    const int R = a.n_rows, P = a.n_proj, G = a.n_groups;
+    const unsigned tile_bytes = (unsigned)(R * P) * 8u;
+    const long long stride = (long long)gridDim.x * nwarps;
+    long long b = (long long)blockIdx.x * nwarps + warp;
+
+    if (HAS_JAC) {
+        if (lane == 0) { sbm_mbar_init(mbar, 1); sbm_mbar_init(mbar + 1, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && b < a.B) {
+            sbm_mbar_expect_tx(mbar, tile_bytes);
+            sbm_tma_load(tile0, a.jac + b * (long long)R * P, tile_bytes, mbar);
+        }
+    }
+    unsigned it = 0;
+    for (; b < a.B; b += stride, ++it) {
+        const int buf = it & 1;
+        double* tile = tile0 + buf * tile_doubles;
+        double* sims = a.sims + b * R;
+        // ---- next set's Jacobian into the other buffer (its previous contents have been read by the bulk store) ----
+        if (HAS_JAC && lane == 0 && b + stride < a.B) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            sbm_mbar_expect_tx(mbar + (buf ^ 1), tile_bytes);
+            sbm_tma_load(tile0 + (buf ^ 1) * tile_doubles, a.jac + (b + stride) * (long long)R * P, tile_bytes, mbar + (buf ^ 1));
+        }
+        // ---- prior rows carry theta itself (base_project.py:427-437); NaN scan (squared_loss_function.py:28-32) ----
+        int bad = 0;
+        for (int r = lane; r < R; r += 32) {
+            const int kind = a.row_kind[r];
+            double s = sims[r];
+            if (kind == SBM_ROW_PARAM_PRIOR) { s = a.theta[b * a.theta_sb + a.row_aux[r] * a.theta_sp]; sims[r] = s; }
+            if (kind != SBM_ROW_SF_PRIOR && s != s) bad = 1;
+            s_sims[r] = s;
+        }
+        const bool allbad = __any_sync(0xffffffffu, bad) != 0;
+        __syncwarp();
+        // ---- optimal scale factor per group ----
+        double* sums = a.sums ? a.sums + b * (long long)G * (3 + 2 * P) : nullptr;
+        for (int g = 0; g < G; ++g) {
+            double p1 = 0.0, p2 = 0.0, p3 = 0.0;
+            if (a.phase != SBM_LOSS_PHASE_FINISH) {
+                for (int q = a.grp_off[g] + lane; q < a.grp_off[g + 1]; q += 32) {
+                    const int r = a.grp_rows[q];
+                    sbm_sf_terms(is_log, s_sims[r], a.data[r], a.sigma[r], p1, p2, p3);
+                }
+                p1 = sbm_warp_sum(p1);
+                p2 = sbm_warp_sum(p2);
+                if (is_log) p3 = sbm_warp_sum(p3);
+                if (a.phase == SBM_LOSS_PHASE_SUMS && lane == 0) {
+                    sums[g * (3 + 2 * P) + 0] = p1; sums[g * (3 + 2 * P) + 1] = p2; sums[g * (3 + 2 * P) + 2] = p3;
+                }
+            } else {
+                p1 = sums[g * (3 + 2 * P) + 0]; p2 = sums[g * (3 + 2 * P) + 1]; p3 = sums[g * (3 + 2 * P) + 2];
+            }
+            if (lane == 0) {
+                const double Bv = sbm_sf_value(is_log, p1, p2, p3);
+                s_sf[g] = Bv; s_p1[g] = p1; s_p2[g] = p2;
+                if (a.phase != SBM_LOSS_PHASE_SUMS) a.sf[b * G + g] = Bv;
+            }
+        }
+        __syncwarp();
+        if (HAS_JAC) {
+            sbm_mbar_wait(mbar + buf, (it >> 1) & 1u);
+            // ---- gradient of the scale factors w.r.t. theta (needs the unscaled model Jacobian) ----
+            for (int g = 0; g < G; ++g) {
+                for (int c = lane; c < P; c += 32) {
+                    double j1 = 0.0, j2 = 0.0;
+                    if (a.phase != SBM_LOSS_PHASE_FINISH) {
+                        for (int q = a.grp_off[g]; q < a.grp_off[g + 1]; ++q) {
+                            const int r = a.grp_rows[q];
+                            sbm_sfgrad_terms(is_log, tile[r * P + c], s_sims[r], a.data[r], a.sigma[r], j1, j2);
+                        }
+                        if (a.phase == SBM_LOSS_PHASE_SUMS) {
+                            sums[g * (3 + 2 * P) + 3 + c] = j1; sums[g * (3 + 2 * P) + 3 + P + c] = j2;
+                        }
+                    } else {
+                        j1 = sums[g * (3 + 2 * P) + 3 + c]; j2 = sums[g * (3 + 2 * P) + 3 + P + c];
+                    }
+                    if (a.phase != SBM_LOSS_PHASE_SUMS) {
+                        const double gB = sbm_sfgrad_value(is_log, s_sf[g], s_p1[g], s_p2[g], j1, j2);
+                        s_sfg[g * P + c] = gB;
+                        a.sfgrad[(b * G + g) * (long long)P + c] = gB;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (a.phase == SBM_LOSS_PHASE_SUMS) continue;       // (the tile is untouched: nothing to store back)
+        // ---- residuals (squared_loss_function.py:34-40, log_squared_loss_function.py:23-64) and SSR ----
+        double acc = 0.0;
+        for (int r = lane; r < R; r += 32) {
+            const int kind = a.row_kind[r];
+            double s = s_sims[r];
+            double res;
+            if (kind == SBM_ROW_MEASUREMENT) {
+                const int g = a.row_group[r];
+                if (g >= 0) s *= s_sf[g];
+                res = is_log ? (log(s) - log(a.data[r])) / a.sigma[r] : (s - a.data[r]) / a.sigma[r];
+            } else {
+                if (kind == SBM_ROW_SF_PRIOR) { s = log(s_sf[a.row_aux[r]]); sims[r] = s; s_sims[r] = s; }
+                res = (s - a.data[r]) / a.sigma[r];
+            }
+            if (allbad) res = __longlong_as_double(SBM_INF_BITS);
+            a.resid[b * R + r] = res;
+            s_res[r] = res;
+            acc += res * res;
+        }
+        acc = sbm_warp_sum(acc);
+        if (lane == 0) a.ssr[b] = 0.5 * acc;               // base_project.py:807-827
+        __syncwarp();
+        // ---- scaled Jacobian  B*J + sim*dB  and  J^T r  (base_project.py:805), in the tile; bulk store back ----
+        if (HAS_JAC) {
+            for (int c = lane; c < P; c += 32) {
+                double gacc = 0.0;
+                for (int r = 0; r < R; ++r) {
+                    double J = sbm_scaled_entry(a, is_log, r, c, a.row_kind[r], tile[r * P + c], s_sims[r], s_sf, s_sfg);
+                    if (allbad) J = __longlong_as_double(SBM_INF_BITS);
+                    tile[r * P + c] = J;
+                    gacc += J * s_res[r];
+                }
+                if (a.grad) a.grad[b * P + c] = gacc;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) sbm_tma_store(a.jac + b * (long long)R * P, tile, tile_bytes);
+        }
+    }
+    if (HAS_JAC && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// =================================================================================================================
+// CTA-per-set kernel: any shape, J stays in global memory
+// =================================================================================================================
+__device__ __forceinline__ double sbm_block_sum(double v, double* red)
+{
+    v = sbm_warp_sum(v);
     const int w = threadIdx.x >> 5;
     __syncthreads();                       // protect red[] from the previous use
     if ((threadIdx.x & 31) == 0) red[w] = v;
@@ -51,7 +329,7 @@ __device__ __forceinline__ double sbm_block_sum(double v, double* red)
 
 __global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_kernel(const SbmLossArgs a)
 {
-    extern __shared__ double dyn[];        // [3][n_groups]: sf, aux1 (sde | inv), aux2 (sds)
+    extern __shared__ double dyn[];        // [3][n_groups]: sf, p1, p2
     __shared__ double red[SBM_LOSS_THREADS / 32];
     __shared__ int s_bad;
     double* s_sf = dyn;
@@ -59,11 +337,14 @@ __global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_kernel(const SbmLos
     double* s_a2 = dyn + 2 * a.n_groups;
     const int tid = threadIdx.x;
     const bool is_log = (a.loss_kind == SBM_LOSS_LOG);
+    const int P = a.n_proj, G = a.n_groups;
 
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
         double* sims = a.sims + b * a.n_rows;
         double* resid = a.resid + b * a.n_rows;
-        double* jac = a.jac ? a.jac + b * (long long)a.n_rows * a.n_proj : nullptr;
+        double* jac = a.jac ? a.jac + b * (long long)a.n_rows * P : nullptr;
+        double* sums = a.sums ? a.sums + b * (long long)G * (3 + 2 * P) : nullptr;
+        double* sfgrad = a.sfgrad ? a.sfgrad + b * (long long)G * P : nullptr;
         if (tid == 0) s_bad = 0;
         __syncthreads();
 
@@ -78,71 +359,53 @@ __global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_kernel(const SbmLos
         __syncthreads();
 
         // ---- optimal scale factor per group
-        for (int g = 0; g < a.n_groups; ++g) {
+        for (int g = 0; g < G; ++g) {
             double p1 = 0.0, p2 = 0.0, p3 = 0.0;
-            for (int q = a.grp_off[g] + tid; q < a.grp_off[g + 1]; q += SBM_LOSS_THREADS) {
-                const int r = a.grp_rows[q];
-                const double s = sims[r], d = a.data[r], sg = a.sigma[r];
-                if (!is_log) {
-                    // linear_scale_factor.py:27-31   B = sum(s d / sigma^2) / sum(s^2 / sigma^2)
-                    const double w = 1.0 / (sg * sg);
-                    p1 += s * d * w;
-                    p2 += s * s * w;
-                } else {
-                    // log_scale_factor.py:17-27 with sigma rescaled by the data (s_i = sigma_i / d_i)
-                    const double sr = sg / d;
-                    const double w = 1.0 / (sr * sr);
-                    p1 += w;
-                    p2 += log(d) * w;
-                    p3 += log(s) * w;
+            if (a.phase != SBM_LOSS_PHASE_FINISH) {
+                for (int q = a.grp_off[g] + tid; q < a.grp_off[g + 1]; q += SBM_LOSS_THREADS) {
+                    const int r = a.grp_rows[q];
+                    sbm_sf_terms(is_log, sims[r], a.data[r], a.sigma[r], p1, p2, p3);
                 }
+                p1 = sbm_block_sum(p1, red);
+                p2 = sbm_block_sum(p2, red);
+                if (is_log) p3 = sbm_block_sum(p3, red);
+                if (a.phase == SBM_LOSS_PHASE_SUMS && tid == 0) {
+                    sums[g * (3 + 2 * P) + 0] = p1; sums[g * (3 + 2 * P) + 1] = p2; sums[g * (3 + 2 * P) + 2] = p3;
+                }
+            } else {
+                p1 = sums[g * (3 + 2 * P) + 0]; p2 = sums[g * (3 + 2 * P) + 1]; p3 = sums[g * (3 + 2 * P) + 2];
             }
-            p1 = sbm_block_sum(p1, red);
-            p2 = sbm_block_sum(p2, red);
-            if (is_log) p3 = sbm_block_sum(p3, red);
             if (tid == 0) {
-                double B;
-                if (!is_log) { B = p1 / p2; s_a1[g] = p1; s_a2[g] = p2; }
-                else { B = exp(p2 / p1) * exp(-p3 / p1); s_a1[g] = p1; s_a2[g] = 0.0; }
-                s_sf[g] = B;
-                a.sf[b * a.n_groups + g] = B;
+                const double Bv = sbm_sf_value(is_log, p1, p2, p3);
+                s_sf[g] = Bv; s_a1[g] = p1; s_a2[g] = p2;
+                if (a.phase != SBM_LOSS_PHASE_SUMS) a.sf[b * G + g] = Bv;
             }
             __syncthreads();
         }
 
         // ---- gradient of the scale factors w.r.t. theta (needs the unscaled model Jacobian)
         if (jac) {
-            for (int g = 0; g < a.n_groups; ++g) {
-                double* out = a.sfgrad + (b * a.n_groups + g) * (long long)a.n_proj;
-                for (int c = tid; c < a.n_proj; c += SBM_LOSS_THREADS) {
+            for (int g = 0; g < G; ++g) {
+                for (int c = tid; c < P; c += SBM_LOSS_THREADS) {
                     double j1 = 0.0, j2 = 0.0;
-                    for (int q = a.grp_off[g]; q < a.grp_off[g + 1]; ++q) {
-                        const int r = a.grp_rows[q];
-                        const double J = jac[(long long)r * a.n_proj + c];
-                        const double s = sims[r], d = a.data[r], sg = a.sigma[r];
-                        if (!is_log) {
-                            const double w = 1.0 / (sg * sg);
-                            j1 += J * d * w;           // jac_dot_exp
-                            j2 += J * s * w;           // jac_dot_sim
-                        } else {
-                            const double sr = sg / d;
-                            j1 += J / (s * sr * sr);
+                    if (a.phase != SBM_LOSS_PHASE_FINISH) {
+                        for (int q = a.grp_off[g]; q < a.grp_off[g + 1]; ++q) {
+                            const int r = a.grp_rows[q];
+                            sbm_sfgrad_terms(is_log, jac[(long long)r * P + c], sims[r], a.data[r], a.sigma[r], j1, j2);
                         }
-                    }
-                    double gB;
-                    if (!is_log) {
-                        // linear_scale_factor.py:33-42 (note the factor 2)
-                        const double sde = s_a1[g], sds = s_a2[g];
-                        gB = j1 / sds - 2.0 * sde * j2 / (sds * sds);
+                        if (a.phase == SBM_LOSS_PHASE_SUMS) {
+                            sums[g * (3 + 2 * P) + 3 + c] = j1; sums[g * (3 + 2 * P) + 3 + P + c] = j2;
+                        }
                     } else {
-                        // log_scale_factor.py:29-36
-                        gB = s_sf[g] * (-1.0 / s_a1[g]) * j1;
+                        j1 = sums[g * (3 + 2 * P) + 3 + c]; j2 = sums[g * (3 + 2 * P) + 3 + P + c];
                     }
-                    out[c] = gB;
+                    if (a.phase != SBM_LOSS_PHASE_SUMS)
+                        sfgrad[g * (long long)P + c] = sbm_sfgrad_value(is_log, s_sf[g], s_a1[g], s_a2[g], j1, j2);
                 }
             }
             __syncthreads();
         }
+        if (a.phase == SBM_LOSS_PHASE_SUMS) continue;
 
         // ---- residuals (squared_loss_function.py:34-40, log_squared_loss_function.py:23-64)
         const bool allbad = (s_bad != 0);
@@ -159,7 +422,7 @@ __global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_kernel(const SbmLos
                 if (kind == SBM_ROW_SF_PRIOR) { s = log(s_sf[a.row_aux[r]]); sims[r] = s; }   // abstract_loss_function.py:93-105
                 res = (s - a.data[r]) / a.sigma[r];
             }
-            if (allbad) res = __longlong_as_double(0x7ff0000000000000ll);
+            if (allbad) res = __longlong_as_double(SBM_INF_BITS);
             resid[r] = res;
             acc += res * res;
         }
@@ -169,42 +432,129 @@ __global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_kernel(const SbmLos
 
         // ---- scaled Jacobian  B*J + sim*dB  (squared_loss_function.py:58-80) and  J^T r  (base_project.py:805)
         if (jac) {
-            for (int c = tid; c < a.n_proj; c += SBM_LOSS_THREADS) {
+            for (int c = tid; c < P; c += SBM_LOSS_THREADS) {
                 double gacc = 0.0;
                 for (int r = 0; r < a.n_rows; ++r) {
-                    const int kind = a.row_kind[r];
-                    double J = jac[(long long)r * a.n_proj + c];
-                    if (kind == SBM_ROW_MEASUREMENT) {
-                        const int g = a.row_group[r];
-                        const double s = sims[r];
-                        if (g >= 0) {
-                            const double gB = a.sfgrad[(b * a.n_groups + g) * (long long)a.n_proj + c];
-                            J = is_log ? (J / s + gB / s_sf[g]) : (J * s_sf[g] + s * gB);
-                        } else if (is_log) {
-                            J = J / s;
-                        }
-                    } else if (kind == SBM_ROW_SF_PRIOR) {
-                        const int g = a.row_aux[r];     // abstract_loss_function.py:107-120, linear_scale_factor.py:44-53
-                        J = a.sfgrad[(b * a.n_groups + g) * (long long)a.n_proj + c] / s_sf[g];
-                    } else if (kind == SBM_ROW_PARAM_PRIOR && (a.flags & SBM_FLAG_PRIOR_JAC_UNIT)) {
-                        J = (a.row_aux[r] == c) ? 1.0 : 0.0;
-                    }
-                    if (allbad) J = __longlong_as_double(0x7ff0000000000000ll);
-                    jac[(long long)r * a.n_proj + c] = J;
+                    double J = sbm_scaled_entry(a, is_log, r, c, a.row_kind[r], jac[(long long)r * P + c], sims[r], s_sf, sfgrad);
+                    if (allbad) J = __longlong_as_double(SBM_INF_BITS);
+                    jac[(long long)r * P + c] = J;
                     gacc += J * resid[r];
                 }
-                if (a.grad) a.grad[b * a.n_proj + c] = gacc;
+                if (a.grad) a.grad[b * P + c] = gacc;
             }
         }
         __syncthreads();
     }
 }
 
-static inline void sbm_launch_loss(const SbmLossArgs& a, cudaStream_t st)
+// tile kernel launch shape: warps per CTA so that two CTAs share an SM's shared memory
+static inline bool sbm_loss_tile_shape(const SbmLossArgs& a, int& warps, int& tile_doubles, int& warp_doubles, size_t& smem)
 {
+    const long long tile = a.jac ? (long long)a.n_rows * a.n_proj : 0;
+    if (a.jac && ((tile & 1) || tile * 8 > 40 * 1024)) return false;      // bulk copies move multiples of 16 bytes
+    if ((reinterpret_cast<size_t>(a.jac) & 15) != 0) return false;
+    tile_doubles = (int)tile;
+    long long wd = 2 * tile + 2ll * a.n_rows + 3ll * a.n_groups + (long long)a.n_groups * a.n_proj;
+    wd += (wd & 1);                                                      // keep every warp's block 16-byte aligned
+    if (wd * 8 > 100 * 1024) return false;
+    warp_doubles = (int)wd;
+    warps = (int)((108 * 1024) / (wd * 8 + 16));
+    if (warps > 8) warps = 8;
+    if (warps < 1) return false;
+    smem = (size_t)warps * ((size_t)wd * 8 + 16);
+    return true;
+}
+
+static inline cudaError_t sbm_launch_loss(const SbmLossArgs& a, cudaStream_t st, int sm_count)
+{
+    int warps = 0, td = 0, wd = 0;
+    size_t smem = 0;
+    static bool attr_set = false;
+    if (!(a.flags & SBM_FLAG_LOSS_GENERIC) && sbm_loss_tile_shape(a, warps, td, wd, smem)) {
+        if (!attr_set) {
+            cudaFuncSetAttribute(sbm_loss_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+            cudaFuncSetAttribute(sbm_loss_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+            attr_set = true;
+        }
+        long long blocks = (a.B + warps - 1) / warps;
+        const long long cap = (long long)(sm_count > 0 ? sm_count : 148) * (a.jac ? 2 : 8);
+        if (blocks > cap) blocks = cap;
+        if (a.jac) sbm_loss_tile_kernel<true><<<(unsigned)blocks, warps * 32, smem, st>>>(a, td, wd);
+        else sbm_loss_tile_kernel<false><<<(unsigned)blocks, warps * 32, smem, st>>>(a, td, wd);
+        return cudaGetLastError();
+    }
     long long blocks = a.B < 1048576 ? a.B : 1048576;
-    size_t smem = (size_t)(3 * (a.n_groups > 0 ? a.n_groups : 1)) * sizeof(double);
-    sbm_loss_kernel<<<(unsigned)blocks, SBM_LOSS_THREADS, smem, st>>>(a);
+    size_t gs = (size_t)(3 * (a.n_groups > 0 ? a.n_groups : 1)) * sizeof(double);
+    sbm_loss_kernel<<<(unsigned)blocks, SBM_LOSS_THREADS, gs, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-set normal equations: out[b] = [ lower triangle of J^T J (row-major, P (P+1) / 2) | J^T r (P) | r^T r ]
+// One warp per set, J rows read coalesced (lane = column), the triangle of a set spread over the lanes.
+// What the Jacobian-block gather of the multi-GPU path ships instead of the full [n_rows x n_proj] blocks
+//  and what an optimiser's normal-equation step consumes.
+// ------------------------------------------------------------------------------------------------
+struct SbmGramArgs {
+    const double* jac;
+    const double* resid;
+    double* out;
+    long long B;
+    int n_rows, n_proj;
+};
+
+__global__ void __launch_bounds__(256) sbm_gram_kernel(const SbmGramArgs a)
+{
+    extern __shared__ double dyn[];        // per warp: one row of J (n_proj) + its residual
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int P = a.n_proj, R = a.n_rows, T = P * (P + 1) / 2, OUT = T + P + 1;
+    double* row = dyn + warp * (P + 1);
+    constexpr int MAXE = 17;               // entries of the triangle per lane: P <= 32 -> T <= 528 = 16.5 * 32
+    for (long long b = (long long)blockIdx.x * nwarps + warp; b < a.B; b += (long long)gridDim.x * nwarps) {
+        const double* J = a.jac + b * (long long)R * P;
+        const double* res = a.resid + b * R;
+        double accT[MAXE], accG = 0.0, accR = 0.0;
+        int ei[MAXE], ej[MAXE];
+#pragma unroll
+        for (int k = 0; k < MAXE; ++k) {
+            accT[k] = 0.0;
+            int e = lane + 32 * k;
+            if (e >= T) e = 0;
+            // (i, j) of the e-th entry of the row-major lower triangle: i = floor((sqrt(8e + 1) - 1) / 2)
+            int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while (i * (i + 1) / 2 > e) --i;
+            while ((i + 1) * (i + 2) / 2 <= e) ++i;
+            ei[k] = i;
+            ej[k] = e - i * (i + 1) / 2;
+        }
+        for (int r = 0; r < R; ++r) {
+            const double rr = res[r];
+            __syncwarp();
+            if (lane < P) row[lane] = J[(long long)r * P + lane];
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < MAXE; ++k)
+                if (lane + 32 * k < T) accT[k] = fma(row[ei[k]], row[ej[k]], accT[k]);
+            if (lane < P) accG = fma(row[lane], rr, accG);
+            if (lane == 0) accR = fma(rr, rr, accR);
+        }
+        double* out = a.out + b * OUT;
+#pragma unroll
+        for (int k = 0; k < MAXE; ++k)
+            if (lane + 32 * k < T) out[lane + 32 * k] = accT[k];
+        if (lane < P) out[T + lane] = accG;
+        if (lane == 0) out[T + P] = accR;
+    }
+}
+
+static inline cudaError_t sbm_launch_gram(const SbmGramArgs& a, cudaStream_t st, int sm_count)
+{
+    const int warps = 8;
+    long long blocks = (a.B + warps - 1) / warps;
+    const long long cap = (long long)(sm_count > 0 ? sm_count : 148) * 8;
+    if (blocks > cap) blocks = cap;
+    sbm_gram_kernel<<<(unsigned)blocks, warps * 32, (size_t)warps * (a.n_proj + 1) * sizeof(double), st>>>(a);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

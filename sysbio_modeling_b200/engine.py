@@ -193,6 +193,60 @@ class DevicePlan(object):
             dp(sims), dp(jac), dp(resid), dp(ssr), dp(sf), dp(sfgrad), dp(grad), ctypes.c_void_p(st)))
 
 
+    def loss_sums_device(self, theta, sims, jac, sums, loss='square', flags=0, stream=None):
+        """First half of the loss epilogue (C ABI ``sbm_loss_sums``): the scale-factor group sums of THIS plan's rows into
+        ``sums`` [B, n_groups, 3 + 2 n_proj]; the experiment shard all-reduces them over the ranks."""
+        import torch
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+
+        def dp(x):
+            return ctypes.c_void_p(x.data_ptr() if x is not None else None)
+        _lib.check(_lib.lib().sbm_loss_sums(
+            self._h, LOSSES[loss], int(flags), theta.shape[0], dp(theta), theta.stride(0), theta.stride(1),
+            dp(sims), dp(jac), dp(sums), ctypes.c_void_p(st)))
+
+    def loss_finish_device(self, theta, sims, jac, sums, resid, ssr, sf, sfgrad, grad, loss='square', flags=0, stream=None):
+        """Second half (C ABI ``sbm_loss_finish``): scale factors from the given (reduced) sums, residuals, SSR, scaled
+        Jacobian and J^T r of this plan's rows."""
+        import torch
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+
+        def dp(x):
+            return ctypes.c_void_p(x.data_ptr() if x is not None else None)
+        _lib.check(_lib.lib().sbm_loss_finish(
+            self._h, LOSSES[loss], int(flags), theta.shape[0], dp(theta), theta.stride(0), theta.stride(1),
+            dp(sims), dp(jac), dp(sums), dp(resid), dp(ssr), dp(sf), dp(sfgrad), dp(grad), ctypes.c_void_p(st)))
+
+
+def normal_equations_device(jac, resid, out=None, stream=None):
+    """Per-set normal equations on device tensors (C ABI ``sbm_normal_equations``): jac [B, n_rows, n_proj], resid
+    [B, n_rows] -> out [B, n_proj (n_proj + 1) / 2 + n_proj + 1] = lower triangle of J^T J (row-major) | J^T r | r^T r."""
+    import torch
+    B, R, P = jac.shape
+    n = P * (P + 1) // 2 + P + 1
+    if out is None:
+        out = torch.empty((B, n), dtype=torch.float64, device=jac.device)
+    if not (jac.is_contiguous() and resid.is_contiguous() and out.is_contiguous()):
+        raise ValueError('normal_equations_device needs contiguous tensors')
+    st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    vp = ctypes.c_void_p
+    _lib.check(_lib.lib().sbm_normal_equations(B, R, P, vp(jac.data_ptr()), vp(resid.data_ptr()), vp(out.data_ptr()), vp(st)))
+    return out
+
+
+def unpack_normal_equations(packed, n_proj):
+    """(J^T J [B, P, P] symmetric, J^T r [B, P], r^T r [B]) from the packed rows of ``normal_equations_device``."""
+    import torch
+    P = n_proj
+    T = P * (P + 1) // 2
+    B = packed.shape[0]
+    A = torch.zeros((B, P, P), dtype=packed.dtype, device=packed.device)
+    ii, jj = torch.tril_indices(P, P, device=packed.device)
+    A[:, ii, jj] = packed[:, :T]
+    A[:, jj, ii] = packed[:, :T]
+    return A, packed[:, T:T + P], packed[:, T + P]
+
+
 def lm_step_device(jac, resid, lam, dscale=None, delta=None, pred=None, gmax=None, info=None, stream=None):
     """Batched Levenberg-Marquardt step on device tensors (C ABI ``sbm_lm_step``, csrc/sbm_lm.cuh):
     ``(J^T J + lam D) delta = -J^T r`` for every parameter set, ``D = max(dscale, diag(J^T J))`` written back to

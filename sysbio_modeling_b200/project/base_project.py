@@ -498,7 +498,8 @@ class Project(object):
     # evaluation
     # ------------------------------------------------------------------------------------------
     def _flags(self):
-        return _lib.SBM_FLAG_PRIOR_JAC_UNIT if self.prior_jacobian_unit else 0
+        return (_lib.SBM_FLAG_PRIOR_JAC_UNIT if self.prior_jacobian_unit else 0) | \
+            (_lib.SBM_FLAG_LOSS_GENERIC if getattr(self, 'loss_generic_kernel', False) else 0)
 
     def _loss_name(self):
         # 'normalized' is folded into the plan's sigma, the kernel then runs the square loss

@@ -830,6 +830,9 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
 
     # --- row i of J*w for C columns at once, J read from shared memory ([entry][lane]); used by the
     #     CTA-transposed kernel (kernels/sbm_dp5_ct.cuh), where `i` is a constant after unrolling
+    L.append('#ifndef SBM_JLOAD')
+    L.append('#define SBM_JLOAD(q) Jp[(q) * 32]')
+    L.append('#endif')
     L.append('template <int C>')
     L.append('__device__ __forceinline__ void sbm_jrow(const int i, const double* __restrict__ Jp,')
     L.append('        const double (&w)[C][SBM_N], double (&acc)[C])')
@@ -838,7 +841,7 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
         ent = [(q, k) for q, (ii, k) in enumerate(jkeys) if ii == i]
         L.append('    %sif (i == %d) {' % ('else ' if i else '', i))
         for q, k in ent:
-            L.append('        const double j%d = Jp[%d * 32];' % (q, q))
+            L.append('        const double j%d = SBM_JLOAD(%d);' % (q, q))
         if ent:
             expr = 'acc[c]'
             for q, k in ent:

@@ -1,0 +1,105 @@
+"""GPU tests of the loss epilogue kernels (csrc/sbm_epilogue.cuh): the warp-per-set kernel with the TMA-staged Jacobian
+tile against the CTA-per-set kernel (same arithmetic, different reduction order), the two-phase form (group sums ->
+finish) the experiment shard uses against the fused call, and the per-set normal equations against numpy."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def c4_eval():
+    import torch
+    from tools import workloads as wl
+    proj, _ = wl.c4_project(1e-8)
+    sm, nominal, y0 = wl.nominal_of('mapk_kholodenko')
+    theta = torch.from_numpy(wl.make_thetas(nominal, 777, 4, 0.25)).cuda()
+    return proj, theta
+
+
+def _clone(o):
+    return {k: v.clone() for k, v in o.items()}
+
+
+def test_tile_kernel_matches_generic_kernel(c4_eval):
+    import torch
+    proj, theta = c4_eval
+    a = _clone(proj.evaluate_device(theta, True))
+    proj.loss_generic_kernel = True
+    try:
+        b = _clone(proj.evaluate_device(theta, True))
+    finally:
+        proj.loss_generic_kernel = False
+    torch.cuda.synchronize()
+    assert torch.isfinite(a['jac']).all()
+    for k in ('resid', 'ssr', 'sf', 'sfgrad', 'jac', 'grad'):
+        scale = b[k].abs().max().item()
+        assert torch.allclose(a[k], b[k], rtol=1e-12, atol=1e-13 * scale), (k, (a[k] - b[k]).abs().max().item())
+    # residual-only path (no Jacobian tile)
+    ar = _clone(proj.evaluate_device(theta, False))
+    proj.loss_generic_kernel = True
+    try:
+        br = _clone(proj.evaluate_device(theta, False))
+    finally:
+        proj.loss_generic_kernel = False
+    for k in ('resid', 'ssr', 'sf'):
+        assert torch.allclose(ar[k], br[k], rtol=1e-12, atol=0), k
+
+
+@pytest.mark.parametrize('generic', [False, True])
+def test_two_phase_loss_equals_fused(c4_eval, generic):
+    """sums -> finish == fused, and summing the sums of two row subsets (what the all-reduce of the experiment shard
+    does) gives the sums of the whole."""
+    import torch
+    from sysbio_modeling_b200 import _lib
+    proj, theta = c4_eval
+    plan, t = proj.device_plan, proj.plan_tables
+    flags = _lib.SBM_FLAG_LOSS_GENERIC if generic else 0
+    B, R, P, G = theta.shape[0], t.n_rows, t.n_proj, t.n_groups
+    ref = {}
+    proj.loss_generic_kernel = generic
+    try:
+        ref = _clone(proj.evaluate_device(theta, True))
+    finally:
+        proj.loss_generic_kernel = False
+    o = {}
+    sims = torch.zeros((B, R), dtype=torch.float64, device='cuda')
+    jac = torch.empty((B, R, P), dtype=torch.float64, device='cuda')
+    status = torch.zeros((B, t.E), dtype=torch.int32, device='cuda')
+    counters = torch.zeros(8, dtype=torch.int64, device='cuda')
+    plan.solve_device(theta, proj._opts('dp5'), sims, jac, status, counters)
+    sums = torch.zeros((B, G, 3 + 2 * P), dtype=torch.float64, device='cuda')
+    plan.loss_sums_device(theta, sims, jac, sums, flags=flags)
+    resid = torch.empty((B, R), dtype=torch.float64, device='cuda')
+    ssr = torch.empty((B,), dtype=torch.float64, device='cuda')
+    sf = torch.empty((B, G), dtype=torch.float64, device='cuda')
+    sfgrad = torch.empty((B, G, P), dtype=torch.float64, device='cuda')
+    grad = torch.empty((B, P), dtype=torch.float64, device='cuda')
+    plan.loss_finish_device(theta, sims, jac, sums, resid, ssr, sf, sfgrad, grad, flags=flags)
+    torch.cuda.synchronize()
+    for k, v in (('resid', resid), ('ssr', ssr), ('sf', sf), ('sfgrad', sfgrad), ('jac', jac), ('grad', grad)):
+        assert torch.equal(v, ref[k]), (k, (v - ref[k]).abs().max().item())
+
+
+def test_normal_equations(c4_eval):
+    import torch
+    from sysbio_modeling_b200 import engine
+    proj, theta = c4_eval
+    o = proj.evaluate_device(theta, True)
+    packed = engine.normal_equations_device(o['jac'], o['resid'])
+    A, g, rr = engine.unpack_normal_equations(packed, 22)
+    torch.cuda.synchronize()
+    J, r = o['jac'].cpu().numpy(), o['resid'].cpu().numpy()
+    A0 = np.einsum('bri,brj->bij', J, J)
+    g0 = np.einsum('bri,br->bi', J, r)
+    assert np.allclose(A.cpu().numpy(), A0, rtol=1e-12, atol=1e-12 * np.abs(A0).max())
+    assert np.allclose(g.cpu().numpy(), g0, rtol=1e-12, atol=1e-12 * np.abs(g0).max())
+    assert np.allclose(g.cpu().numpy(), o['grad'].cpu().numpy(), rtol=1e-11, atol=1e-12 * np.abs(g0).max())
+    assert np.allclose(rr.cpu().numpy(), 2 * o['ssr'].cpu().numpy(), rtol=1e-12)
+    # odd shapes: 1 column, 32 columns, rows not a multiple of anything
+    for R, P in ((5, 1), (7, 32), (33, 13)):
+        J = torch.randn((50, R, P), dtype=torch.float64, device='cuda')
+        r = torch.randn((50, R), dtype=torch.float64, device='cuda')
+        A, g, rr = engine.unpack_normal_equations(engine.normal_equations_device(J, r), P)
+        assert torch.allclose(A, torch.einsum('bri,brj->bij', J, J), rtol=1e-12, atol=1e-12)
+        assert torch.allclose(g, torch.einsum('bri,br->bi', J, r), rtol=1e-12, atol=1e-12)
