@@ -101,12 +101,11 @@ __device__ __forceinline__ double sbm_sfgrad_value(const bool is_log, const doub
 
 // scaled Jacobian entry (squared_loss_function.py:58-80, log_squared_loss_function.py:66-98; prior rows:
 // abstract_loss_function.py:107-120, linear_scale_factor.py:44-53, base_project.py:519-530)
-__device__ __forceinline__ double sbm_scaled_entry(const SbmLossArgs& a, const bool is_log, const int r, const int c,
-                                                   const int kind, double J, const double s,
+__device__ __forceinline__ double sbm_scaled_entry(const SbmLossArgs& a, const bool is_log, const int c,
+                                                   const int kind, const int g, const int aux, double J, const double s,
                                                    const double* __restrict__ sfv, const double* __restrict__ sfg)
 {
     if (kind == SBM_ROW_MEASUREMENT) {
-        const int g = a.row_group[r];
         if (g >= 0) {
             const double gB = sfg[g * a.n_proj + c];
             J = is_log ? (J / s + gB / sfv[g]) : (J * sfv[g] + s * gB);
@@ -114,10 +113,9 @@ __device__ __forceinline__ double sbm_scaled_entry(const SbmLossArgs& a, const b
             J = J / s;
         }
     } else if (kind == SBM_ROW_SF_PRIOR) {
-        const int g = a.row_aux[r];
-        J = sfg[g * a.n_proj + c] / sfv[g];
+        J = sfg[aux * a.n_proj + c] / sfv[aux];
     } else if (kind == SBM_ROW_PARAM_PRIOR && (a.flags & SBM_FLAG_PRIOR_JAC_UNIT)) {
-        J = (a.row_aux[r] == c) ? 1.0 : 0.0;
+        J = (aux == c) ? 1.0 : 0.0;
     }
     return J;
 }
@@ -163,8 +161,11 @@ __device__ __forceinline__ void sbm_tma_store(void* dst_gmem, const void* src_sm
 }
 
 // =================================================================================================================
-// warp-per-set kernel.  Dynamic shared memory per warp (doubles): 2 * tile | sims[n_rows] | resid[n_rows] |
-// sf[G] | p1[G] | p2[G] | sfgrad[G * n_proj] ; then 2 mbarriers per warp at the end of the CTA's block.
+// warp-per-set kernel.  Dynamic shared memory per warp (doubles): 2 * tile | sims[n_rows] | resid[n_rows] | w1[n_rows] |
+// w2[n_rows] | meta[n_rows] (ints in double slots) | sf[G] | p1[G] | p2[G] | sfgrad[G * n_proj] ; then 2 mbarriers per
+// warp at the end of the CTA's block.  Everything a row contributes to the column loops (its kind / group, the weights
+// d / sigma^2 and s / sigma^2 of the scale-factor gradient) is formed ONCE per set by the lanes over the rows; the column
+// loops (lane = project column) are then shared-memory loads and FMAs only.
 // =================================================================================================================
 template <bool HAS_JAC>
 __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a, const int tile_doubles, const int warp_doubles)
@@ -175,7 +176,10 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
     double* tile0 = base;
     double* s_sims = base + 2 * tile_doubles;
     double* s_res = s_sims + a.n_rows;
-    double* s_sf = s_res + a.n_rows;
+    double* s_w1 = s_res + a.n_rows;
+    double* s_w2 = s_w1 + a.n_rows;
+    int* s_meta = reinterpret_cast<int*>(s_w2 + a.n_rows);          // kind | (group + 1) << 4 | aux << 16
+    double* s_sf = s_w2 + 2 * a.n_rows;
     double* s_p1 = s_sf + a.n_groups;
     double* s_p2 = s_p1 + a.n_groups;
     double* s_sfg = s_p2 + a.n_groups;
@@ -214,6 +218,13 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
             if (kind == SBM_ROW_PARAM_PRIOR) { s = a.theta[b * a.theta_sb + a.row_aux[r] * a.theta_sp]; sims[r] = s; }
             if (kind != SBM_ROW_SF_PRIOR && s != s) bad = 1;
             s_sims[r] = s;
+            const int g = a.row_group[r];
+            s_meta[r] = kind | ((g + 1) << 4) | (a.row_aux[r] << 16);
+            if (HAS_JAC && kind == SBM_ROW_MEASUREMENT && g >= 0) {
+                const double d = a.data[r], sg = a.sigma[r];
+                if (!is_log) { const double w = 1.0 / (sg * sg); s_w1[r] = d * w; s_w2[r] = s * w; }
+                else { const double sr = sg / d; s_w1[r] = 1.0 / (s * sr * sr); s_w2[r] = 0.0; }
+            }
         }
         const bool allbad = __any_sync(0xffffffffu, bad) != 0;
         __syncwarp();
@@ -249,9 +260,13 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
                 for (int c = lane; c < P; c += 32) {
                     double j1 = 0.0, j2 = 0.0;
                     if (a.phase != SBM_LOSS_PHASE_FINISH) {
-                        for (int q = a.grp_off[g]; q < a.grp_off[g + 1]; ++q) {
-                            const int r = a.grp_rows[q];
-                            sbm_sfgrad_terms(is_log, tile[r * P + c], s_sims[r], a.data[r], a.sigma[r], j1, j2);
+                        // j1 += J d / sigma^2, j2 += J s / sigma^2 (log loss: j1 += J / (s sr^2)); the weights come staged
+                        const int q1 = a.grp_off[g + 1];
+                        for (int q = a.grp_off[g]; q < q1; ++q) {
+                            const int r = __ldg(a.grp_rows + q);
+                            const double J = tile[r * P + c];
+                            j1 = fma(J, s_w1[r], j1);
+                            j2 = fma(J, s_w2[r], j2);
                         }
                         if (a.phase == SBM_LOSS_PHASE_SUMS) {
                             sums[g * (3 + 2 * P) + 3 + c] = j1; sums[g * (3 + 2 * P) + 3 + P + c] = j2;
@@ -272,15 +287,16 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
         // ---- residuals (squared_loss_function.py:34-40, log_squared_loss_function.py:23-64) and SSR ----
         double acc = 0.0;
         for (int r = lane; r < R; r += 32) {
-            const int kind = a.row_kind[r];
+            const int meta = s_meta[r];
+            const int kind = meta & 15;
             double s = s_sims[r];
             double res;
             if (kind == SBM_ROW_MEASUREMENT) {
-                const int g = a.row_group[r];
+                const int g = ((meta >> 4) & 0xfff) - 1;
                 if (g >= 0) s *= s_sf[g];
                 res = is_log ? (log(s) - log(a.data[r])) / a.sigma[r] : (s - a.data[r]) / a.sigma[r];
             } else {
-                if (kind == SBM_ROW_SF_PRIOR) { s = log(s_sf[a.row_aux[r]]); sims[r] = s; s_sims[r] = s; }
+                if (kind == SBM_ROW_SF_PRIOR) { s = log(s_sf[meta >> 16]); sims[r] = s; s_sims[r] = s; }
                 res = (s - a.data[r]) / a.sigma[r];
             }
             if (allbad) res = __longlong_as_double(SBM_INF_BITS);
@@ -296,7 +312,9 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
             for (int c = lane; c < P; c += 32) {
                 double gacc = 0.0;
                 for (int r = 0; r < R; ++r) {
-                    double J = sbm_scaled_entry(a, is_log, r, c, a.row_kind[r], tile[r * P + c], s_sims[r], s_sf, s_sfg);
+                    const int meta = s_meta[r];
+                    double J = sbm_scaled_entry(a, is_log, c, meta & 15, ((meta >> 4) & 0xfff) - 1, meta >> 16, tile[r * P + c],
+                                                s_sims[r], s_sf, s_sfg);
                     if (allbad) J = __longlong_as_double(SBM_INF_BITS);
                     tile[r * P + c] = J;
                     gacc += J * s_res[r];
@@ -435,7 +453,7 @@ __global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_kernel(const SbmLos
             for (int c = tid; c < P; c += SBM_LOSS_THREADS) {
                 double gacc = 0.0;
                 for (int r = 0; r < a.n_rows; ++r) {
-                    double J = sbm_scaled_entry(a, is_log, r, c, a.row_kind[r], jac[(long long)r * P + c], sims[r], s_sf, sfgrad);
+                    double J = sbm_scaled_entry(a, is_log, c, a.row_kind[r], a.row_group[r], a.row_aux[r], jac[(long long)r * P + c], sims[r], s_sf, sfgrad);
                     if (allbad) J = __longlong_as_double(SBM_INF_BITS);
                     jac[(long long)r * P + c] = J;
                     gacc += J * resid[r];
@@ -454,7 +472,7 @@ static inline bool sbm_loss_tile_shape(const SbmLossArgs& a, int& warps, int& ti
     if (a.jac && ((tile & 1) || tile * 8 > 40 * 1024)) return false;      // bulk copies move multiples of 16 bytes
     if ((reinterpret_cast<size_t>(a.jac) & 15) != 0) return false;
     tile_doubles = (int)tile;
-    long long wd = 2 * tile + 2ll * a.n_rows + 3ll * a.n_groups + (long long)a.n_groups * a.n_proj;
+    long long wd = 2 * tile + 5ll * a.n_rows + 3ll * a.n_groups + (long long)a.n_groups * a.n_proj;
     wd += (wd & 1);                                                      // keep every warp's block 16-byte aligned
     if (wd * 8 > 100 * 1024) return false;
     warp_doubles = (int)wd;
