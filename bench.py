@@ -5,12 +5,16 @@ Workload (BASELINE.json configs[3], the one north_star quotes its target on): Kh
 8 states x 22 parameters -> 184 sensitivity-augmented states, one experiment observing MAPK_PP and MKK_PP at
 20 time points, 65,536 parameter sets per GPU (theta = log(nominal) + 0.25 N(0,1)), one step = one
 evaluation of the full scaled Jacobian [40 x 22] + residuals + SSR + J^T r for every parameter set
-(sensitivity-augmented Dormand-Prince solve + loss epilogue).  Tolerances default to the reference's
+(sensitivity-augmented Dormand-Prince solve + loss epilogue) + the per-set normal equations J^T J | J^T r that
+the optimiser consumes (all-gathered over the ranks at N > 1).  Tolerances default to the reference's
 hard-coded rtol = atol = 1e-10 (model/ode_model.py:122-123).
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+    python bench.py --impl reference ...        # the reference's own CPU path on the host cores
+
+After the timed headline region the N = 1 run also times the other BASELINE configs (C2, C3, C5; reduced step count)
+and checks 8 parameter sets of the headline against the CPU oracle (``parity``).
 """
 import argparse
 import json
@@ -29,43 +33,13 @@ import numpy as np   # noqa: E402
 
 METRIC = 'sensitivity_ode_solves_per_sec'
 UNIT = 'solves/s'
-OBS = {'MAPK_PP': 7, 'MKK_PP': 4}
-T_OBS = np.linspace(150.0, 3000.0, 20)
+SURVEY_FLOPS_SENS_RHS_C4 = 1004        # SymPy count_ops of f + sensitivity RHS after CSE
 
 
 # ------------------------------------------------------------------------------------------------
-# workload
-# ------------------------------------------------------------------------------------------------
-def mapk_model_info():
-    from sysbio_modeling_b200 import model_files
-    mod = model_files.module('mapk_kholodenko')
-    from sysbio_modeling_b200.symbolic import symbolic_model_from_file
-    sm = symbolic_model_from_file(model_files.path('mapk_kholodenko'), name='mapk')
-    nominal = np.array([mod.nominal[p] for p in sm.param_order])
-    return sm, nominal, np.array(mod.initial_conditions)
-
-
-def make_thetas(nominal, B, seed):
-    rng = np.random.default_rng(seed)
-    return np.log(nominal)[None, :] + 0.25 * rng.standard_normal((B, len(nominal)))
-
-
-def build_project(tol, data=None, shape=(0, 0, 0)):
-    import sysbio_modeling_b200 as sb
-    from sysbio_modeling_b200 import model_files
-    mod = model_files.module('mapk_kholodenko')
-    om = sb.OdeModel.from_model_file(model_files.path('mapk_kholodenko'), model_name='mapk', group_lanes=shape[0],
-                                     cols_per_lane=shape[1], sens_layout=shape[2])
-    if data is None:
-        data = {k: np.ones_like(T_OBS) for k in OBS}
-    meas = [sb.TimecourseMeasurement(k, data[k], T_OBS, 0.05 * np.abs(data[k]) + 1e-3) for k in OBS]
-    exp = sb.Experiment('MAPK_cascade', meas, initial_conditions=mod.initial_conditions)
-    return sb.Project(om, [exp], {}, {k: ('direct', v) for k, v in OBS.items()}, sf_groups=list(OBS.keys()),
-                      rtol=tol, atol=tol)
-
-
-# ------------------------------------------------------------------------------------------------
-# CPU reference path (oracle port: SciPy LSODA + numba-compiled generated sensitivity RHS)
+# CPU reference path: the reference's UNMODIFIED OdeModel.calc_jacobian (baseline/_ref, see oracle/build_ref.py) -
+# SciPy LSODA rtol = atol = 1e-10 on the 1000-node grid with the numba-compiled generated sensitivity RHS; falls back
+# to the oracle port when the copy is absent
 # ------------------------------------------------------------------------------------------------
 _W = {}
 
@@ -82,44 +56,73 @@ def _cpu_init(tol):
         _W['tp'] = threadpool_limits(1)
     except Exception:
         pass
-    import sbm_oracle
+    from tools import workloads as wl
     from sysbio_modeling_b200.symbolic import make_ode_model
-    sm, nominal, y0 = mapk_model_info()
-    sens = make_ode_model(sm, True)
-    try:
-        import numba
-        sens = numba.jit("void(f8[:], f8, f8[:], f8[:])", nopython=True)(sens)   # ode_model.py:50-51
-        jitted = True
-    except Exception:
-        jitted = False
-    _W.update(dict(oracle=sbm_oracle, sens=sens, sm=sm, y0=y0, tol=tol, jitted=jitted))
-    # warm up (numba compile excluded from timing)
-    _cpu_solve(np.log(nominal))
-    return jitted
+    import build_ref
+    sm, nominal, y0 = wl.nominal_of('mapk_kholodenko')
+    model, sens = make_ode_model(sm, False), make_ode_model(sm, True)
+    RefOdeModel = build_ref.load_reference_odemodel() if tol == 1e-10 else None     # the reference hard-codes 1e-10
+    kind = 'port'
+    if RefOdeModel is not None:
+        try:
+            _W['ref'] = RefOdeModel(model, sens, sm.n_vars, list(sm.param_order), use_jit=True)     # numba, ode_model.py:46-57
+            kind = 'reference'
+        except Exception:
+            _W.pop('ref', None)
+    if 'ref' not in _W:
+        import sbm_oracle
+        try:
+            import numba
+            sens = numba.jit("void(f8[:], f8, f8[:], f8[:])", nopython=True)(sens)   # ode_model.py:50-51
+        except Exception:
+            pass
+        _W.update(dict(oracle=sbm_oracle, sens=sens))
+    _W.update(dict(sm=sm, y0=y0, tol=tol, kind=kind, t_end=float(wl.C4_T[-1])))
+    _cpu_solve(np.log(nominal))          # warm up (numba compile excluded from timing)
+    return kind
 
 
 def _cpu_solve(theta):
     """One reference sensitivity solve: OdeModel.calc_jacobian on the 1000-node grid (base_project.py:510-515)."""
-    O, sm = _W['oracle'], _W['sm']
+    sm = _W['sm']
     p = np.exp(theta)
-    t_sim = np.linspace(0, T_OBS[-1], 1000)
+    t_sim = np.linspace(0, _W['t_end'], 1000)
     y0 = np.concatenate([_W['y0'], np.zeros(sm.n_vars * sm.n_free)])
-    S = O.calc_jacobian(_W['sens'], sm.n_vars, p, t_sim, y0, rtol=_W['tol'], atol=_W['tol'])
+    if 'ref' in _W:
+        S = _W['ref'].calc_jacobian(p, t_sim, y0)
+    else:
+        S = _W['oracle'].calc_jacobian(_W['sens'], sm.n_vars, p, t_sim, y0, rtol=_W['tol'], atol=_W['tol'])
     return float(S[-1, 0])
+
+
+def _cpu_kind(_):
+    return _W.get('kind', 'port')
+
+
+def cpu_pool(tol, cores):
+    import multiprocessing as mp
+    _single_thread_env()
+    ctx = mp.get_context('spawn')
+    return ctx.Pool(cores, initializer=_cpu_init, initargs=(tol,))
 
 
 def cpu_reference_rate(thetas, tol, cores=None):
     """Solves/s of the reference CPU path on `cores` host processes over the given parameter sets."""
-    import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
-    _single_thread_env()
-    ctx = mp.get_context('spawn')
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(tol,)) as pool:
+    with cpu_pool(tol, cores) as pool:
+        kind = pool.map(_cpu_kind, range(cores))[0]
         pool.map(_cpu_solve, [thetas[0]] * cores)           # make sure every worker is warm
         t0 = time.perf_counter()
         pool.map(_cpu_solve, list(thetas), chunksize=max(1, len(thetas) // (cores * 4)))
         dt = time.perf_counter() - t0
-    return len(thetas) / dt, dt, cores
+    return len(thetas) / dt, dt, cores, kind
+
+
+def cpu_sample_text(kind, n, tol, dt, cores):
+    who = ('the reference\'s unmodified model/ode_model.py OdeModel.calc_jacobian (baseline/_ref)' if kind == 'reference'
+           else 'oracle port of OdeModel.calc_jacobian')
+    return ('%d parameter sets of the bench distribution; %s: SciPy odeint (LSODA) rtol=atol=%g on the 1000-node grid, '
+            'numba-compiled generated sensitivity RHS; %.1f s wall on %d processes' % (n, who, tol, dt, cores))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -165,18 +168,26 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------
+def workload_config(args, batch):
+    return {'workload': 'C4 Kholodenko MAPK (8 states, 22 params, 184 augmented states), %d parameter sets per GPU, '
+                        '1 experiment x 2 observables x 20 time points, full scaled Jacobian 40x22 + residuals + SSR + J^T r'
+                        % batch,
+            'param_sets_per_gpu': batch, 'rtol': args.tol, 'atol': args.tol, 'solver': 'dp5',
+            'cache': 'L2 flushed (256 MiB write) between timed steps; Jacobian output (%.0f MB) exceeds L2'
+                     % (batch * 40 * 22 * 8 / 1e6)}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
-    sm, nominal, _ = mapk_model_info()
+    from tools import workloads as wl
+    sm, nominal, _ = wl.nominal_of('mapk_kholodenko')
     cores = os.cpu_count() or 1
     per_step = args.cpu_sample if args.cpu_sample > 0 else 100 * cores      # ~3 s of CPU work per step
-    thetas = make_thetas(nominal, per_step * (args.steps + args.warmup), 4)
-    import multiprocessing as mp
-    _single_thread_env()
-    ctx = mp.get_context('spawn')
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(args.tol,)) as pool:
+    thetas = wl.make_thetas(nominal, per_step * (args.steps + args.warmup), 4, 0.25)
+    with cpu_pool(args.tol, cores) as pool:
+        kind = pool.map(_cpu_kind, range(cores))[0]
         pool.map(_cpu_solve, [thetas[0]] * cores)
         k = 0
         for _ in range(args.warmup):
@@ -191,23 +202,141 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': dict(workload_config(args, args.batch), sample_per_step=per_step),
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                             'sample': '%d parameter sets per step, SciPy odeint (LSODA) rtol=atol=%g on the reference\'s '
-                                       '1000-node grid, numba-compiled generated sensitivity RHS, %d processes'
-                                       % (per_step, args.tol, cores)},
+            'config': workload_config(args, args.batch),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                             'sample': 'each step: ' + cpu_sample_text(kind, per_step, args.tol, dt / args.steps, cores)},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
     return 0
 
 
-def workload_config(args, batch):
-    return {'workload': 'C4 Kholodenko MAPK (8 states, 22 params, 184 augmented states), %d parameter sets per GPU, '
-                        '1 experiment x 2 observables x 20 time points, full scaled Jacobian 40x22 + residuals + SSR + J^T r'
-                        % batch,
-            'param_sets_per_gpu': batch, 'rtol': args.tol, 'atol': args.tol, 'solver': 'dp5',
-            'cache': 'L2 flushed (256 MiB write) between timed steps; Jacobian output (%.0f MB) exceeds L2'
-                     % (batch * 40 * 22 * 8 / 1e6)}
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE configs (N = 1 only, after the headline): solves/s, residual / Jacobian evaluations per second
+# including the loss epilogue, algorithmic flops from the kernels' counters, fraction of the measured FP64 peak
+# ------------------------------------------------------------------------------------------------
+def _time_eval(proj, theta, with_jac, solver, reps):
+    import torch
+    bufs = {}
+    proj.evaluate_device(theta, with_jacobian=with_jac, solver=solver, out=bufs)
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        opts = proj._opts('dp5' if with_jac else solver)
+        bufs['sims'].zero_()
+        bufs['counters'].zero_()
+        ev[0].record()
+        proj.device_plan.solve_device(theta, opts, bufs['sims'], bufs.get('jac') if with_jac else None, bufs['status'],
+                                      bufs['counters'])
+        ev[1].record()
+        proj.device_plan.loss_device(theta, bufs['sims'], bufs.get('jac') if with_jac else None, bufs['resid'], bufs['ssr'],
+                                     bufs['sf'], bufs.get('sfgrad') if with_jac else None,
+                                     bufs.get('grad') if with_jac else None, loss=proj._loss_name(), flags=proj._flags())
+        ev[2].record()
+        torch.cuda.synchronize()
+        t = (ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]))
+        if best is None or sum(t) < sum(best):
+            best = t
+    from sysbio_modeling_b200 import _lib
+    cnt = dict(zip(_lib.COUNTER_NAMES, [int(x) for x in bufs['counters'].cpu().numpy()[:5]]))
+    failed = int((bufs['status'] != 0).sum().item())
+    return best, cnt, failed
+
+
+def extra_configs(peak_tf, quick=False):
+    import torch
+    from tools import workloads as wl
+    dev = torch.device('cuda')
+    out = {}
+    # ---- C3: Robertson, 1,048,576 parameter sets, residuals only, Rosenbrock kernel (rtol 1e-6, atol 1e-10) ----
+    B3 = 131072 if quick else 1048576
+    proj, _ = wl.c3_project()
+    sm, nominal, _ = wl.nominal_of('robertson')
+    th = torch.from_numpy(wl.make_thetas(nominal, B3, 3, 0.5)).to(dev)
+    (ms_i, ms_l), cnt, failed = _time_eval(proj, th, False, 'rodas4', 2)
+    cs = proj._model.compiled.cuda
+    N, s_ = 3, 6
+    f_step = cs.flops_jac_dense + (2.0 / 3.0) * N ** 3 + s_ * (2 * N * N + cs.flops_f) + N * (2 * s_ * (s_ - 1) + 2 * s_ + 5)
+    flops = cnt['steps'] * f_step
+    out['c3'] = {'workload': 'C3 Robertson (3 states), %d parameter sets, 2 observables x 12 log-spaced times, residuals only, '
+                             'RODAS4 rtol 1e-6 atol 1e-10' % B3,
+                 'solves_per_sec': B3 / ms_i * 1e3, 'residual_evals_per_sec': B3 / (ms_i + ms_l) * 1e3,
+                 'sbm_rodas4_plain_ms': ms_i, 'sbm_loss_ms': ms_l, 'loss_share_of_step': ms_l / (ms_i + ms_l),
+                 'steps_per_solve': cnt['steps'] / B3, 'lu_per_solve': cnt['lu'] / B3, 'failed': failed,
+                 'algorithmic_flops': flops, 'flops_per_step': f_step, 'tflops': flops / ms_i / 1e9,
+                 'frac_fp64_peak': flops / ms_i / 1e9 / peak_tf}
+    del th
+    # ---- C5: EGFR-scale network (25 states, 52 parameters), 131,072 walkers, SSR only, plain DP5 ----
+    B5 = 16384 if quick else 131072
+    proj, _ = wl.c5_project()
+    sm, nominal, _ = wl.nominal_of('egfr_signalling')
+    th = torch.from_numpy(wl.make_thetas(nominal, B5, 5, 0.1)).to(dev)
+    (ms_i, ms_l), cnt, failed = _time_eval(proj, th, False, 'dp5', 2)
+    cs = proj._model.compiled.cuda
+    flops = cnt['rhs_evals'] * cs.flops_f + cnt['steps'] * 57 * sm.n_vars
+    out['c5'] = {'workload': 'C5 EGFR-scale network (25 states, 52 parameters), %d walkers, 2 observables x 12 times, SSR only, '
+                             'DP5 rtol = atol = 1e-10' % B5,
+                 'solves_per_sec': B5 / ms_i * 1e3, 'residual_evals_per_sec': B5 / (ms_i + ms_l) * 1e3,
+                 'sbm_dp5_plain_ms': ms_i, 'sbm_loss_ms': ms_l, 'steps_per_solve': cnt['steps'] / B5, 'failed': failed,
+                 'algorithmic_flops': flops, 'flops_per_rhs': cs.flops_f, 'tflops': flops / ms_i / 1e9,
+                 'frac_fp64_peak': flops / ms_i / 1e9 / peak_tf}
+    del th
+    # ---- C2: reversible MM, experiment-local parameters, sensitivities.  (a) the integrator on 4,096 experiments x 64 sets
+    #      through OdeModel (raw dy/dp), (b) the Project objective with 4,096 experiments: one residual / Jacobian evaluation
+    #      = 4,096 solves; the dense scaled Jacobian [65,536 x 16,384] is 8.6 GB per parameter set ----
+    import sysbio_modeling_b200 as sb
+    from sysbio_modeling_b200 import model_files
+    mod = model_files.module('reversible_mm')
+    om = sb.OdeModel.from_model_file(model_files.path('reversible_mm'))
+    nominal = np.array([mod.nominal[k] for k in om.param_order])
+    n2 = 4096 * (8 if quick else 64)
+    P = nominal * np.exp(0.3 * np.random.default_rng(2).standard_normal((n2, 4)))
+    t2 = np.concatenate([[0.0], wl.C2_T])
+    om.calc_jacobian_batch(P[:256], t2, mod.initial_conditions)
+    best = 1e30
+    for _ in range(2):
+        om.calc_jacobian_batch(P, t2, mod.initial_conditions)
+        best = min(best, om.last_solve_ms)
+    cs = om.compiled.cuda
+    cnt = om.last_counters
+    flops = cnt['rhs_evals'] * cs.flops_sens_rhs + cnt['steps'] * 57 * 20
+    out['c2'] = {'workload': 'C2 reversible MM (4 states, 4 params, 20 augmented states), 4,096 experiments x %d parameter sets, '
+                             '16 time points, sensitivities, DP5 rtol = atol = 1e-10' % (n2 // 4096),
+                 'solves_per_sec': n2 / best * 1e3, 'sbm_dp5_ct_ms': best, 'steps_per_solve': cnt['steps'] / n2,
+                 'failed': int((om.last_status != 0).sum()), 'algorithmic_flops': flops, 'flops_per_rhs': cs.flops_sens_rhs,
+                 'tflops': flops / best / 1e9, 'frac_fp64_peak': flops / best / 1e9 / peak_tf}
+    if not quick:
+        E = 4096
+        proj, _ = wl.c2_project(E)
+        th = torch.from_numpy(wl.c2_theta(E, 2)).to(dev)
+        (ms_i, ms_l), cnt, failed = _time_eval(proj, th, True, 'dp5', 1)
+        out['c2'].update({'project_experiments': E, 'project_sets': 2,
+                          'jacobian_evals_per_sec': 2 / (ms_i + ms_l) * 1e3, 'project_solve_ms': ms_i, 'project_loss_ms': ms_l,
+                          'project_jacobian_bytes_per_set': 16 * E * 4 * E * 8, 'project_failed': failed})
+        (ms_i, ms_l), cnt, failed = _time_eval(proj, th, False, 'dp5', 2)
+        out['c2'].update({'residual_evals_per_sec': 2 / (ms_i + ms_l) * 1e3})
+    return out
+
+
+def parity_check(proj, make_oracle, thetas, out_gpu):
+    """8 parameter sets of the timed batch against the CPU oracle (OracleProject: LSODA 1e-10 on the 1000-node grid)."""
+    oracle = make_oracle()
+    worst = {'ssr_rel': 0.0, 'resid_abs': 0.0, 'jac_rel_to_max': 0.0, 'grad_rel_to_max': 0.0, 'sf_rel': 0.0}
+    for b in range(len(thetas)):
+        r0 = oracle.residuals(thetas[b])
+        sf0 = np.array([oracle.sf[g] for g in oracle.sf_groups])
+        J0 = oracle.jacobian(thetas[b])
+        g0 = (J0.T * r0).sum(axis=1)
+        ssr0 = 0.5 * np.sum(r0 ** 2)
+        worst['ssr_rel'] = max(worst['ssr_rel'], abs(out_gpu['ssr'][b] - ssr0) / ssr0)
+        worst['resid_abs'] = max(worst['resid_abs'], float(np.abs(out_gpu['resid'][b] - r0).max()))
+        worst['jac_rel_to_max'] = max(worst['jac_rel_to_max'], float(np.abs(out_gpu['jac'][b] - J0).max() / np.abs(J0).max()))
+        worst['grad_rel_to_max'] = max(worst['grad_rel_to_max'], float(np.abs(out_gpu['grad'][b] - g0).max() / np.abs(g0).max()))
+        worst['sf_rel'] = max(worst['sf_rel'], float(np.abs(out_gpu['sf'][b] / sf0 - 1).max()))
+    ok = worst['ssr_rel'] <= 1e-6 and worst['jac_rel_to_max'] <= 1e-5 and worst['sf_rel'] <= 1e-7
+    return dict(worst, sets=len(thetas), ok=bool(ok),
+                oracle='OracleProject: the reference path restated (LSODA rtol = atol = 1e-10, 1000-node grid); '
+                       'bars: SSR 1e-6 relative (north_star), Jacobian 1e-5 of its largest entry, scale factors 1e-7')
 
 
 def main():
@@ -220,6 +349,8 @@ def main():
     ap.add_argument('--tol', type=float, default=1e-10, help='rtol = atol (reference: 1e-10)')
     ap.add_argument('--cpu-sample', type=int, default=0, help='parameter sets in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the C2 / C3 / C5 measurements after the headline')
+    ap.add_argument('--quick-configs', action='store_true', help='reduced batch sizes for C2 / C3 / C5')
     ap.add_argument('--shape', default='0,0,0', help='group_lanes,cols_per_lane,sens_layout of the sensitivity kernel (0,0,0 = auto; layout 1 = lane-per-column groups, 2 = CTA-transposed)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
@@ -230,7 +361,9 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from sysbio_modeling_b200 import _lib
+    from sysbio_modeling_b200 import _lib, engine
+    from sysbio_modeling_b200.distributed import ShardedProject
+    from tools import workloads as wl
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -240,38 +373,31 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    sm, nominal, y0 = mapk_model_info()
+    sm, nominal, y0 = wl.nominal_of('mapk_kholodenko')
     B = args.batch
-    # synthetic data: the model at the nominal parameters with 5 % noise (seeded)
     shape = tuple(int(x) for x in args.shape.split(','))
-    proj0 = build_project(args.tol, shape=shape)
-    sims = proj0.residuals_batch(np.log(nominal)[None, :])['sims'][0]
-    rng = np.random.default_rng(40)
-    labels = [l[1] for l in proj0._labels]
-    data = {k: np.array([sims[i] for i, l in enumerate(labels) if l == k]) * (1 + 0.05 * rng.standard_normal(20))
-            for k in OBS}
-    proj = build_project(args.tol, data, shape)
+    proj, make_oracle = wl.c4_project(args.tol, shape)      # data: the model at the nominal parameters with 5 % noise (seeded)
     t = proj.plan_tables
     info = proj._model.compiled.info()
     cuda_src = proj._model.compiled.cuda
+    sharded = ShardedProject(proj)
 
-    theta_h = torch.from_numpy(make_thetas(nominal, B, 4 + rank)).pin_memory()
+    # every rank draws the SAME sample of the parameter distribution (weak scaling: fixed work per GPU; different samples
+    # differ by ~1 % in their total step count, which only shows up as skew at the gather)
+    theta_np = wl.make_thetas(nominal, B, 4, 0.25)
+    theta_h = torch.from_numpy(theta_np).pin_memory()
     theta = theta_h.to(dev)
-    bufs = {}
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    n_packed = t.n_proj * (t.n_proj + 1) // 2 + t.n_proj + 1
+    packed_all = torch.empty((B * world, n_packed), dtype=torch.float64, device=dev) if world > 1 else None
 
-    def step():
-        proj.evaluate_device(theta, with_jacobian=True, out=bufs)
-        if world > 1:
-            dist.all_gather_into_tensor(ssr_all, bufs['ssr'])
-
-    ssr_all = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
     for _ in range(max(args.warmup, 1)):
-        step()
+        sharded.step_local_blocks(theta, packed_all)
     torch.cuda.synchronize()
+    bufs = sharded._bufs
 
     # ---- timed region: K steps, device time by CUDA events on the launching (current) stream ----
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     opts_sens = proj._opts('dp5')
     if world > 1:
         dist.barrier()
@@ -280,24 +406,34 @@ def main():
         for k in range(args.steps):
             flush.fill_(float(k))
             ev[k][0].record()
-            # same two launches as proj.evaluate_device, with an event between them
+            # the launches of ShardedProject.step_local_blocks, with events between them
             proj.device_plan.solve_device(theta, opts_sens, bufs['sims'].zero_(), bufs['jac'], bufs['status'],
                                           bufs['counters'].zero_())
             ev[k][1].record()
             proj.device_plan.loss_device(theta, bufs['sims'], bufs['jac'], bufs['resid'], bufs['ssr'], bufs['sf'],
                                          bufs['sfgrad'], bufs['grad'], loss='square')
-            if world > 1:
-                dist.all_gather_into_tensor(ssr_all, bufs['ssr'])
             ev[k][2].record()
+            packed = engine.normal_equations_device(bufs['jac'], bufs['resid'], out=bufs['normal'])
+            if world > 1:
+                dist.all_gather_into_tensor(packed_all, packed)
+            ev[k][3].record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-    ms_step = [ev[k][0].elapsed_time(ev[k][2]) for k in range(args.steps)]
+    ms_step = [ev[k][0].elapsed_time(ev[k][3]) for k in range(args.steps)]
     ms_solve = [ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]
+    ms_loss = [ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)]
+    ms_gather = [ev[k][2].elapsed_time(ev[k][3]) for k in range(args.steps)]
     total_ms = float(sum(ms_step))
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    per_rank = torch.tensor([float(np.mean(ms_solve)), float(np.mean(ms_loss)), float(np.mean(ms_gather))],
+                            dtype=torch.float64, device=dev)
+    per_rank_all = [torch.zeros_like(per_rank) for _ in range(world)]
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_gather(per_rank_all, per_rank)
+    else:
+        per_rank_all = [per_rank]
     total_ms_max = float(tmax.item())
     n_solves_rank = B * t.E
     value = n_solves_rank * world * args.steps / (total_ms_max * 1e-3)
@@ -306,8 +442,10 @@ def main():
     status_bad = int((bufs['status'] != 0).sum().item())
     cnt = dict(zip(_lib.COUNTER_NAMES, [int(x) for x in counters[:5]]))
     n_aug = sm.n_vars * (sm.n_free + 1)
-    flops_launch = cnt['rhs_evals'] * cuda_src.flops_sens_rhs + cnt['steps'] * 57 * n_aug
+    flops_survey = cnt['rhs_evals'] * SURVEY_FLOPS_SENS_RHS_C4 + cnt['steps'] * 57 * n_aug
+    flops_emitter = cnt['rhs_evals'] * cuda_src.flops_sens_rhs + cnt['steps'] * 57 * n_aug
     solve_ms = float(np.mean(ms_solve))
+    gpu_first = {k: bufs[k][:8].cpu().numpy() for k in ('ssr', 'resid', 'jac', 'grad', 'sf')}
 
     # ---- end-to-end through the C-ABI host entry point: pinned host theta in, pinned host results out ----
     jac_h = torch.empty((B, t.n_rows, t.n_proj), dtype=torch.float64).pin_memory()
@@ -339,15 +477,19 @@ def main():
     e2e_value = n_solves_rank * world * n_e2e / float(e2e_t.item())
     h2d = B * t.n_proj * 8
     d2h = B * (t.n_rows * t.n_proj + t.n_rows + 1 + t.n_proj) * 8
-    # spot-check that both paths agree
-    same = bool(torch.allclose(ssr_h.to(dev), bufs['ssr'], rtol=1e-9, atol=0))
+    # both paths agree (the host path evaluates the batch in chunks: same arithmetic per parameter set)
+    same = bool(torch.equal(ssr_h.to(dev), bufs['ssr'])) and bool(torch.equal(jac_h[:64].to(dev), bufs['jac'][:64]))
 
     peak_tf, peak_ms = _lib.fp64_peak()
-    achieved_tf = flops_launch / (solve_ms * 1e-3) / 1e12
+    achieved_tf = flops_survey / (solve_ms * 1e-3) / 1e12
+    achieved_tf_emitter = flops_emitter / (solve_ms * 1e-3) / 1e12
 
     ct = info['sens_layout'] == 2
     kname = 'sbm_dp5_ct' if ct else 'sbm_dp5_sens'
-    kern_info = {kname + '_ms': solve_ms, 'sbm_loss_kernel_ms': float(np.mean(ms_step)) - solve_ms,
+    kern_info = {kname + '_ms': solve_ms, 'sbm_loss_tile_kernel_ms': float(np.mean(ms_loss)),
+                 'sbm_gram_kernel_plus_gather_ms': float(np.mean(ms_gather)),
+                 'per_rank_ms': [{'solve': float(x[0]), 'loss': float(x[1]), 'normal_eq_gather': float(x[2])} for x in per_rank_all],
+                 'loss_algorithmic_gbs': B * (2 * t.n_rows * t.n_proj + 3 * t.n_rows + 3 * t.n_proj + 4) * 8 / (np.mean(ms_loss) * 1e-3) / 1e9,
                  'sens_layout': 'cta-transposed (lane = trajectory, warp = column group)' if ct
                  else 'lane-per-column warp groups'}
     if ct:
@@ -359,13 +501,13 @@ def main():
         kern_info.update({'group_lanes': info['group_lanes'], 'cols_per_lane': info['cols_per_lane'],
                           'block_threads': info['block_threads'], 'dyn_smem_bytes': info['dyn_smem_bytes'],
                           'regs': info['regs_dp5_sens'], 'local_bytes': info['local_dp5_sens']})
-    # DRAM traffic of the dominant kernel from the committed ncu capture, scaled to this launch's batch
+    # DRAM traffic of the dominant kernel: from the committed ncu capture of THIS configuration (same batch), else null
     traffic, traffic_note = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
-        if tr.get('kernel') == kname:
-            traffic = (tr['dram_bytes_read'] + tr['dram_bytes_write']) * B / float(tr['param_sets'])
-            traffic_note = 'dram read+write of one launch at %d parameter sets (%s), scaled by batch' % (
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
+        if tr.get('kernel') == kname and int(tr['param_sets']) == B:
+            traffic = tr['dram_bytes_read'] + tr['dram_bytes_write']
+            traffic_note = 'dram__bytes_read.sum + dram__bytes_write.sum of one launch at %d parameter sets (%s)' % (
                 tr['param_sets'], tr['source'])
     except Exception:
         pass
@@ -377,8 +519,14 @@ def main():
             'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, B),
             'jacobian_evals_per_sec': B * world * args.steps / (total_ms_max * 1e-3),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'calls': n_e2e, 'matches_device_path': same},
-            'gpu_launches': 2 * args.steps,
+                    'calls': n_e2e, 'matches_device_path': same,
+                    'how': 'sbm_jacobian_host (C ABI), pinned host buffers; the batch is evaluated in chunks whose device-to-host '
+                           'copies overlap the integration of the following chunks'},
+            'gpu_launches': 3 * args.steps,
+            'multi_gpu': {'path': 'ShardedProject.step_local_blocks (sysbio_modeling_b200/distributed.py)',
+                          'exchange': 'all_gather_into_tensor of the packed per-set normal equations J^T J | J^T r | r^T r '
+                                      '(%d doubles per set, %.1f MB per rank)' % (n_packed, B * n_packed * 8 / 1e6),
+                          'theta': 'same sample of the distribution on every rank'},
             'kernels': kern_info,
             'counters_per_step': cnt, 'failed_trajectories': status_bad,
             'roofline': {'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
@@ -387,24 +535,37 @@ def main():
                          'kernel': kname,
                          'peak_source': 'measured: sbm_fp64_peak DFMA microbenchmark in this run '
                                         '(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)',
-                         'algorithmic_flops_per_launch': flops_launch,
-                         'flops_model': 'rhs_evals x %d (CSE op count of f,J,G once + %d columns x J*s + G) + steps x 57 x %d'
-                                        % (cuda_src.flops_sens_rhs, sm.n_free, n_aug)},
+                         'algorithmic_flops_per_launch': flops_survey,
+                         'flops_model': 'SURVEY.md 8(d): rhs_evals x %d + attempted steps x 57 x %d'
+                                        % (SURVEY_FLOPS_SENS_RHS_C4, n_aug),
+                         'achieved_emitter_count': achieved_tf_emitter, 'frac_emitter_count': achieved_tf_emitter / peak_tf,
+                         'flops_model_emitter_count': 'rhs_evals x %d (op count of the emitted f, J, G + 22 columns x (2 nnz(J) FMA flops) '
+                                                      '+ nnz(G)) + steps x 57 x %d' % (cuda_src.flops_sens_rhs, n_aug)},
             'clocks': clocks.summary(),
         }
     if world > 1:
         dist.barrier()
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        sample = args.cpu_sample if args.cpu_sample > 0 else min(B, 400 * cores)       # ~12 s of CPU work
-        th = make_thetas(nominal, sample, 4)
-        rate, dt, cores = cpu_reference_rate(th, args.tol, cores)
-        line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                'sample': 'first %d of the %d parameter sets; SciPy odeint (LSODA) rtol=atol=%g on the '
-                                          'reference\'s 1000-node grid with the numba-compiled generated sensitivity RHS '
-                                          '(reference OdeModel.calc_jacobian path), %.1f s wall on %d processes'
-                                          % (sample, B, args.tol, dt, cores)}
+    if rank == 0 and world == 1:
+        try:
+            line['parity'] = parity_check(proj, make_oracle, theta_np[:8], gpu_first)
+        except Exception as exc:                      # the bench line must survive a broken checker
+            line['parity'] = {'error': repr(exc)}
+        if not args.no_configs:
+            del jac_h, flush
+            for k in list(bufs.keys()):
+                del bufs[k]
+            torch.cuda.empty_cache()
+            try:
+                line['configs'] = extra_configs(peak_tf, args.quick_configs)
+            except Exception as exc:
+                line['configs'] = {'error': repr(exc)}
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = args.cpu_sample if args.cpu_sample > 0 else min(B, 400 * cores)       # ~12 s of CPU work
+            rate, dt, cores, kind = cpu_reference_rate(theta_np[:sample], args.tol, cores)
+            line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                                    'sample': 'first ' + cpu_sample_text(kind, sample, args.tol, dt, cores)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -70,7 +70,25 @@
 #define SBM_CT_I_NSTEP  5
 #define SBM_CT_NI       8
 
-#define SBM_CT_BAR(nt) asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory")
+// -DSBM_CT_JITTER=<n>: random delays (up to ~n x 32 ns, different in every launch, warp and call site) before every CTA
+// barrier, every block of tensor-memory transfers and every share of the model.  A missing barrier / fence between a
+// producer and a consumer shows up as results that change from launch to launch (tests/test_gpu_determinism.py).
+#ifdef SBM_CT_JITTER
+__device__ __forceinline__ void sbm_ct_jitter(const unsigned site)
+{
+    unsigned z = (unsigned)clock() * 2654435761u ^ (threadIdx.x >> 5) * 40503u ^ site * 2246822519u ^ blockIdx.x * 3266489917u;
+    z ^= z >> 15; z *= 2246822519u; z ^= z >> 13;
+    z = __shfl_sync(0xffffffffu, z, 0);             // one decision per warp: the delay must not split it
+    if ((z & 3u) == 0u) __nanosleep(((z >> 8) % (unsigned)(SBM_CT_JITTER)) * 32u);
+}
+#define SBM_CT_JIT(site) sbm_ct_jitter(site)
+#else
+#define SBM_CT_JIT(site)
+#endif
+#define SBM_CT_BAR(nt) do { SBM_CT_JIT(1u); asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory"); } while (0)
+#ifndef SBM_CT_BUF_ARG
+#define SBM_CT_BUF_ARG 0
+#endif
 #ifndef SBM_CT_ACCEPT_AT_BEGIN
 #define SBM_CT_ACCEPT_AT_BEGIN 0
 #endif
@@ -112,6 +130,87 @@ __device__ __forceinline__ double sbm_absmax_hi(const double a, const double b)
     const bool ta = ha >= hb;
     return __hiloint2double(ta ? ha : hb, ta ? __double2loint(a) : __double2loint(b));
 }
+
+#ifndef SBM_CT_JTM
+#define SBM_CT_JTM 0
+#endif
+#ifndef SBM_NJU
+#define SBM_NJU SBM_NJ
+#endif
+#define SBM_NJS (SBM_CT_JTM ? SBM_NJP : SBM_NJU)       /* doubles per lane of one J buffer in shared memory */
+
+#if SBM_CT_JTM
+// ---- J through tensor memory ---------------------------------------------------------------------------------
+// The model warp stores J of a stage to shared memory as [entry pair][lane][2 doubles] (16 bytes per lane and pair);
+// one tcgen05.cp ...32x128b.warpx4 per entry pair copies the 32 x 16 bytes to 4 tensor-memory columns of lanes 0-31
+// AND of the other three lane quadrants (measured with tools/tcp_probe.cu: lane l receives the 16 bytes at
+// base + (l / 8) * SBO + (l % 8) * 16, SBO = 128: contiguous), so every column warp reads the J entries of its 32
+// trajectories from its own quadrant with one tcgen05.ld per row pair instead of one shared-memory load per entry:
+// 11 warps x 26 loads x 256 B = 73 KB per stage were 60 % of the kernel's shared-memory traffic, which bounds a stage.
+__device__ __forceinline__ void sbm_ct_j_copy(const double* jsm, const unsigned tdst, unsigned long long* bar)
+{
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(jsm);
+    // shared-memory matrix descriptor (no swizzle): start address >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46
+    unsigned long long desc = (unsigned long long)((addr & 0x3ffffu) >> 4) | (1ull << 16) | (8ull << 32) | (1ull << 46);
+#pragma unroll
+    for (int k = 0; k < SBM_NJP / 2; ++k) {
+        asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" :: "r"(tdst + 4u * k), "l"(desc) : "memory");
+        desc += 32ull;                                 // next [lane][16 B] block: 512 bytes on
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+__device__ __forceinline__ void sbm_ct_j_wait_bar(unsigned long long* bar, const unsigned parity)
+{
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok = 0, spins = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();      // a protocol error must not hang the GPU
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+struct SbmCtJRegs { unsigned r[2 * SBM_JRP]; };
+__device__ __forceinline__ void sbm_ct_j_issue(const unsigned ta, SbmCtJRegs& q)
+{
+#if SBM_JRP == 8
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(q.r[0]), "=r"(q.r[1]), "=r"(q.r[2]), "=r"(q.r[3]), "=r"(q.r[4]), "=r"(q.r[5]), "=r"(q.r[6]), "=r"(q.r[7]),
+                   "=r"(q.r[8]), "=r"(q.r[9]), "=r"(q.r[10]), "=r"(q.r[11]), "=r"(q.r[12]), "=r"(q.r[13]), "=r"(q.r[14]), "=r"(q.r[15])
+                 : "r"(ta));
+#elif SBM_JRP == 4
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(q.r[0]), "=r"(q.r[1]), "=r"(q.r[2]), "=r"(q.r[3]), "=r"(q.r[4]), "=r"(q.r[5]), "=r"(q.r[6]), "=r"(q.r[7])
+                 : "r"(ta));
+#else
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(q.r[0]), "=r"(q.r[1]), "=r"(q.r[2]), "=r"(q.r[3]) : "r"(ta));
+#endif
+}
+__device__ __forceinline__ void sbm_ct_j_wait(SbmCtJRegs& q, double (&jr)[SBM_JRP])
+{
+    // the registers are valid only after the wait: the doubles are formed inside the same asm block (see SbmCtStoreTmem)
+#if SBM_JRP == 8
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n\tmov.b64 %0, {%8, %9};\n\tmov.b64 %1, {%10, %11};\n\tmov.b64 %2, {%12, %13};\n\t"
+                 "mov.b64 %3, {%14, %15};\n\tmov.b64 %4, {%16, %17};\n\tmov.b64 %5, {%18, %19};\n\tmov.b64 %6, {%20, %21};\n\t"
+                 "mov.b64 %7, {%22, %23};"
+                 : "=d"(jr[0]), "=d"(jr[1]), "=d"(jr[2]), "=d"(jr[3]), "=d"(jr[4]), "=d"(jr[5]), "=d"(jr[6]), "=d"(jr[7])
+                 : "r"(q.r[0]), "r"(q.r[1]), "r"(q.r[2]), "r"(q.r[3]), "r"(q.r[4]), "r"(q.r[5]), "r"(q.r[6]), "r"(q.r[7]),
+                   "r"(q.r[8]), "r"(q.r[9]), "r"(q.r[10]), "r"(q.r[11]), "r"(q.r[12]), "r"(q.r[13]), "r"(q.r[14]), "r"(q.r[15]));
+#elif SBM_JRP == 4
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n\tmov.b64 %0, {%4, %5};\n\tmov.b64 %1, {%6, %7};\n\tmov.b64 %2, {%8, %9};\n\t"
+                 "mov.b64 %3, {%10, %11};"
+                 : "=d"(jr[0]), "=d"(jr[1]), "=d"(jr[2]), "=d"(jr[3])
+                 : "r"(q.r[0]), "r"(q.r[1]), "r"(q.r[2]), "r"(q.r[3]), "r"(q.r[4]), "r"(q.r[5]), "r"(q.r[6]), "r"(q.r[7]));
+#else
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n\tmov.b64 %0, {%2, %3};\n\tmov.b64 %1, {%4, %5};"
+                 : "=d"(jr[0]), "=d"(jr[1]) : "r"(q.r[0]), "r"(q.r[1]), "r"(q.r[2]), "r"(q.r[3]));
+#endif
+}
+#endif  /* SBM_CT_JTM */
 
 // stage input from the vectors of one element
 template <int S>
@@ -235,7 +334,7 @@ struct SbmCtStoreReg {
 // dense G buffer: the entry of (column c, state i) sits at Gw[SBM_GIDX(c*NE + i)], structural zeros hold 0.
 // -------------------------------------------------------------------------------------------------
 template <int S, int CW, class ST>
-__device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* __restrict__ Jp,
+__device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* __restrict__ Jp, const unsigned jt,
                                                   const double* __restrict__ Gw,
                                                   double (&y)[CW][SBM_N], double (&s2)[CW][SBM_N],
                                                   double (&s3)[CW][SBM_N], ST& st,
@@ -244,6 +343,7 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
 {
     constexpr int N = SBM_N, NE = N + (N & 1), NP2 = NE / 2;
     __syncwarp();                                  // tcgen05.ld/st are warp-collective: be converged (cheap insurance)
+    SBM_CT_JIT(2u + S);
     // Tensor-memory transfers are pipelined by hand: tcgen05.wait::ld waits for EVERY outstanding load of the thread, so
     // the vectors a row pair needs in its update (k1 in stage 4, the error accumulator from stage 5 on) are requested one
     // row pair ahead - right AFTER the wait for the current one - and their latency hides behind the FMA chains of the
@@ -254,6 +354,13 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
 #pragma unroll
         for (int c = 0; c < CW; ++c) st.issue(USLOT, c * NE, pu[0][c]);       // joins the batch of the stage inputs
     }
+#if SBM_CT_JTM
+    // J of this stage: tensor-memory columns jt .. jt + 2 NJP of this warp's lane quadrant, one load per row pair.
+    // Stages 2 and 3 (no update work to hide a load behind, registers to spare) keep two row pairs in flight.
+    constexpr bool JDBL = (S <= 3);
+    SbmCtJRegs jq[2];
+    sbm_ct_j_issue(jt, jq[0]);
+#endif
     // ---- stage input of every element (element e = c*NE + i; S1 comes in row pairs) ----
     double w[CW][N];
     if (S <= 5) {
@@ -296,8 +403,17 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
             acc[1][c] = g2.y;
 #endif
         }
+#if SBM_CT_JTM
+        {
+            double jr[SBM_JRP];
+            sbm_ct_j_wait(jq[JDBL ? par : 0], jr);
+            if (JDBL && i0 + 2 < N) sbm_ct_j_issue(jt + (unsigned)((i0 >> 1) + 1) * (2u * SBM_JRP), jq[par ^ 1]);
+            sbm_jrow_tm<CW>(i0 >> 1, jr, w, acc[0], acc[1]);
+        }
+#else
         sbm_jrow<CW>(i0, Jp, w, acc[0]);
         if (two) sbm_jrow<CW>(i0 + 1, Jp, w, acc[1]);
+#endif
         double ua[CW], ub[CW];
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
@@ -308,6 +424,9 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
 #pragma unroll
             for (int c = 0; c < CW; ++c) st.issue(USLOT, c * NE + i0 + 2, pu[par ^ 1][c]);
         }
+#if SBM_CT_JTM
+        if (!JDBL && i0 + 2 < N) sbm_ct_j_issue(jt + (unsigned)((i0 >> 1) + 1) * (2u * SBM_JRP), jq[0]);
+#endif
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
             double v1a = 0.0, v1b = 0.0, v4a = 0.0, v4b = 0.0;
@@ -370,6 +489,8 @@ struct SbmCtShared {
     double* em_tk;       // [32]               the output time after the staged one
     int* em_kt;          // [32]               output-time index the staging belongs to (-1: none)
     unsigned tmem_base;  // TMEM allocation holding S1 and S4 of the sensitivity columns
+    unsigned jt_base;    // first tensor-memory column of the two J buffers (SBM_CT_JTM)
+    unsigned long long* jbar;  // [2] mbarriers: the tcgen05.cp transfers of J buffer b have completed
     unsigned long long* mbar;  // [2*NB + 2] mbarriers of the asynchronous hand-over: full[NB], empty[NB], done, go
 };
 
@@ -491,7 +612,7 @@ __device__ __forceinline__ void sbm_ct_cols_begin(const SbmSolveArgs& a, const S
 
 template <int CW, class ST>
 __device__ __forceinline__ void sbm_ct_cols_stage(const int s, const int info, const double h, const double* __restrict__ Jp,
-                                                  const double* __restrict__ Gw,
+                                                  const unsigned jt, const double* __restrict__ Gw,
                                                   double (&y)[CW][SBM_N], double (&s2)[CW][SBM_N],
                                                   double (&s3)[CW][SBM_N], ST& st,
                                                   const double rtol, const double atol,
@@ -509,12 +630,12 @@ __device__ __forceinline__ void sbm_ct_cols_stage(const int s, const int info, c
                 for (int i = 0; i < SBM_N; ++i) y[c][i] = s3[c][i];
         }
 #endif
-        sbm_ct_sens_stage<2, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
-    case 3: sbm_ct_sens_stage<3, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
-    case 4: sbm_ct_sens_stage<4, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
-    case 5: sbm_ct_sens_stage<5, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
-    case 6: sbm_ct_sens_stage<6, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
-    default: sbm_ct_sens_stage<7, CW, ST>(h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+        sbm_ct_sens_stage<2, CW, ST>(h, Jp, jt, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 3: sbm_ct_sens_stage<3, CW, ST>(h, Jp, jt, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 4: sbm_ct_sens_stage<4, CW, ST>(h, Jp, jt, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 5: sbm_ct_sens_stage<5, CW, ST>(h, Jp, jt, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    case 6: sbm_ct_sens_stage<6, CW, ST>(h, Jp, jt, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
+    default: sbm_ct_sens_stage<7, CW, ST>(h, Jp, jt, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1); break;
     }
 }
 
@@ -872,19 +993,24 @@ __device__ __forceinline__ void sbm_ct_primal(const SbmCtShared& sh, const int w
 {
     // with one CTA barrier per stage the buffer is the stage's parity (the compiler then sees one expression for the
     // producer and the consumers; passing it in was measured to change the generated code's results - see DESIGN.md)
-    const int b = SBM_CT_ASYNC ? buf : (S & 1);
+    const int b = (SBM_CT_ASYNC || SBM_CT_BUF_ARG) ? buf : (S & 1);
+    SBM_CT_JIT(16u + S);
     const double ts = fma(sbm_dp_c[S], h, sh.cd[SBM_CT_D_T * 32 + lane]);
     const double* Pp = (S == 2) ? sh.yb + lane : sh.Pb + (S & 1) * SBM_N * 32 + lane;
     // stage 2 is the head of the step: its step size exists only after the previous step has been judged, so it
     // overlaps with nothing and is split over more warps (sbm_primal_head) than the stages that run one ahead
     if (S == 2 && !SBM_CT_ASYNC)
-        sbm_primal_head<32>(warp, ts, Pp, sh.fh + lane, h * DP_A21, sh.pb + lane, sh.Jb + b * SBM_NJ * 32 + lane,
+        sbm_primal_head<32>(warp, ts, Pp, sh.fh + lane, h * DP_A21, sh.pb + lane, sh.Jb + b * SBM_NJS * 32 + (SBM_CT_JTM ? 2 : 1) * lane,
                             sh.Gd + b * SBM_NF * (SBM_N + (SBM_N & 1)) * 32 + 2 * lane, sh.fh + SBM_N * 32 + lane);
     else
         sbm_primal_share<32>(warp, ts, Pp, sh.fh + (S - 2) * SBM_N * 32 + lane, h * sbm_dp_a[S][S - 2], sh.pb + lane,
-                             sh.Jb + b * SBM_NJ * 32 + lane,
+                             sh.Jb + b * SBM_NJS * 32 + (SBM_CT_JTM ? 2 : 1) * lane,
                              sh.Gd + b * SBM_NF * (SBM_N + (SBM_N & 1)) * 32 + 2 * lane,
                              sh.fh + (S - 1) * SBM_N * 32 + lane);
+#if SBM_CT_JTM
+    // the J entries just stored are read by the tensor-memory copy engine (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
 }
 
 // partial stage values of stage S (3..7) for the state components this warp looks after (any warp can: the state
@@ -944,6 +1070,7 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
 #ifdef SBM_CT_PROF
     long long cbusy[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ctprev = 0;
 #endif
+    unsigned jk = 0;                               // stages consumed: J buffer (jk & 1), fill number jk >> 1
     for (;;) {
         if (XW == 0 && warp == 0) { SbmCtCarry none; sbm_ct_control<W, C, SBM_NF - (W - 1) * C, 0>(a, sh, lane, none); }
         SBM_CT_BAR(NT);                            // controller output published
@@ -967,9 +1094,15 @@ __device__ __forceinline__ void sbm_ct_warp(const SbmSolveArgs& a, const SbmCtSh
         for (int s = 1; s <= 7; ++s) {
 #ifndef SBM_WHATIF_COLS_SKIP   /* experiment: the model warp alone (results are wrong) */
             if (s >= 2) {
-                const double* Jp = sh.Jb + (s & 1) * SBM_NJ * 32 + lane;
+                const double* Jp = sh.Jb + (s & 1) * SBM_NJS * 32 + lane;
                 const double* Gw = sh.Gd + ((s & 1) * SBM_NF + col0) * (N + (N & 1)) * 32 + 2 * lane;
-                sbm_ct_cols_stage<CW, ST>(s, info, h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
+                unsigned jt = 0;
+#if SBM_CT_JTM
+                sbm_ct_j_wait_bar(sh.jbar + (s & 1), (jk >> 1) & 1u);
+                ++jk;
+                jt = sh.tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + sh.jt_base + (unsigned)(s & 1) * (2u * SBM_NJP);
+#endif
+                sbm_ct_cols_stage<CW, ST>(s, info, h, Jp, jt, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
             }
 #endif
             if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
@@ -1030,9 +1163,22 @@ __device__ __forceinline__ void sbm_ct_model_warp(const SbmSolveArgs& a, const S
 #endif
 #pragma unroll 1
         for (int s = 1; s <= 7; ++s) {
+#if SBM_CT_JTM
+            // J at the input of stage 2 is written by several warps (head shares): copied once they have all arrived
+            if (s == 2 && warp == W && lane == 0)
+                sbm_ct_j_copy(sh.Jb, sh.tmem_base + sh.jt_base, sh.jbar);
+#endif
             if (s < 6) sbm_ct_prepare<W + XW>(sh, warp, lane, s + 2, h);
             if (s < 7) sbm_ct_primal(sh, warp, lane, s + 1, h, (s + 1) & 1);
-            else if (warp == W) {
+#if SBM_CT_JTM
+            if (s >= 2 && s < 7 && warp == W) {
+                __syncwarp();
+                if (lane == 0)
+                    sbm_ct_j_copy(sh.Jb + ((s + 1) & 1) * SBM_NJS * 32, sh.tmem_base + sh.jt_base + (unsigned)((s + 1) & 1) * (2u * SBM_NJP),
+                                  sh.jbar + ((s + 1) & 1));
+            }
+#endif
+            if (s == 7 && warp == W) {
                 // while the column warps finish stage 7: the state column's part of the controller's input
                 cy.sqs = cy.q0 = cy.q1 = 0.0;
                 sbm_ct_state_column(sh, lane, h, a.rtol, a.atol, cy.ynew, cy.f7, cy.sqs, cy.q0, cy.q1);
@@ -1134,7 +1280,7 @@ __device__ __forceinline__ void sbm_ct_warp_async(const SbmSolveArgs& a, const S
             sbm_mb_wait(full + b, (gc / NB) & 1u); // J, G of this stage are in buffer b
             const double* Jp = sh.Jb + b * SBM_NJ * 32 + lane;
             const double* Gw = sh.Gd + (b * SBM_NF + col0) * NE * 32 + 2 * lane;
-            sbm_ct_cols_stage<CW, ST>(s, info, h, Jp, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
+            sbm_ct_cols_stage<CW, ST>(s, info, h, Jp, 0u, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
             __syncwarp();
             if (lane == 0) sbm_mb_arrive(empty + b);   // this warp is done with buffer b
             ++gc;
@@ -1168,8 +1314,10 @@ __device__ __forceinline__ void sbm_ct_model_warp_async(const SbmSolveArgs& a, c
         for (int S = 2; S <= 7; ++S) {
             const unsigned b = gp % NB;
             if (gp >= (unsigned)NB) sbm_mb_wait(empty + b, ((gp / NB) - 1u) & 1u);   // every column warp has left buffer b
+#ifndef SBM_WHATIF_ASYNC_NOMODEL   /* experiment: how fast are the column warps when the model costs nothing (results are wrong) */
             if (S >= 3) sbm_ct_prepare<1>(sh, 0, lane, S, h);
             sbm_ct_primal(sh, W, lane, S, h, (int)b);
+#endif
             __syncwarp();
             if (lane == 0) sbm_mb_arrive(full + b);
             ++gp;
@@ -1206,7 +1354,7 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
 #else
     constexpr int NBUF = 2;
 #endif
-    sh.Gd = sh.Jb + NBUF * SBM_NJ * 32;
+    sh.Gd = sh.Jb + NBUF * SBM_NJS * 32;
     sh.fh = sh.Gd + NBUF * SBM_NF * (N + (N & 1)) * 32;
     sh.yb = sh.fh + 7 * N * 32;
     sh.ynb = sh.yb + N * 32;
@@ -1223,6 +1371,8 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     sh.cta = sh.ktb + 32;
     sh.park = (double*)(sh.cta + 32);
     sh.mbar = (unsigned long long*)(sh.park + 2 * W * 32);
+    sh.jbar = sh.mbar + 12;                          // (the asynchronous hand-over uses at most 2 * 3 + 2 of the 16 slots)
+    sh.jt_base = 0;
     sh.em_mask = sh.mbar + 16;
     sh.em_off = (long long*)(sh.em_mask + SBM_CT_EM * 32);
     sh.em_n = (int*)(sh.em_off + SBM_CT_EM * 32);
@@ -1241,7 +1391,7 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     const int warp = threadIdx.x >> 5;
     // ---- one-time initialisation of the shared state ----
     for (int q = threadIdx.x; q < NBUF * SBM_NF * (N + (N & 1)) * 32; q += WT * 32) sh.Gd[q] = 0.0;   // structural zeros of G
-    for (int q = threadIdx.x; q < NBUF * SBM_NJ * 32; q += WT * 32) sh.Jb[q] = 0.0;
+    for (int q = threadIdx.x; q < NBUF * SBM_NJS * 32; q += WT * 32) sh.Jb[q] = 0.0;
     for (int q = threadIdx.x; q < 7 * N * 32; q += WT * 32) sh.fh[q] = 0.0;
     for (int q = threadIdx.x; q < 2 * N * 32; q += WT * 32) sh.Pb[q] = 0.0;
     for (int q = threadIdx.x; q < (W + 3) * 32; q += WT * 32) sh.sqb[q] = 0.0;
@@ -1273,7 +1423,18 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     SBM_CT_BAR(WT * 32);
 #else
     // tensor memory for S1 / S4: ceil(W/4) warps per lane quadrant, 4*C*NE columns each (power of two >= 32)
-    constexpr int TM_NEED = ((W + 3) / 4) * 4 * C * (N + (N & 1));
+    constexpr int TM_S = ((W + 3) / 4) * 4 * C * (N + (N & 1));
+#if SBM_CT_JTM
+    constexpr int TM_NEED = TM_S + 2 * 2 * SBM_NJP;   // + two buffers of J (2 columns per double)
+    sh.jt_base = TM_S;
+    if (threadIdx.x == 0) {
+        sbm_mb_init(sh.jbar, 1);
+        sbm_mb_init(sh.jbar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#else
+    constexpr int TM_NEED = TM_S;
+#endif
     constexpr int TM_COLS = TM_NEED <= 32 ? 32 : TM_NEED <= 64 ? 64 : TM_NEED <= 128 ? 128 : TM_NEED <= 256 ? 256 : 512;
     static_assert(TM_NEED <= 512, "sensitivity columns do not fit in tensor memory");
     if (warp == 0) {

@@ -219,7 +219,7 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     m->layout = desc->sens_layout > 0 ? desc->sens_layout : 0;
     {
         const int N = desc->n_vars, NF = desc->n_free;
-        int NJ = 1, NG = 1, W = 0, C = 0, XW = 0, TM = 0, RV = 0, AS = 0, NB = 2;
+        int NJ = 1, NG = 1, W = 0, C = 0, XW = 0, TM = 0, RV = 0, AS = 0, NB = 2, NJP = 0, JTM = 0;
         const char* q;
         if ((q = strstr(model_src, "#define SBM_NJ "))) NJ = atoi(q + 15);
         if ((q = strstr(model_src, "#define SBM_NG "))) NG = atoi(q + 15);
@@ -229,7 +229,11 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
         if ((q = strstr(model_src, "#define SBM_CT_TMEM "))) TM = atoi(q + 20);
         if ((q = strstr(model_src, "#define SBM_CT_REGV "))) RV = atoi(q + 20);
         if ((q = strstr(model_src, "#define SBM_CT_ASYNC "))) AS = atoi(q + 21);
+        if ((q = strstr(model_src, "#define SBM_NJU "))) NJ = atoi(q + 16);       // J entries equal up to sign share a slot
+        if ((q = strstr(model_src, "#define SBM_NJP "))) NJP = atoi(q + 16);
+        if ((q = strstr(model_src, "#define SBM_CT_JTM "))) JTM = atoi(q + 19);
         if (AS) NB = 3;
+        if (JTM) NJ = NJP;                        // J buffers in shared memory: row pairs padded for the tensor-memory copies
         (void)NG;
         if (W >= 1 && C >= 1 && NF >= 1) {
             const int CL = NF - (W - 1) * C;
@@ -238,7 +242,7 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
                                     4ll * (8 * 32 + 3 * 32) + 8ll * 2 * W * 32 +
                                     8ll * (2 * 4 * 32 + 32) + 4ll * (32 + (desc->n_params + (desc->n_params & 1)) * 32) +
                                     8ll * (2 * 4 * 32 + 32) + 4ll * 32;   // rows staged ahead by the model warp: offsets, values, next time, index   // staged rows (SBM_CT_EM = 4), row base, project columns
-            const int tm_need = ((W + 3) / 4) * 4 * C * (N + (N & 1));
+            const int tm_need = ((W + 3) / 4) * 4 * C * (N + (N & 1)) + (JTM ? 4 * NJP : 0);
             if (CL >= 1 && CL <= C && CL * N >= 2 && W + XW <= 32 && bytes <= 227 * 1024 && ((TM == 1 && tm_need <= 512) || RV == 1)) {
                 m->ctW = W; m->ctC = C; m->ctCS = CL; m->ctXW = XW; m->ct_dyn_smem = (int)bytes; m->ct_ok = true;
                 // tensor-memory columns one CTA allocates (power of two >= 32): bounds the CTAs that can run on an SM
@@ -408,6 +412,8 @@ extern "C" void sbm_model_destroy(sbm_model* m)
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
+#define SBM_HOST_CHUNKS_MAX 8
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -435,8 +441,10 @@ struct sbm_plan {
     bool jac_full = false;        // the integrator writes EVERY entry of jac (no memset needed before the launch)
     int sm_count = 0;
     std::mutex mu;                // the *_host entry points share the workspaces below: one call at a time per plan
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    // chunked host evaluation: two compute streams (the persistent integrator launches of consecutive chunks overlap
+    // tail-to-head), one copy stream, one event per chunk
+    cudaStream_t cs[2] = {nullptr, nullptr}, copy_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_chunk[SBM_HOST_CHUNKS_MAX] = {}, ev_end[3] = {};
     // grow-only workspaces of the *_host entry points
     DevBuf w_theta, w_sims, w_jac, w_resid, w_ssr, w_sf, w_sfgrad, w_grad, w_status, w_counters;
 };
@@ -461,7 +469,10 @@ extern "C" void sbm_plan_destroy(sbm_plan* p)
     p->w_theta.release(); p->w_sims.release(); p->w_jac.release(); p->w_resid.release(); p->w_ssr.release();
     p->w_sf.release(); p->w_sfgrad.release(); p->w_grad.release(); p->w_status.release(); p->w_counters.release();
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
-    for (int i = 0; i < 2; ++i) { if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]); if (p->ev_free[i]) cudaEventDestroy(p->ev_free[i]); }
+    for (int i = 0; i < 2; ++i) if (p->cs[i]) cudaStreamDestroy(p->cs[i]);
+    if (p->ev_in) cudaEventDestroy(p->ev_in);
+    for (int i = 0; i < SBM_HOST_CHUNKS_MAX; ++i) if (p->ev_chunk[i]) cudaEventDestroy(p->ev_chunk[i]);
+    for (int i = 0; i < 3; ++i) if (p->ev_end[i]) cudaEventDestroy(p->ev_end[i]);
     delete p;
 }
 
@@ -566,6 +577,8 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
         blocks = (ntraj + 31) / 32;
         const long long resident = (long long)m->sm_count * m->ct_ctas_per_sm;
         if (blocks > resident) blocks = resident;
+        // experiment / determinism tests: a smaller persistent grid changes which trajectories share a CTA and when
+        if (const char* mc = getenv("SBM_CT_MAX_CTAS")) { long long v = atoll(mc); if (v >= 1 && v < blocks) blocks = v; }
         RT(cudaMemsetAsync(counters + SBM_CNT_QUEUE, 0, sizeof(unsigned long long), st));
     }
     else if (jac) { ks = &m->dp5_sens; threads = ntraj * m->G; block = m->block; dyn = m->dyn_smem; }
@@ -673,6 +686,29 @@ extern "C" int sbm_lm_step(long long B, int n_rows, int n_proj, const double* ja
 // ------------------------------------------------------------------------------------------------
 // fused host-buffer entry points
 // ------------------------------------------------------------------------------------------------
+// Chunks of a host evaluation: bounds[0..n] of n chunks.  The device-to-host copy of a large result (C4: 494 MB of scaled
+// Jacobians per 65,536 sets, ~10 ms) hides behind the integration of the chunks that follow, so the LAST chunk's copy is
+// what stays exposed: two chunks, 80 % / 20 %.  More chunks cost more than they hide - every launch of the persistent
+// integrator ends in a tail (lanes idle once its trajectory queue is empty, ~15 ms on C4) and a chunk of a few waves is
+// mostly tail (measured: 8 equal chunks 122 k solves/s end to end against 158 k serial).  The launches of consecutive
+// chunks go to two streams, so the CTAs of chunk c+1 start on the SMs chunk c's tail frees.
+// SBM_HOST_CHUNKS=n forces n equal chunks (1 = serial).
+static int host_chunks(long long B, bool with_jac, size_t out_bytes, long long* bounds)
+{
+    int n = 1;
+    bool equal = false;
+    if (const char* e = getenv("SBM_HOST_CHUNKS")) {
+        int v = atoi(e);
+        if (v >= 1 && v <= SBM_HOST_CHUNKS_MAX && (long long)v <= B) { n = v; equal = true; }
+    } else if (with_jac && out_bytes >= (64u << 20) && B >= 6 * 4736) {
+        n = 2;
+    }
+    bounds[0] = 0;
+    if (equal || n == 1) { for (int c = 1; c <= n; ++c) bounds[c] = B * c / n; }
+    else { bounds[1] = (B * 4 / 5 + 31) / 32 * 32; if (bounds[1] >= B) bounds[1] = B / 2; bounds[2] = B; }
+    return n;
+}
+
 static int host_eval(sbm_plan* p, const sbm_solver_opts_t* o, int loss_kind, int flags, long long B, bool with_jac,
                      const double* theta_host, double* jac_host, double* model_jac_host, double* resid_host,
                      double* ssr_host, double* grad_host, double* sf_host, double* sims_host, int* status_host,
@@ -682,40 +718,85 @@ static int host_eval(sbm_plan* p, const sbm_solver_opts_t* o, int loss_kind, int
     if (B <= 0) return fail(SBM_E_INVALID, "B must be positive");
     int rc = require_device();
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(p->mu);          // the workspaces below belong to the plan: one host call at a time
     cudaStream_t st = (cudaStream_t)stream;
     const size_t R = (size_t)p->d.n_rows, P = (size_t)p->d.n_proj, Gn = (size_t)p->d.n_groups, E = (size_t)p->d.E;
     const size_t nB = (size_t)B;
+    const size_t out_bytes = nB * R * 8 * (1 + (with_jac && jac_host ? P : 0));
+    long long bounds[SBM_HOST_CHUNKS_MAX + 1];
+    int nch = host_chunks(B, with_jac, out_bytes, bounds);
+    if (model_jac_host) { nch = 1; bounds[1] = B; }
     if (p->w_theta.ensure(nB * P * 8) || p->w_sims.ensure(nB * R * 8) || p->w_resid.ensure(nB * R * 8) ||
         p->w_ssr.ensure(nB * 8) || p->w_sf.ensure((nB * Gn + 1) * 8) || p->w_status.ensure(nB * E * 4) ||
-        p->w_counters.ensure(SBM_N_COUNTERS * 8))
+        p->w_counters.ensure((size_t)SBM_HOST_CHUNKS_MAX * SBM_N_COUNTERS * 8))
         return fail(SBM_E_NOMEM, "device workspace allocation failed");
     if (with_jac && (p->w_jac.ensure(nB * R * P * 8) || p->w_sfgrad.ensure((nB * Gn * P + 1) * 8) || p->w_grad.ensure(nB * P * 8)))
         return fail(SBM_E_NOMEM, "device workspace allocation failed (Jacobian)");
     double* d_theta = (double*)p->w_theta.p;
     double* d_sims = (double*)p->w_sims.p;
     double* d_jac = with_jac ? (double*)p->w_jac.p : nullptr;
+    unsigned long long* d_cnt = (unsigned long long*)p->w_counters.p;
     RT(cudaMemcpyAsync(d_theta, theta_host, nB * P * 8, cudaMemcpyHostToDevice, st));
-    RT(cudaMemsetAsync(p->w_counters.p, 0, SBM_N_COUNTERS * 8, st));
+    RT(cudaMemsetAsync(d_cnt, 0, (size_t)SBM_HOST_CHUNKS_MAX * SBM_N_COUNTERS * 8, st));
     RT(cudaMemsetAsync(d_sims, 0, nB * R * 8, st));
-    rc = sbm_solve(p, o, B, d_theta, (long long)P, 1, d_sims, d_jac, (int*)p->w_status.p,
-                   (unsigned long long*)p->w_counters.p, stream);
-    if (rc) return rc;
-    if (with_jac && model_jac_host) RT(cudaMemcpyAsync(model_jac_host, d_jac, nB * R * P * 8, cudaMemcpyDeviceToHost, st));
-    rc = sbm_loss(p, loss_kind, flags, B, d_theta, (long long)P, 1, d_sims, d_jac, (double*)p->w_resid.p,
-                  (double*)p->w_ssr.p, (double*)p->w_sf.p, with_jac ? (double*)p->w_sfgrad.p : nullptr,
-                  with_jac ? (double*)p->w_grad.p : nullptr, stream);
-    if (rc) return rc;
-    if (resid_host) RT(cudaMemcpyAsync(resid_host, p->w_resid.p, nB * R * 8, cudaMemcpyDeviceToHost, st));
-    if (ssr_host) RT(cudaMemcpyAsync(ssr_host, p->w_ssr.p, nB * 8, cudaMemcpyDeviceToHost, st));
-    if (sf_host && Gn) RT(cudaMemcpyAsync(sf_host, p->w_sf.p, nB * Gn * 8, cudaMemcpyDeviceToHost, st));
-    if (sims_host) RT(cudaMemcpyAsync(sims_host, d_sims, nB * R * 8, cudaMemcpyDeviceToHost, st));
-    if (status_host) RT(cudaMemcpyAsync(status_host, p->w_status.p, nB * E * 4, cudaMemcpyDeviceToHost, st));
-    if (counters_host) RT(cudaMemcpyAsync(counters_host, p->w_counters.p, SBM_N_COUNTERS * 8, cudaMemcpyDeviceToHost, st));
-    if (with_jac) {
-        if (jac_host) RT(cudaMemcpyAsync(jac_host, d_jac, nB * R * P * 8, cudaMemcpyDeviceToHost, st));
-        if (grad_host) RT(cudaMemcpyAsync(grad_host, p->w_grad.p, nB * P * 8, cudaMemcpyDeviceToHost, st));
+    if (nch > 1) {
+        if (!p->copy_stream) {
+            RT(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) RT(cudaStreamCreateWithFlags(&p->cs[i], cudaStreamNonBlocking));
+            RT(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+            for (int i = 0; i < SBM_HOST_CHUNKS_MAX; ++i) RT(cudaEventCreateWithFlags(&p->ev_chunk[i], cudaEventDisableTiming));
+            for (int i = 0; i < 3; ++i) RT(cudaEventCreateWithFlags(&p->ev_end[i], cudaEventDisableTiming));
+        }
+        RT(cudaEventRecord(p->ev_in, st));
+        for (int i = 0; i < 2; ++i) RT(cudaStreamWaitEvent(p->cs[i], p->ev_in, 0));
+    }
+    for (int c = 0; c < nch; ++c) {
+        const size_t lo = (size_t)bounds[c], hi = (size_t)bounds[c + 1], n = hi - lo;
+        if (!n) continue;
+        cudaStream_t s = nch > 1 ? p->cs[c & 1] : st;
+        cudaStream_t sc = nch > 1 ? p->copy_stream : st;
+        rc = sbm_solve(p, o, (long long)n, d_theta + lo * P, (long long)P, 1, d_sims + lo * R, d_jac ? d_jac + lo * R * P : nullptr,
+                       (int*)p->w_status.p + lo * E, d_cnt + (size_t)c * SBM_N_COUNTERS, s);
+        if (rc) return rc;
+        if (with_jac && model_jac_host) RT(cudaMemcpyAsync(model_jac_host, d_jac, nB * R * P * 8, cudaMemcpyDeviceToHost, s));
+        rc = sbm_loss(p, loss_kind, flags, (long long)n, d_theta + lo * P, (long long)P, 1, d_sims + lo * R,
+                      d_jac ? d_jac + lo * R * P : nullptr, (double*)p->w_resid.p + lo * R, (double*)p->w_ssr.p + lo,
+                      (double*)p->w_sf.p + lo * Gn, with_jac ? (double*)p->w_sfgrad.p + lo * Gn * P : nullptr,
+                      with_jac ? (double*)p->w_grad.p + lo * P : nullptr, s);
+        if (rc) return rc;
+        if (nch > 1) {
+            RT(cudaEventRecord(p->ev_chunk[c], s));
+            RT(cudaStreamWaitEvent(sc, p->ev_chunk[c], 0));
+        }
+        if (with_jac && jac_host) RT(cudaMemcpyAsync(jac_host + lo * R * P, d_jac + lo * R * P, n * R * P * 8, cudaMemcpyDeviceToHost, sc));
+        if (resid_host) RT(cudaMemcpyAsync(resid_host + lo * R, (double*)p->w_resid.p + lo * R, n * R * 8, cudaMemcpyDeviceToHost, sc));
+        if (sims_host) RT(cudaMemcpyAsync(sims_host + lo * R, d_sims + lo * R, n * R * 8, cudaMemcpyDeviceToHost, sc));
+    }
+    // small results in one piece, after everything
+    cudaStream_t sc = nch > 1 ? p->copy_stream : st;
+    if (nch > 1) {
+        // the copy stream already waits for every chunk; the caller's stream waits for all three internal streams
+        for (int i = 0; i < 2; ++i) { RT(cudaEventRecord(p->ev_end[i], p->cs[i])); RT(cudaStreamWaitEvent(sc, p->ev_end[i], 0)); }
+    }
+    if (ssr_host) RT(cudaMemcpyAsync(ssr_host, p->w_ssr.p, nB * 8, cudaMemcpyDeviceToHost, sc));
+    if (sf_host && Gn) RT(cudaMemcpyAsync(sf_host, p->w_sf.p, nB * Gn * 8, cudaMemcpyDeviceToHost, sc));
+    if (status_host) RT(cudaMemcpyAsync(status_host, p->w_status.p, nB * E * 4, cudaMemcpyDeviceToHost, sc));
+    if (with_jac && grad_host) RT(cudaMemcpyAsync(grad_host, p->w_grad.p, nB * P * 8, cudaMemcpyDeviceToHost, sc));
+    unsigned long long cnt_h[SBM_HOST_CHUNKS_MAX * SBM_N_COUNTERS];
+    if (counters_host) RT(cudaMemcpyAsync(cnt_h, d_cnt, sizeof cnt_h, cudaMemcpyDeviceToHost, sc));
+    if (nch > 1) {
+        RT(cudaEventRecord(p->ev_end[2], sc));
+        RT(cudaStreamWaitEvent(st, p->ev_end[2], 0));
+        RT(cudaStreamSynchronize(sc));
     }
     RT(cudaStreamSynchronize(st));
+    if (counters_host) {
+        for (int k = 0; k < SBM_N_COUNTERS; ++k) {
+            unsigned long long v = 0;
+            for (int c = 0; c < nch; ++c) v += cnt_h[c * SBM_N_COUNTERS + k];
+            counters_host[k] = v;
+        }
+    }
     return 0;
 }
 

@@ -94,8 +94,15 @@ class OdeModel(ModelABC):
         if P.shape[1] != NP:
             raise ValueError('expected %d parameters, got %d' % (NP, P.shape[1]))
         t_sim = np.asarray(t_sim, dtype=np.float64)
-        if np.any(np.diff(t_sim) <= 0) or t_sim[0] < 0:
-            raise ValueError('t_sim must be non-negative and strictly increasing')
+        if np.any(np.diff(t_sim) <= 0):
+            raise ValueError('t_sim must be strictly increasing')
+        # the reference hands t_sim straight to odeint, which takes t_sim[0] as the INITIAL time: y(t_sim[0]) = init_conditions
+        # (ode_model.py:122-123, 167-168).  The kernels integrate from 0, so the grid is shifted; that is exact for an
+        # autonomous right-hand side (every model the symbolic front end has produced so far) and refused otherwise.
+        if t_sim[0] != 0.0:
+            if not self.symbolic.autonomous:
+                raise NotImplementedError('t_sim[0] != 0 with a time-dependent right-hand side is not supported by the CUDA backend')
+            t_sim = t_sim - t_sim[0]
         tpos = t_sim[t_sim > 0]
         T = len(tpos)
         y0 = np.broadcast_to(np.asarray(y0, dtype=np.float64), (nb, N))

@@ -505,7 +505,20 @@ class Project(object):
         # 'normalized' is folded into the plan's sigma, the kernel then runs the square loss
         return 'square' if self._loss_kind == 'normalized' else self._loss_kind
 
+    def _warn_failed(self, status):
+        """Numerical failure is not an exception in the reference - it is inf residuals / Jacobian - but
+        a silent inf hides WHY: surface the integrator's per-trajectory status (max_steps: typically a stiff region the
+        explicit sensitivity integrator cannot cross - the stiff kernel integrates states only)."""
+        status = np.asarray(status)
+        if status.size and np.any(status != 0):
+            bad = status[status != 0]
+            names = sorted(set(_lib.STATUS_NAMES.get(int(x), str(int(x))) for x in bad))
+            warnings.warn('%d of %d trajectories failed in the integrator (%s): their parameter sets get inf residuals; '
+                          'the sensitivity path is explicit (DP5) - a stiff model needs solver="rodas4" (states only)'
+                          % (bad.size, status.size, ', '.join(names)), RuntimeWarning, stacklevel=3)
+
     def _store_last(self, theta, out, with_jac):
+        self._warn_failed(out['status'])
         self._project_param_vector = np.copy(theta)
         last = {'sims': out['sims'][0], 'resid': out['resid'][0], 'sf': out['sf'][0], 'status': out['status'][0],
                 'counters': out['counters']}
@@ -580,16 +593,20 @@ class Project(object):
     # ---- additive batch API -------------------------------------------------------------------
     def residuals_batch(self, thetas, solver=None):
         """thetas f8[B, n_proj] -> dict(resid [B, n_rows], ssr [B], sf [B, G], sims, status [B, E], counters)."""
-        return self.device_plan.residuals_host(np.asarray(thetas, dtype=np.float64), self._opts(solver),
-                                               self._loss_name())
+        out = self.device_plan.residuals_host(np.asarray(thetas, dtype=np.float64), self._opts(solver),
+                                              self._loss_name())
+        self._warn_failed(out['status'])
+        return out
 
     def ssr_batch(self, thetas, solver=None):
         return self.residuals_batch(thetas, solver)['ssr']
 
     def jacobian_batch(self, thetas):
         """thetas f8[B, n_proj] -> dict(jac [B, n_rows, n_proj], model_jac, resid, ssr, grad [B, n_proj], ...)."""
-        return self.device_plan.jacobian_host(np.asarray(thetas, dtype=np.float64), self._opts('dp5'),
-                                              self._loss_name(), self._flags())
+        out = self.device_plan.jacobian_host(np.asarray(thetas, dtype=np.float64), self._opts('dp5'),
+                                             self._loss_name(), self._flags())
+        self._warn_failed(out['status'])
+        return out
 
     def rss_gradient_batch(self, thetas):
         return self.jacobian_batch(thetas)['grad']

@@ -29,6 +29,7 @@ import textwrap
 from collections import OrderedDict
 from dataclasses import dataclass, field
 
+import numpy as np
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
 from sympy.printing.pycode import PythonCodePrinter
@@ -568,7 +569,7 @@ def _instr_cost(e):
 
 
 def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0, fname='sbm_primal_share',
-                        n_shares=None, head=False):
+                        n_shares=None, head=False, jpos=None, jslot=None, jrep=None):
     """Split the model's primal part - f, the non-zeros of J = df/dy and of G = df/dp - into W shares, one per
     warp of the CTA-transposed kernel.  Each share is straight-line code that recomputes the sub-expressions it
     needs (a share that owns several outputs of one rate law computes its reciprocal once), reads only the stage
@@ -715,7 +716,12 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0, f
             if kind == 'f':
                 body.append('        fo[%d * 32] = %s;' % (idx, pr.doprint(e)))
             elif kind == 'J':
-                body.append('        Jo[%d * 32] = %s;' % (idx, pr.doprint(e)))
+                if jrep is not None and jrep.get(idx) is not None:
+                    body.append('#if SBM_CT_JTM')
+                    body.append('        Jo[SBM_JPOS(%d, %d)] = %s;' % (idx, jpos[idx], pr.doprint(e)))
+                    body.append('#endif')
+                else:
+                    body.append('        Jo[SBM_JPOS(%d, %d)] = %s;' % (jslot[idx] if jslot is not None else idx, jpos[idx], pr.doprint(e)))
             else:
                 i, j = gkeys[idx]
                 body.append('        Go[SBM_GIDX(%d)] = %s;' % (j * (N + (N & 1)) + i, pr.doprint(e)))
@@ -828,6 +834,45 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     L.append('}')
     L.append('')
 
+    # --- entries of J that are equal up to sign (conservation: a reaction leaves one pool and enters another, so the rows
+    #     of a conserved pair differ only in sign) share ONE slot of the shared-memory J buffer of the CTA-transposed kernel:
+    #     fewer stores for the model warp, fewer loads for every column warp (the DFMA takes the sign for free)
+    jslot, jsign, jrep, n_ju = {}, {}, {}, 0
+    # candidates by numerical evaluation at two random points (cheap), confirmed symbolically (exact)
+    syms = sorted(set().union(*[e.free_symbols for e in J_x]) if J_x else [], key=str)
+    vals = []
+    if syms:
+        rng_ = np.random.default_rng(12345)
+        fn_ = sp.lambdify(syms, [e.xreplace({a: a for a in ()}) for e in J_x], modules=[{'sbm_rcp': lambda x: 1.0 / x, 'sbm_log': np.log,
+                                                                                         'sbm_exp': np.exp}, 'numpy'])
+        for _ in range(2):
+            vals.append(np.array(fn_(*list(0.5 + rng_.random(len(syms)))), dtype=np.float64))
+    for q, e in enumerate(J_x):
+        hit = None
+        for q2 in range(q):
+            if jrep[q2] is not None:
+                continue
+            sgn = 0
+            if vals:
+                a0, b0, a1, b1 = vals[0][q], vals[0][q2], vals[1][q], vals[1][q2]
+                tol_ = 1e-12 * max(abs(a0), abs(a1), 1e-300)
+                if abs(a0 - b0) <= tol_ and abs(a1 - b1) <= tol_:
+                    sgn = 1
+                elif abs(a0 + b0) <= tol_ and abs(a1 + b1) <= tol_:
+                    sgn = -1
+            else:
+                sgn = 1 if e == J_x[q2] else (-1 if e == -J_x[q2] else 0)
+            if sgn and sp.simplify(e - sgn * J_x[q2]) == 0:
+                hit = (q2, sgn)
+                break
+        if hit is None:
+            jrep[q] = None
+            jslot[q], jsign[q] = n_ju, 1
+            n_ju += 1
+        else:
+            jrep[q] = hit[0]
+            jslot[q], jsign[q] = jslot[hit[0]], hit[1]
+    L.append('#define SBM_NJU %d' % max(n_ju, 1))
     # --- row i of J*w for C columns at once, J read from shared memory ([entry][lane]); used by the
     #     CTA-transposed kernel (kernels/sbm_dp5_ct.cuh), where `i` is a constant after unrolling
     L.append('#ifndef SBM_JLOAD')
@@ -840,14 +885,44 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     for i in range(N):
         ent = [(q, k) for q, (ii, k) in enumerate(jkeys) if ii == i]
         L.append('    %sif (i == %d) {' % ('else ' if i else '', i))
-        for q, k in ent:
-            L.append('        const double j%d = SBM_JLOAD(%d);' % (q, q))
+        for sl in sorted(set(jslot[q] for q, k in ent)):
+            L.append('        const double j%d = SBM_JLOAD(%d);' % (sl, sl))
         if ent:
             expr = 'acc[c]'
             for q, k in ent:
-                expr = 'fma(j%d, w[c][%d], %s)' % (q, k, expr)
+                expr = 'fma(%sj%d, w[c][%d], %s)' % ('-' if jsign[q] < 0 else '', jslot[q], k, expr)
             L.append('#pragma unroll')
             L.append('        for (int c = 0; c < C; ++c) acc[c] = %s;' % expr)
+        L.append('    }')
+    L.append('}')
+    # --- the same for a row PAIR with the entries of J in registers (loaded from tensor memory, where the model warp's
+    #     J arrives through tcgen05.cp): the entries of rows 2 rp and 2 rp + 1 are adjacent, each row pair padded to
+    #     SBM_JRP doubles (a power of two: one tcgen05.ld per row pair)
+    NP2 = (N + 1) // 2
+    rp_ent = [[(q, ii, k) for q, (ii, k) in enumerate(jkeys) if ii // 2 == rp] for rp in range(NP2)]
+    JRP = 2
+    while JRP < max([len(e) for e in rp_ent] + [1]):
+        JRP *= 2
+    jpos = {}
+    for rp in range(NP2):
+        for n_, (q, ii, k) in enumerate(rp_ent[rp]):
+            jpos[q] = rp * JRP + n_
+    L.append('#define SBM_JRP %d' % JRP)
+    L.append('#define SBM_NJP %d' % (NP2 * JRP))
+    L.append('template <int C>')
+    L.append('__device__ __forceinline__ void sbm_jrow_tm(const int rp, const double (&jr)[SBM_JRP],')
+    L.append('        const double (&w)[C][SBM_N], double (&acc0)[C], double (&acc1)[C])')
+    L.append('{')
+    for rp in range(NP2):
+        L.append('    %sif (rp == %d) {' % ('else ' if rp else '', rp))
+        for r_, accn in ((2 * rp, 'acc0'), (2 * rp + 1, 'acc1')):
+            ent = [(n_, k) for n_, (q, ii, k) in enumerate(rp_ent[rp]) if ii == r_]
+            if ent:
+                expr = '%s[c]' % accn
+                for n_, k in ent:
+                    expr = 'fma(jr[%d], w[c][%d], %s)' % (n_, k, expr)
+                L.append('#pragma unroll')
+                L.append('        for (int c = 0; c < C; ++c) %s[c] = %s;' % (accn, expr))
         L.append('    }')
     L.append('}')
     W_ct, C_ct = ct_layout(N, NF, ct_cols)
@@ -878,10 +953,26 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     if 'SBM_CT_ASYNC' in _os.environ:
         asyn = int(_os.environ['SBM_CT_ASYNC']) if (XW_ct == 1 and n_sh == 1) else 0
     L.append('#define SBM_CT_ASYNC %d' % asyn)
-    L.append('#define SBM_CT_TMEM %d' % (1 if (W_ct and not regv and ((W_ct + 3) // 4) * 4 * C_ct * NE_ct <= 512) else 0))
+    tm_cols = ((W_ct + 3) // 4) * 4 * C_ct * NE_ct
+    L.append('#define SBM_CT_TMEM %d' % (1 if (W_ct and not regv and tm_cols <= 512) else 0))
+    # J of a stage handed to the column warps through tensor memory (tcgen05.cp broadcasts the model warp's [lane][16 B]
+    # blocks to the four lane quadrants) instead of W x NJ shared-memory loads per stage: needs the model warp, the
+    # synchronous hand-over and room for two buffers of 2 * NJP columns
+    jtm_ok = XW_ct == 1 and not regv and not asyn and JRP <= 8 and tm_cols + 4 * NP2 * JRP <= 512
+    # (measured on C4: 120 k solves/s against 157 k - every tcgen05.cp costs the issuing model warp ~55 clocks, 16 per stage:
+    #  the critical path grows by more than the column warps save; kept as an option, off by default)
+    jtm = 0
+    if 'SBM_CT_JTM' in _os.environ:
+        jtm = int(_os.environ['SBM_CT_JTM']) if jtm_ok else 0
+    L.append('#define SBM_CT_JTM %d' % jtm)
+    L.append('#if SBM_CT_JTM')
+    L.append('#define SBM_JPOS(q, qp) ((((qp) >> 1) * 64) + ((qp) & 1))')
+    L.append('#else')
+    L.append('#define SBM_JPOS(q, qp) ((q) * 32)')
+    L.append('#endif')
     if W_ct:
         ysyms = [sp.Symbol('y[%d]' % i, real=True) for i in range(N)]
-        _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct)
+        _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct, jpos=jpos, jslot=jslot, jrep=jrep)
         # a second, wider split for the first stage of a step: its step size is only known once the previous step
         # has been judged, so nothing overlaps it and every warp is free to help
         # (measured on C4 with the model warp: 1 / 2 / 3 / 4 / 6 head shares = 144.2 / 141.7 / 145.1 / 144.5 / 142.9 k solves/s;
@@ -889,7 +980,7 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
         n_head = int(_os.environ.get('SBM_CT_HEAD_SHARES', '0')) or min(W_ct + XW_ct, 4)
         L.append('#define SBM_CT_HEAD_SHARES %d' % n_head)
         _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W_ct, C_ct, NF, ysyms, XW_ct, fname='sbm_primal_head',
-                            n_shares=n_head, head=True)
+                            n_shares=n_head, head=True, jpos=jpos, jslot=jslot, jrep=jrep)
 
     # --- dense Jacobian (row-major Jd[i*N+k]) and df/dt for the Rosenbrock kernel
     rep, red = sp.cse(J_x, symbols=sp.numbered_symbols('c_'), optimizations='basic')

@@ -129,10 +129,15 @@ def test_ct_layout_and_primal_shares_cover_every_output_once():
         body = src[src.index('void sbm_primal_share('):]
         body = body[:body.index('\n}\n')]
         f_idx = sorted(int(x) for x in re.findall(r'fo\[(\d+) \* 32\] =', body))
-        j_idx = sorted(int(x) for x in re.findall(r'Jo\[(\d+) \* 32\] =', body))
+        # J entries equal up to sign share a slot of the J buffer (SBM_NJU slots); the first argument of SBM_JPOS is the
+        # slot, written once - the duplicates only exist for the padded tensor-memory layout (#if SBM_CT_JTM)
+        plain = re.sub(r'#if SBM_CT_JTM\n.*\n#endif\n', '', body)
+        j_idx = sorted(int(x) for x in re.findall(r'Jo\[SBM_JPOS\((\d+), \d+\)\] =', plain))
+        nju = int(re.search(r'#define SBM_NJU (\d+)', src).group(1))
+        assert 1 <= nju <= cs.nnz_J
         g_idx = sorted(int(x) for x in re.findall(r'Go\[SBM_GIDX\((\d+)\)\] =', body))
         assert f_idx == list(range(sm.n_vars))
-        assert j_idx == list(range(cs.nnz_J))
+        assert j_idx == list(range(nju))
         # dense G slot = parameter * N + state, one per structural non-zero
         ne = sm.n_vars + (sm.n_vars & 1)
         assert g_idx == sorted(j * ne + i for (i, j) in sm.G.keys())
