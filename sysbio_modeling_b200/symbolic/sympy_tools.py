@@ -843,7 +843,7 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     vals = []
     if syms:
         rng_ = np.random.default_rng(12345)
-        fn_ = sp.lambdify(syms, [e.xreplace({a: a for a in ()}) for e in J_x], modules=[{'sbm_rcp': lambda x: 1.0 / x, 'sbm_log': np.log,
+        fn_ = sp.lambdify(syms, list(J_x), modules=[{'sbm_rcp': lambda x: 1.0 / x, 'sbm_log': np.log,
                                                                                          'sbm_exp': np.exp}, 'numpy'])
         for _ in range(2):
             vals.append(np.array(fn_(*list(0.5 + rng_.random(len(syms)))), dtype=np.float64))
