@@ -197,6 +197,18 @@ int sbm_jacobian_host(sbm_plan* p, const sbm_solver_opts_t* opts, int loss_kind,
                       double* grad_host, double* sf_host, double* sims_host, int* status_host,
                       unsigned long long* counters_host, void* stream);
 
+/* ---- pipelined form of sbm_jacobian_host: the copy-out of one evaluation (C4: 494 MB of scaled Jacobians, ~9 ms over PCIe)
+ * cannot hide inside its own call (the persistent integrator fills every SM), but it hides behind the NEXT evaluation.
+ * sbm_jacobian_host_begin enqueues copy-in, integrator and loss epilogue on the caller's stream and the copy-out on the
+ * plan's own copy stream, using workspace slot 0 or 1, and returns without waiting; sbm_host_end(slot) waits until that
+ * slot's host buffers are complete.  A consumer of Project.calc_project_jacobian that evaluates points back to back
+ * (multistart LM, an ensemble sampler) keeps two evaluations in flight.  Host buffers should be pinned.                  */
+int sbm_jacobian_host_begin(sbm_plan* p, const sbm_solver_opts_t* opts, int loss_kind, int flags, long long B,
+                            const double* theta_host, double* jac_host, double* resid_host, double* ssr_host,
+                            double* grad_host, double* sf_host, double* sims_host, int* status_host,
+                            unsigned long long* counters_host, void* stream, int slot);
+int sbm_host_end(sbm_plan* p, int slot);
+
 /* ---- batched Levenberg-Marquardt step (the consumer of residuals + Jacobian) ---------------------------
  * Replaces the inner linear algebra of scipy.optimize.leastsq(proj.residuals, x0, Dfun=proj.calc_project_jacobian)
  * (reference call sites tests/test_Project.py:202-213, 351-357) for B parameter sets at once, on the device:

@@ -61,14 +61,14 @@
 #define SBM_CT_D_TK     3
 #define SBM_CT_D_TEND   4
 #define SBM_CT_D_FACOLD 5
-#define SBM_CT_ND       6
+#define SBM_CT_ND       12    /* (the lagged controller keeps a second, speculative set) */
 #define SBM_CT_I_KT     0
 #define SBM_CT_I_KT1    1
 #define SBM_CT_I_STATUS 2
 #define SBM_CT_I_MODE   3
 #define SBM_CT_I_BITS   4     /* 1 lastrej, 2 clipped, 4 refresh, 8 initf, 16 exhausted */
 #define SBM_CT_I_NSTEP  5
-#define SBM_CT_NI       8
+#define SBM_CT_NI       12
 
 // -DSBM_CT_JITTER=<n>: random delays (up to ~n x 32 ns, different in every launch, warp and call site) before every CTA
 // barrier, every block of tensor-memory transfers and every share of the model.  A missing barrier / fence between a
@@ -88,6 +88,15 @@ __device__ __forceinline__ void sbm_ct_jitter(const unsigned site)
 #define SBM_CT_BAR(nt) do { SBM_CT_JIT(1u); asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory"); } while (0)
 #ifndef SBM_CT_BUF_ARG
 #define SBM_CT_BUF_ARG 0
+#endif
+#ifndef SBM_CT_LAG
+#define SBM_CT_LAG 0
+#endif
+#ifndef SBM_CTL_SAFETY
+#define SBM_CTL_SAFETY 0.9f
+#endif
+#ifndef SBM_CTL_FACMAX
+#define SBM_CTL_FACMAX 5.0f
 #endif
 #ifndef SBM_CT_ACCEPT_AT_BEGIN
 #define SBM_CT_ACCEPT_AT_BEGIN 0
@@ -342,7 +351,14 @@ __device__ __forceinline__ void sbm_ct_sens_stage(const double h, const double* 
                                                   const bool anyinit, double& sq, double& d0, double& d1)
 {
     constexpr int N = SBM_N, NE = N + (N & 1), NP2 = NE / 2;
-    __syncwarp();                                  // tcgen05.ld/st are warp-collective: be converged (cheap insurance)
+    // tcgen05.ld / st are .sync.aligned: every thread of the warp must execute the same instruction together.  The stage
+    // follows per-lane branches (accept copy, rows of an output time, garbage of a rejected lane) after which the compiler
+    // is free to leave the warp diverged; without this reconvergence the transfers below are undefined behaviour.  That is
+    // what round 1 met as a "code-generation hazard" (results changing with the way the buffer index reached
+    // sbm_ct_primal: a different code layout left a different branch unconverged); experiment: -DSBM_WHATIF_NO_SYNCWARP.
+#ifndef SBM_WHATIF_NO_SYNCWARP
+    __syncwarp();
+#endif
     SBM_CT_JIT(2u + S);
     // Tensor-memory transfers are pipelined by hand: tcgen05.wait::ld waits for EVERY outstanding load of the thread, so
     // the vectors a row pair needs in its update (k1 in stage 4, the error accumulator from stage 5 on) are requested one
@@ -1333,6 +1349,497 @@ __device__ __forceinline__ void sbm_ct_model_warp_async(const SbmSolveArgs& a, c
     }
 }
 
+// =================================================================================================================
+// SBM_CT_LAG: lagged step-size control - the controller and the head of a step leave the critical path.
+//
+// In the synchronous schedule above a step is EIGHT barrier intervals: controller | head (model at the input of stage 2) |
+// stages 2..7, and in the first two (19 % of a step, measured) the column warps have nothing to do, because the step
+// size of step k+1 is only known once the error of step k is.  Here the step size of step k+1 is fixed BEFORE the error
+// of step k is known - from the error of step k-1 (an I-controller on a one-step-old error constant; measured on the
+// C4 distribution with a Python model of the kernel's controller: 3,051 steps per solve and 1.9 % rejections against
+// 3,162 steps and 0.3 % with the PI controller) - and the error of step k only decides whether step k is accepted:
+//
+//   interval 7 of step k    columns: stage 7 (k7, error norm)   model warp: state column of step k, set-up of step k+1
+//                                                                ASSUMING step k is accepted, model at the input of
+//                                                                stage 2 of step k+1 (speculative)
+//   interval 2 of step k+1  columns: every warp sums the partial error norms itself and decides (same arithmetic in
+//                           every warp); accepted: y <- Y7, rows of an output time, stage 2.  model warp: the same
+//                           decision, then the bookkeeping of step k (commit / reject, FSAL, step size of step k+2, output
+//                           values, trajectory queue), model at the input of stage 3
+//   intervals 3..6          as before
+//
+// A step is SIX barrier intervals.  A rejected lane turns step k+1 into the zero-length refresh step the push form needs
+// anyway (k1 of its columns was destroyed in stage 4): h = 0 for that lane; what the model warp evaluated speculatively
+// for its stage 2 belongs to the wrong state, so k2 of that lane is cleared (it only ever meets a zero coefficient).
+// The model warp owns the state column: it forms every stage value itself (the column warps no longer prepare them).
+// =================================================================================================================
+#if SBM_CT_LAG
+
+#define SBM_CTL_F_NORMAL 16           /* sh.fl: the step in flight is a normal step: its error decides */
+
+// controller state (per lane, shared memory, model warp only): [cur] describes the step in flight, [spec] what the
+// set-up computed for the next step assuming the one in flight is accepted
+#define SBM_CTL_D_T       0
+#define SBM_CTL_D_TK      1
+#define SBM_CTL_D_TEND    2
+#define SBM_CTL_D_HCUR    3
+#define SBM_CTL_D_HPROP   4           /* cruise step before clipping of the step in flight */
+#define SBM_CTL_D_HCRUISE 5
+#define SBM_CTL_D_FACOLD  6
+#define SBM_CTL_D_TS      7
+#define SBM_CTL_D_TKS     8
+#define SBM_CTL_D_HPROPS  9
+#define SBM_CTL_I_KT      0
+#define SBM_CTL_I_KT1     1
+#define SBM_CTL_I_STATUS  2
+#define SBM_CTL_I_MODE    3
+#define SBM_CTL_I_BITS    4           /* 1 lastrej, 2 clipped, 8 initf, 16 exhausted */
+#define SBM_CTL_I_NSTEP   5
+#define SBM_CTL_I_KTS     6
+#define SBM_CTL_I_MODES   7
+#define SBM_CTL_I_BITSS   8
+#define SBM_CTL_I_STATUSS 9
+
+// err^2 of the step in flight from the partial sums of the column warps and of the state column: EVERY warp runs this
+// (same loads, same order of additions), so every warp takes the same decision without a hand-over
+template <int W>
+__device__ __forceinline__ bool sbm_ctl_accepted(const SbmCtShared& sh, const int lane, const int flags, double& err2)
+{
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int w = 0; w < W; ++w) part[w & 3] += sh.sqb[w * 32 + lane];
+    const double sq = ((part[0] + part[1]) + (part[2] + part[3])) + sh.sqb[W * 32 + lane];
+    err2 = sq * (1.0 / (double)(SBM_N * (SBM_NF + 1)));
+    return !(flags & SBM_CTL_F_NORMAL) || err2 <= 1.0;                 // false for NaN
+}
+
+// ---- column warp ------------------------------------------------------------------------------------------------
+template <int W, int C, int CW, int XW>
+__device__ __forceinline__ void sbm_ctl_warp(const SbmSolveArgs& a, const SbmCtShared& sh, const int warp, const int lane)
+{
+    constexpr int N = SBM_N, NT = (W + XW) * 32, NE = N + (N & 1);
+    const int col0 = warp * C;
+    typedef SbmCtStoreTmem ST;
+    ST st;
+    st.t1 = sh.tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 4 * C * NE);
+    st.t4 = st.t1 + 2u * CW * NE;
+    double y[CW][N], s2[CW][N], s3[CW][N];
+#pragma unroll
+    for (int c = 0; c < CW; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i) { y[c][i] = 0.0; s2[c][i] = 0.0; s3[c][i] = 0.0; }
+#pragma unroll
+    for (int c = 0; c < CW; ++c)
+#pragma unroll
+        for (int ip = 0; ip < NE / 2; ++ip) { st.store(1, c * NE + 2 * ip, 0.0, 0.0); st.store(4, c * NE + 2 * ip, 0.0, 0.0); }
+    st.fence();
+    const double rtol = a.rtol, atol = a.atol;
+#ifdef SBM_CT_PROF
+    long long cbusy[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ctprev = 0;
+#endif
+    SBM_CT_BAR(NT);                                // the first set-up is published
+#ifdef SBM_CT_PROF
+    ctprev = sbm_ct_clock_after_barrier(sh.cta);
+#endif
+    for (;;) {
+        const int cflags = sh.cta[0];
+        if (!(cflags & SBM_CT_ALIVE)) break;
+        const int fl = sh.fl[lane];
+        double err2;
+        const bool acc = sbm_ctl_accepted<W>(sh, lane, fl, err2);
+        const double h = acc ? sh.hb[lane] : 0.0;  // a rejected lane: zero-length refresh step
+        int info = fl & (SBM_CT_F_POISON | SBM_CT_F_RESET);
+        if (acc && (fl & SBM_CTL_F_NORMAL)) info |= SBM_CT_F_ACCEPT;
+        if (acc && (fl & SBM_CT_F_EMIT)) info |= SBM_CT_F_EMIT;
+        sbm_ct_cols_begin<CW, ST>(a, sh, info, cflags, h, col0, lane, y, s3, st);
+#ifdef SBM_CT_PROF
+        cbusy[0] += clock64() - ctprev;
+        cbusy[8] += 1;
+#endif
+        const bool anyinit = (cflags & SBM_CT_ANYINIT) != 0;
+        double sq = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll 1
+        for (int s = 2; s <= 7; ++s) {
+            const double* Jp = sh.Jb + (s & 1) * SBM_NJS * 32 + lane;
+            const double* Gw = sh.Gd + ((s & 1) * SBM_NF + col0) * NE * 32 + 2 * lane;
+            sbm_ct_cols_stage<CW, ST>(s, info, h, Jp, 0u, Gw, y, s2, s3, st, rtol, atol, anyinit, sq, d0, d1);
+            if (s == 2 && !acc) {
+                // the model at the input of stage 2 was evaluated for the trial state of the rejected step: k2 is garbage
+#pragma unroll
+                for (int c = 0; c < CW; ++c)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) s2[c][i] = 0.0;
+            }
+            if (s == 7) {
+                sh.sqb[warp * 32 + lane] = sq;
+                if (anyinit) { sh.park[warp * 32 + lane] = d0; sh.park[(W + warp) * 32 + lane] = d1; }
+            }
+#ifdef SBM_CT_PROF
+            cbusy[s] += clock64() - ctprev;
+#endif
+            SBM_CT_BAR(NT);
+#ifdef SBM_CT_PROF
+            ctprev = sbm_ct_clock_after_barrier(sh.cta);
+#endif
+        }
+    }
+#ifdef SBM_CT_PROF
+    if (blockIdx.x == 0 && (warp == SBM_CT_PROF || warp == W - 1) && lane == 0)
+        printf("SBM_CT_PROF column warp %d busy: begin %lld s2 %lld s3 %lld s4 %lld s5 %lld s6 %lld s7 %lld\n", warp,
+               cbusy[0] / cbusy[8], cbusy[2] / cbusy[8], cbusy[3] / cbusy[8], cbusy[4] / cbusy[8], cbusy[5] / cbusy[8],
+               cbusy[6] / cbusy[8], cbusy[7] / cbusy[8]);
+#endif
+}
+
+// ---- model warp ---------------------------------------------------------------------------------------------------
+// stage value Y_S = y + h sum_j a_Sj f_j of the state column into sh.Pb (one value per state and lane), S = 3..7
+__device__ __forceinline__ void sbm_ctl_form_y(const SbmCtShared& sh, const int lane, const int S, const double h)
+{
+    double cf[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) cf[j] = sbm_dp_a[S][j];
+#pragma unroll
+    for (int i = 0; i < SBM_N; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v = fma(cf[j], sh.fh[(j * SBM_N + i) * 32 + lane], v);
+        sh.Pb[i * 32 + lane] = fma(h, v, sh.yb[i * 32 + lane]);
+    }
+}
+
+// the model at the stage value in sh.Pb -> J, G of stage S (buffer S & 1), f_S
+__device__ __forceinline__ void sbm_ctl_model(const SbmCtShared& sh, const int share, const int lane, const int S, const double ts)
+{
+    const int b = S & 1;
+    SBM_CT_JIT(16u + S);
+    sbm_primal_share<32>(share, ts, sh.Pb + lane, sh.Pb + lane, 0.0, sh.pb + lane, sh.Jb + b * SBM_NJS * 32 + lane,
+                         sh.Gd + b * SBM_NF * (SBM_N + (SBM_N & 1)) * 32 + 2 * lane, sh.fh + (S - 1) * SBM_N * 32 + lane);
+}
+
+struct SbmCtlRegs {
+    double ynew[SBM_N], f7[SBM_N];     // trial state and its derivative (the FSAL k1 of the next step) of the step in flight
+    double q0, q1;                     // start-up norms of the state column
+};
+
+// set-up of the next step, assuming the step in flight is accepted; publishes hb / fl / cta flags for the column warps
+template <int W>
+__device__ __forceinline__ void sbm_ctl_setup(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane, SbmCtlRegs& r)
+{
+    constexpr int N = SBM_N;
+    constexpr unsigned FULL = 0xffffffffu;
+    const long long ntraj = a.B * (long long)a.E;
+    unsigned long long* queue = a.counters + SBM_CNT_QUEUE;
+    const double t = sh.cd[SBM_CTL_D_T * 32 + lane], hcur = sh.cd[SBM_CTL_D_HCUR * 32 + lane];
+    const double tk = sh.cd[SBM_CTL_D_TK * 32 + lane], hcruise = sh.cd[SBM_CTL_D_HCRUISE * 32 + lane];
+    const int kt = sh.ci[SBM_CTL_I_KT * 32 + lane], kt1 = sh.ci[SBM_CTL_I_KT1 * 32 + lane];
+    const int status = sh.ci[SBM_CTL_I_STATUS * 32 + lane], mode = sh.ci[SBM_CTL_I_MODE * 32 + lane];
+    const int bits = sh.ci[SBM_CTL_I_BITS * 32 + lane];
+    const bool clipped = bits & 2, initf = bits & 8;
+    bool exhausted = bits & 16;
+
+    double ts = t, tks = tk, hs = 0.0, hprops = 0.0;
+    int kts = kt, modes = mode, statuss = status, flags = 0;
+    bool clippeds = false, initfs = false, fetched = false, landed = false;
+    long long traj = sh.trj[lane];
+    if (mode == SBM_CT_NORMAL) {
+        flags |= SBM_CTL_F_NORMAL;
+        ts = clipped ? tk : t + hcur;
+        landed = clipped;
+    } else if (mode == SBM_CT_ZERO) {
+        if (status != SBM_OK) landed = true;        // failed trajectory: flush the remaining rows as NaN, one time per step
+        else if (initf) modes = SBM_CT_ZERO;        // the step after the start-up step is a filler: h0 arrives one step late
+        else modes = SBM_CT_NORMAL;
+    } else if (!exhausted) {
+        // ---- fetch a new trajectory (warp-aggregated) ----
+        const unsigned want = __activemask();
+        const int leader = __ffs(want) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(want));
+        base = __shfl_sync(want, base, leader);
+        const long long nt = (long long)base + __popc(want & ((1u << lane) - 1u));
+        if (nt < ntraj) {
+            traj = nt;
+            fetched = true;
+            const int e = (int)(traj % a.E);
+            const long long b = traj / a.E;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { sh.yb[i * 32 + lane] = a.y0[e * N + i]; r.ynew[i] = a.y0[e * N + i]; r.f7[i] = 0.0; }
+            for (int q = 0; q < 7 * N; ++q) sh.fh[q * 32 + lane] = 0.0;
+            sh.trj[lane] = traj;
+            sh.trow[lane] = b * a.n_rows;
+            sh.ci[SBM_CTL_I_KT1 * 32 + lane] = a.tout_off[e + 1];
+            sh.ci[SBM_CTL_I_NSTEP * 32 + lane] = 0;
+            sh.cd[SBM_CTL_D_FACOLD * 32 + lane] = 1e-8;             // (1e-4)^2: the controller keeps squared errors
+            kts = a.tout_off[e];
+            ts = 0.0;
+            statuss = SBM_OK;
+            if (a.tout_off[e + 1] > kts) {
+                tks = a.tout[kts];
+                sh.cd[SBM_CTL_D_TEND * 32 + lane] = a.tout[a.tout_off[e + 1] - 1];
+                modes = SBM_CT_ZERO;
+                initfs = true;
+                flags |= SBM_CT_F_RESET;
+            } else {
+                a.status[traj] = SBM_OK;                            // no output times: nothing to integrate
+                sh.cnt[3 * 32 + lane] += 1;
+            }
+        } else {
+            exhausted = true;
+        }
+    }
+    // ---- model parameters of the new trajectories: exp(theta) for optimised, the raw value for fixed parameters
+    //      (base_project.py:343-363), gathered by the whole warp ----
+    for (unsigned need = __ballot_sync(FULL, fetched); need; need &= need - 1u) {
+        const int L = __ffs(need) - 1;
+        const long long trajL = __shfl_sync(FULL, traj, L);
+        const int e = (int)(trajL % a.E);
+        const long long b = trajL / a.E;
+        for (int m = lane; m < SBM_NP; m += 32) {
+            const int c = a.pmap[e * SBM_NP + m];
+            sh.pb[m * 32 + L] = (c >= 0) ? exp(a.theta[b * a.theta_sb + c * a.theta_sp]) : a.pfix[e * SBM_NP + m];
+            sh.pcb[m * 32 + L] = c;
+        }
+    }
+    // ---- an output time is reached (or flushed): stage its rows; the trajectory may end there ----
+    if (landed) {
+        flags |= SBM_CT_F_EMIT;
+        if (status != SBM_OK) flags |= SBM_CT_F_POISON;
+        const long long rowbase = sh.trow[lane];
+        const int r0 = __ldg(a.orow_off + kt), r1 = __ldg(a.orow_off + kt + 1);
+        sh.em_n[lane] = r1 - r0;
+        sh.ktb[lane] = kt;
+        for (int q = r0; q < r1 && q - r0 < SBM_CT_EM; ++q) {
+            const unsigned long long mask = __ldg(a.row_mask + q);
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc += ((mask >> i) & 1ull) ? r.ynew[i] : 0.0;                  // utils.py:10-26, 48-68
+            if (status != SBM_OK) acc = __longlong_as_double(0x7ff8000000000000ll);
+            sh.em_mask[(q - r0) * 32 + lane] = mask;
+            sh.em_off[(q - r0) * 32 + lane] = (rowbase + __ldg(a.row_jac + q)) * (long long)a.n_proj;
+            sh.em_soff[(q - r0) * 32 + lane] = rowbase + __ldg(a.row_sim + q);
+            sh.em_val[(q - r0) * 32 + lane] = acc;
+        }
+        kts = kt + 1;
+        if (kts >= kt1) modes = SBM_CT_IDLE;
+        else tks = __ldg(a.tout + kts);
+    }
+    // ---- step size of a normal next step: the cruise step is one step old (lagged), clipped onto the output time ----
+    if (modes == SBM_CT_NORMAL && statuss == SBM_OK) {
+        double h = hcruise;
+        hprops = h;
+        if (ts + 1.01 * h >= tks) { h = tks - ts; clippeds = true; }
+        if ((unsigned)sh.ci[SBM_CTL_I_NSTEP * 32 + lane] >= (unsigned)a.max_steps) statuss = SBM_ERR_MAXSTEPS;
+        else if (!clippeds && !(h > 1e-15 * fmax(ts, 1e-300))) statuss = SBM_ERR_UNDERFLOW;
+        if (statuss == SBM_OK) hs = h;
+        else { modes = SBM_CT_ZERO; clippeds = false; }
+    } else if (modes == SBM_CT_NORMAL) {
+        modes = SBM_CT_ZERO;                       // failed: zero-length steps that flush the rows
+    }
+    sh.hb[lane] = hs;
+    sh.fl[lane] = flags;
+    sh.cd[SBM_CTL_D_TS * 32 + lane] = ts;
+    sh.cd[SBM_CTL_D_TKS * 32 + lane] = tks;
+    sh.cd[SBM_CTL_D_HPROPS * 32 + lane] = hprops;
+    sh.ci[SBM_CTL_I_KTS * 32 + lane] = kts;
+    sh.ci[SBM_CTL_I_MODES * 32 + lane] = modes;
+    sh.ci[SBM_CTL_I_STATUSS * 32 + lane] = statuss;
+    sh.ci[SBM_CTL_I_BITSS * 32 + lane] = (clippeds ? 2 : 0) | (initfs ? 8 : 0) | (exhausted ? 16 : 0);
+    sh.ci[SBM_CTL_I_BITS * 32 + lane] = (bits & ~16) | (exhausted ? 16 : 0);
+    // a lane whose step in flight is a normal step is alive whatever the set-up assumed (the step may be rejected)
+    const bool alive = __any_sync(FULL, mode != SBM_CT_IDLE || modes != SBM_CT_IDLE) || !__all_sync(FULL, exhausted);
+    const bool anyemit = __any_sync(FULL, (flags & SBM_CT_F_EMIT) != 0);
+    const bool anyinit = __any_sync(FULL, initfs);
+    if (lane == 0)
+        sh.cta[0] = (alive ? SBM_CT_ALIVE : 0) | (anyemit ? SBM_CT_ANYEMIT : 0) | (anyinit ? SBM_CT_ANYINIT : 0);
+}
+
+// bookkeeping of the step that has just finished (its error is known now); returns the step size of the step in flight
+template <int W>
+__device__ __forceinline__ double sbm_ctl_book(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane, const SbmCtlRegs& r)
+{
+    constexpr int N = SBM_N;
+    const int flags = sh.fl[lane];
+    double err2;
+    const bool acc = sbm_ctl_accepted<W>(sh, lane, flags, err2);
+    const int mode = sh.ci[SBM_CTL_I_MODE * 32 + lane];
+    int bits = sh.ci[SBM_CTL_I_BITS * 32 + lane];
+    int status = sh.ci[SBM_CTL_I_STATUS * 32 + lane];
+    const double hcur = sh.cd[SBM_CTL_D_HCUR * 32 + lane];
+    bool commit = true;
+    if (mode == SBM_CT_NORMAL) {
+        // I-controller on the error of the step just finished; the result is the cruise step of the step AFTER the one
+        // in flight.  facold holds the SQUARE of the previous accepted error (Hairer's PI term, beta = 0.04).
+        float facold = (float)sh.cd[SBM_CTL_D_FACOLD * 32 + lane];
+        const bool finite = (err2 == err2) && (err2 < 1e300);
+        const float ferr2 = fmaxf((float)err2, 1e-37f);
+        const float e17 = __powf(ferr2, 0.5f * (0.2f - 0.04f * 0.75f));
+        float ra = fminf(SBM_CTL_FACMAX, fmaxf(0.2f, SBM_CTL_SAFETY * __fdividef(__powf(facold, 0.5f * 0.04f), e17)));
+        if (bits & 1) ra = fminf(ra, 1.0f);
+        const float rr = finite ? fmaxf(0.2f, __fdividef(SBM_CTL_SAFETY, e17)) : 0.1f;
+        double hnew = hcur * (double)(acc ? ra : rr);
+        const double hprop = sh.cd[SBM_CTL_D_HPROP * 32 + lane];
+        if (acc && (bits & 2) && hnew < hprop) hnew = hprop;         // a clipped step must not shrink the cruise step
+        sh.cd[SBM_CTL_D_HCRUISE * 32 + lane] = hnew;
+        sh.ci[SBM_CTL_I_NSTEP * 32 + lane] += 1;
+        sh.cnt[0 * 32 + lane] += 1;
+        sh.cnt[2 * 32 + lane] += acc ? 6 : 7;        // after a rejection k1 of the sensitivity columns is re-evaluated
+        if (acc) {
+            sh.cd[SBM_CTL_D_FACOLD * 32 + lane] = (double)fmaxf(ferr2, 1e-8f);
+#pragma unroll
+            for (int i = 0; i < N; ++i) { sh.yb[i * 32 + lane] = r.ynew[i]; sh.fh[i * 32 + lane] = r.f7[i]; }
+            bits &= ~1;
+        } else {
+            commit = false;
+            sh.cnt[1 * 32 + lane] += 1;
+            bits = (bits | 1) & ~(2 | 8);
+            if (!finite && hnew < 1e-300) status = SBM_ERR_NONFINITE;
+            // the stage derivatives of the rejected trial (and of the speculative stage 2) may be non-finite: they must not
+            // meet the zero coefficients of the refresh step (0 * Inf)
+#pragma unroll
+            for (int j = 1; j < 7; ++j)
+#pragma unroll
+                for (int i = 0; i < N; ++i) sh.fh[(j * N + i) * 32 + lane] = 0.0;
+            sh.ci[SBM_CTL_I_MODE * 32 + lane] = SBM_CT_ZERO;
+            sh.ci[SBM_CTL_I_BITS * 32 + lane] = bits;
+            sh.ci[SBM_CTL_I_STATUS * 32 + lane] = status;
+            sh.cd[SBM_CTL_D_HCUR * 32 + lane] = 0.0;
+        }
+    } else if (mode == SBM_CT_ZERO) {
+        // a zero-length step re-evaluated F(y) in every stage: FSAL
+#pragma unroll
+        for (int i = 0; i < N; ++i) sh.fh[i * 32 + lane] = r.f7[i];
+        if (bits & 8) {
+            // initial step size (Hairer, Norsett, Wanner II.4): h0 = 0.01 |y|/|f|; start at the rule's upper bound 100 h0
+            double q0 = r.q0, q1 = r.q1;
+#pragma unroll
+            for (int w = 0; w < W; ++w) { q0 += sh.park[w * 32 + lane]; q1 += sh.park[(W + w) * 32 + lane]; }
+            const double inv_naug = 1.0 / (double)(N * (SBM_NF + 1));
+            const double n0 = sqrt(q0 * inv_naug), n1 = sqrt(q1 * inv_naug);
+            const double h0 = (n0 < 1e-5 || n1 < 1e-5) ? 1e-6 : 0.01 * n0 / n1;
+            double h = fmin(100.0 * h0, sh.cd[SBM_CTL_D_TEND * 32 + lane]);
+            if (a.h0 > 0.0) h = fmin(a.h0, sh.cd[SBM_CTL_D_TEND * 32 + lane]);
+            sh.cd[SBM_CTL_D_HCRUISE * 32 + lane] = h;
+            sh.cnt[2 * 32 + lane] += 1;
+        }
+    }
+    if (commit) {
+        // the set-up's assumption holds: its results become the state of the step in flight
+        if (flags & SBM_CT_F_EMIT) {
+            const int n = sh.em_n[lane];
+            for (int q = 0; q < n && q < SBM_CT_EM; ++q) a.sims[sh.em_soff[q * 32 + lane]] = sh.em_val[q * 32 + lane];
+            if (n > SBM_CT_EM) {
+                const long long rowbase = sh.trow[lane];
+                const int r0 = __ldg(a.orow_off + sh.ktb[lane]);
+                for (int q = r0 + SBM_CT_EM; q < r0 + n; ++q) {
+                    const unsigned long long mask = __ldg(a.row_mask + q);
+                    double v = 0.0;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) v += ((mask >> i) & 1ull) ? sh.yb[i * 32 + lane] : 0.0;
+                    if (flags & SBM_CT_F_POISON) v = __longlong_as_double(0x7ff8000000000000ll);
+                    a.sims[rowbase + __ldg(a.row_sim + q)] = v;
+                }
+            }
+            if (sh.ci[SBM_CTL_I_MODES * 32 + lane] == SBM_CT_IDLE) {
+                a.status[sh.trj[lane]] = status;
+                sh.cnt[3 * 32 + lane] += 1;
+            }
+        }
+        const int bs = sh.ci[SBM_CTL_I_BITSS * 32 + lane];
+        sh.cd[SBM_CTL_D_T * 32 + lane] = sh.cd[SBM_CTL_D_TS * 32 + lane];
+        sh.cd[SBM_CTL_D_TK * 32 + lane] = sh.cd[SBM_CTL_D_TKS * 32 + lane];
+        sh.cd[SBM_CTL_D_HPROP * 32 + lane] = sh.cd[SBM_CTL_D_HPROPS * 32 + lane];
+        sh.cd[SBM_CTL_D_HCUR * 32 + lane] = sh.hb[lane];
+        sh.ci[SBM_CTL_I_KT * 32 + lane] = sh.ci[SBM_CTL_I_KTS * 32 + lane];
+        sh.ci[SBM_CTL_I_MODE * 32 + lane] = sh.ci[SBM_CTL_I_MODES * 32 + lane];
+        sh.ci[SBM_CTL_I_STATUS * 32 + lane] = sh.ci[SBM_CTL_I_STATUSS * 32 + lane];
+        sh.ci[SBM_CTL_I_BITS * 32 + lane] = (bits & 1) | (bs & (2 | 8 | 16));
+    }
+    return sh.cd[SBM_CTL_D_HCUR * 32 + lane];
+}
+
+template <int W, int C, int XW>
+__device__ __forceinline__ void sbm_ctl_model_warp(const SbmSolveArgs& a, const SbmCtShared& sh, const int warp, const int lane)
+{
+    constexpr int N = SBM_N, NT = (W + XW) * 32;
+    SbmCtlRegs r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { r.ynew[i] = 0.0; r.f7[i] = 0.0; }
+    r.q0 = r.q1 = 0.0;
+#ifdef SBM_CT_PROF
+    long long prof[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, busy[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+    // prologue: every lane is idle; fetch trajectories, publish the first step, model at the input of its stage 2
+    sbm_ctl_setup<W>(a, sh, lane, r);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < N; ++i) sh.Pb[i * 32 + lane] = r.ynew[i];
+    sbm_ctl_model(sh, warp, lane, 2, sh.cd[SBM_CTL_D_TS * 32 + lane]);
+    SBM_CT_BAR(NT);
+#ifdef SBM_CT_PROF
+    tprev = sbm_ct_clock_after_barrier(sh.cta);
+#endif
+    for (;;) {
+        if (!(sh.cta[0] & SBM_CT_ALIVE)) break;
+        // ---- interval 2: the error of the finished step is known ----
+        const double h = sbm_ctl_book<W>(a, sh, lane, r);
+        const double t = sh.cd[SBM_CTL_D_T * 32 + lane];
+#ifdef SBM_CT_PROF
+        prof[8] += 1;
+        busy[0] += clock64() - tprev;
+#endif
+#pragma unroll 1
+        for (int S = 3; S <= 7; ++S) {
+            sbm_ctl_form_y(sh, lane, S, h);
+            if (S == 7) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) r.ynew[i] = sh.Pb[i * 32 + lane];
+            }
+            sbm_ctl_model(sh, warp, lane, S, fma(sbm_dp_c[S], h, t));
+#ifdef SBM_CT_PROF
+            busy[S - 1] += clock64() - tprev;
+#endif
+            SBM_CT_BAR(NT);
+#ifdef SBM_CT_PROF
+            { const long long tn = sbm_ct_clock_after_barrier(sh.cta); prof[S - 1] += tn - tprev; tprev = tn; }
+#endif
+        }
+        // ---- interval 7: state column of the step in flight, set-up of the next step, model at the input of its stage 2 ----
+        {
+            double yn[N], sqs = 0.0;
+            r.q0 = r.q1 = 0.0;
+            sbm_ct_state_column(sh, lane, h, a.rtol, a.atol, yn, r.f7, sqs, r.q0, r.q1);
+            sh.sqb[W * 32 + lane] = sqs;
+        }
+        sbm_ctl_setup<W>(a, sh, lane, r);
+        __syncwarp();
+        {
+            const double hs = sh.hb[lane];
+            const int ms = sh.ci[SBM_CTL_I_MODES * 32 + lane];
+            // (a lane that has just fetched starts from y0, which the set-up put into r.ynew; its f7 is zero)
+#pragma unroll
+            for (int i = 0; i < N; ++i) sh.Pb[i * 32 + lane] = fma(hs * DP_A21, r.f7[i], r.ynew[i]);
+            (void)ms;
+            sbm_ctl_model(sh, warp, lane, 2, fma(DP_C2, hs, sh.cd[SBM_CTL_D_TS * 32 + lane]));
+        }
+#ifdef SBM_CT_PROF
+        busy[7] += clock64() - tprev;
+#endif
+        SBM_CT_BAR(NT);
+#ifdef SBM_CT_PROF
+        { const long long tn = sbm_ct_clock_after_barrier(sh.cta); prof[7] += tn - tprev; tprev = tn; }
+#endif
+    }
+#ifdef SBM_CT_PROF
+    if (blockIdx.x == 0 && lane == 0) {
+        printf("SBM_CT_PROF steps %lld clocks/step: s2 %lld s3 %lld s4 %lld s5 %lld s6 %lld s7 %lld\n", prof[8],
+               prof[2] / prof[8], prof[3] / prof[8], prof[4] / prof[8], prof[5] / prof[8], prof[6] / prof[8], prof[7] / prof[8]);
+        printf("SBM_CT_PROF model warp busy: book %lld s2 %lld s3 %lld s4 %lld s5 %lld s6 %lld s7 %lld\n", busy[0] / prof[8],
+               busy[2] / prof[8], busy[3] / prof[8], busy[4] / prof[8], busy[5] / prof[8], busy[6] / prof[8], busy[7] / prof[8]);
+    }
+#endif
+}
+#endif  /* SBM_CT_LAG */
+
 // W column warps per CTA (warps 0..W-2 carry C sensitivity columns each, warp W-1 the remaining
 // CL = NF - (W-1)*C) plus XW warps without columns.  Shared-memory carve-up in doubles (sbm_api.cu computes the same
 // size on the host):
@@ -1466,6 +1973,11 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
         else if (warp == W - 1 && CL != C) sbm_ct_warp<W, C, CL, XW>(a, sh, warp, lane);
         else sbm_ct_warp<W, C, C, XW>(a, sh, warp, lane);
     }
+#elif SBM_CT_LAG
+    static_assert(XW == 1, "the lagged controller needs the dedicated model warp");
+    if (warp >= W) sbm_ctl_model_warp<W, C, XW>(a, sh, warp, lane);
+    else if (warp == W - 1 && CL != C) sbm_ctl_warp<W, C, CL, XW>(a, sh, warp, lane);
+    else sbm_ctl_warp<W, C, C, XW>(a, sh, warp, lane);
 #else
     if (XW > 0 && warp >= W) sbm_ct_model_warp<W, C, XW>(a, sh, warp, lane);
     else if (warp == W - 1 && CL != C) sbm_ct_warp<W, C, CL, XW>(a, sh, warp, lane);

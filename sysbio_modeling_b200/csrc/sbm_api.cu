@@ -238,8 +238,8 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
         if (W >= 1 && C >= 1 && NF >= 1) {
             const int CL = NF - (W - 1) * C;
             const long long bytes = 8ll * (NB * NJ * 32 + NB * NF * (N + (N & 1)) * 32 + 16 + 7 * N * 32 + 2 * N * 32 + 2 * N * 32 + desc->n_params * 32 +
-                                           (W + 3) * 32 + 32 + 6 * 32 + 4 * 32 + 32) +
-                                    4ll * (8 * 32 + 3 * 32) + 8ll * 2 * W * 32 +
+                                           (W + 3) * 32 + 32 + 12 * 32 + 4 * 32 + 32) +
+                                    4ll * (12 * 32 + 3 * 32) + 8ll * 2 * W * 32 +
                                     8ll * (2 * 4 * 32 + 32) + 4ll * (32 + (desc->n_params + (desc->n_params & 1)) * 32) +
                                     8ll * (2 * 4 * 32 + 32) + 4ll * 32;   // rows staged ahead by the model warp: offsets, values, next time, index   // staged rows (SBM_CT_EM = 4), row base, project columns
             const int tm_need = ((W + 3) / 4) * 4 * C * (N + (N & 1)) + (JTM ? 4 * NJP : 0);
@@ -412,8 +412,6 @@ extern "C" void sbm_model_destroy(sbm_model* m)
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-#define SBM_HOST_CHUNKS_MAX 8
-
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -429,6 +427,20 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+struct HostSlot {
+    DevBuf theta, sims, jac, resid, ssr, sf, sfgrad, grad, status, counters;
+    cudaEvent_t ev_loss = nullptr, ev_copied = nullptr;
+    bool pending = false;
+    void release()
+    {
+        theta.release(); sims.release(); jac.release(); resid.release(); ssr.release(); sf.release(); sfgrad.release();
+        grad.release(); status.release(); counters.release();
+        if (ev_loss) cudaEventDestroy(ev_loss);
+        if (ev_copied) cudaEventDestroy(ev_copied);
+        ev_loss = ev_copied = nullptr;
+    }
+};
+
 struct sbm_plan {
     sbm_model* model = nullptr;
     sbm_plan_desc_t d{};
@@ -441,12 +453,8 @@ struct sbm_plan {
     bool jac_full = false;        // the integrator writes EVERY entry of jac (no memset needed before the launch)
     int sm_count = 0;
     std::mutex mu;                // the *_host entry points share the workspaces below: one call at a time per plan
-    // chunked host evaluation: two compute streams (the persistent integrator launches of consecutive chunks overlap
-    // tail-to-head), one copy stream, one event per chunk
-    cudaStream_t cs[2] = {nullptr, nullptr}, copy_stream = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_chunk[SBM_HOST_CHUNKS_MAX] = {}, ev_end[3] = {};
-    // grow-only workspaces of the *_host entry points
-    DevBuf w_theta, w_sims, w_jac, w_resid, w_ssr, w_sf, w_sfgrad, w_grad, w_status, w_counters;
+    cudaStream_t copy_stream = nullptr;      // copy-out of the *_host entry points
+    HostSlot* slots = nullptr;        // [2] grow-only workspaces of the *_host entry points
 };
 
 template <typename T>
@@ -462,17 +470,14 @@ static int upload(sbm_plan* p, T*& dst, const T* src, size_t n)
     return 0;
 }
 
+static void plan_release_slots(sbm_plan* p);
+
 extern "C" void sbm_plan_destroy(sbm_plan* p)
 {
     if (!p) return;
     for (void* q : p->owned) cudaFree(q);
-    p->w_theta.release(); p->w_sims.release(); p->w_jac.release(); p->w_resid.release(); p->w_ssr.release();
-    p->w_sf.release(); p->w_sfgrad.release(); p->w_grad.release(); p->w_status.release(); p->w_counters.release();
+    plan_release_slots(p);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
-    for (int i = 0; i < 2; ++i) if (p->cs[i]) cudaStreamDestroy(p->cs[i]);
-    if (p->ev_in) cudaEventDestroy(p->ev_in);
-    for (int i = 0; i < SBM_HOST_CHUNKS_MAX; ++i) if (p->ev_chunk[i]) cudaEventDestroy(p->ev_chunk[i]);
-    for (int i = 0; i < 3; ++i) if (p->ev_end[i]) cudaEventDestroy(p->ev_end[i]);
     delete p;
 }
 
@@ -486,6 +491,7 @@ extern "C" int sbm_plan_create(sbm_model* m, const sbm_plan_desc_t* d, sbm_plan*
     sbm_plan* p = new sbm_plan();
     p->model = m;
     p->d = *d;
+    p->slots = new HostSlot[2];
 #define UP(field, n) if ((rc = upload(p, p->field, d->field, (size_t)(n)))) { sbm_plan_destroy(p); return rc; }
     if (m) {
         const size_t NP = (size_t)m->desc.n_params, N = (size_t)m->desc.n_vars;
@@ -686,118 +692,91 @@ extern "C" int sbm_lm_step(long long B, int n_rows, int n_proj, const double* ja
 // ------------------------------------------------------------------------------------------------
 // fused host-buffer entry points
 // ------------------------------------------------------------------------------------------------
-// Chunks of a host evaluation: bounds[0..n] of n chunks.  The device-to-host copy of a large result (C4: 494 MB of scaled
-// Jacobians per 65,536 sets, ~10 ms) hides behind the integration of the chunks that follow, so the LAST chunk's copy is
-// what stays exposed: two chunks, 80 % / 20 %.  More chunks cost more than they hide - every launch of the persistent
-// integrator ends in a tail (lanes idle once its trajectory queue is empty, ~15 ms on C4) and a chunk of a few waves is
-// mostly tail (measured: 8 equal chunks 122 k solves/s end to end against 158 k serial).  The launches of consecutive
-// chunks go to two streams, so the CTAs of chunk c+1 start on the SMs chunk c's tail frees.
-// SBM_HOST_CHUNKS=n forces n equal chunks (1 = serial).
-static int host_chunks(long long B, bool with_jac, size_t out_bytes, long long* bounds)
-{
-    int n = 1;
-    bool equal = false;
-    if (const char* e = getenv("SBM_HOST_CHUNKS")) {
-        int v = atoi(e);
-        if (v >= 1 && v <= SBM_HOST_CHUNKS_MAX && (long long)v <= B) { n = v; equal = true; }
-    } else if (with_jac && out_bytes >= (64u << 20) && B >= 6 * 4736) {
-        n = 2;
-    }
-    bounds[0] = 0;
-    if (equal || n == 1) { for (int c = 1; c <= n; ++c) bounds[c] = B * c / n; }
-    else { bounds[1] = (B * 4 / 5 + 31) / 32 * 32; if (bounds[1] >= B) bounds[1] = B / 2; bounds[2] = B; }
-    return n;
-}
-
+// Host evaluations.  A call copies theta in, integrates, runs the loss epilogue and copies the results out.  On C4 the
+// copy-out is 494 MB of scaled Jacobians per 65,536 sets (~9 ms over PCIe against ~400 ms of integration).  It cannot hide
+// inside ONE call: the persistent integrator fills every SM (all registers, 150 KB of shared memory), so a second launch
+// only starts in the tail of the first, and the loss kernel of an early chunk then queues behind the next chunk's CTAs -
+// measured on C4: 2 chunks (80 % / 20 %, two streams) 155 k solves/s end to end, 8 equal chunks 122 k, serial 158 k.
+// What does hide it is the NEXT evaluation: sbm_jacobian_host_begin enqueues an evaluation on the caller's stream and its
+// copy-out on the plan's copy stream (two workspace slots), sbm_host_end waits for a slot.  An optimiser that evaluates
+// trial points back to back (or a sampler) keeps two in flight.
 static int host_eval(sbm_plan* p, const sbm_solver_opts_t* o, int loss_kind, int flags, long long B, bool with_jac,
                      const double* theta_host, double* jac_host, double* model_jac_host, double* resid_host,
                      double* ssr_host, double* grad_host, double* sf_host, double* sims_host, int* status_host,
-                     unsigned long long* counters_host, void* stream)
+                     unsigned long long* counters_host, void* stream, int slot, bool wait)
 {
     if (!p || !o || !theta_host) return fail(SBM_E_INVALID, "null argument");
     if (B <= 0) return fail(SBM_E_INVALID, "B must be positive");
+    if (slot < 0 || slot > 1) return fail(SBM_E_INVALID, "slot must be 0 or 1");
     int rc = require_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(p->mu);          // the workspaces below belong to the plan: one host call at a time
+    HostSlot& w = p->slots[slot];
+    if (w.pending) return fail(SBM_E_INVALID, "this slot still has an evaluation in flight (call sbm_host_end first)");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t R = (size_t)p->d.n_rows, P = (size_t)p->d.n_proj, Gn = (size_t)p->d.n_groups, E = (size_t)p->d.E;
     const size_t nB = (size_t)B;
-    const size_t out_bytes = nB * R * 8 * (1 + (with_jac && jac_host ? P : 0));
-    long long bounds[SBM_HOST_CHUNKS_MAX + 1];
-    int nch = host_chunks(B, with_jac, out_bytes, bounds);
-    if (model_jac_host) { nch = 1; bounds[1] = B; }
-    if (p->w_theta.ensure(nB * P * 8) || p->w_sims.ensure(nB * R * 8) || p->w_resid.ensure(nB * R * 8) ||
-        p->w_ssr.ensure(nB * 8) || p->w_sf.ensure((nB * Gn + 1) * 8) || p->w_status.ensure(nB * E * 4) ||
-        p->w_counters.ensure((size_t)SBM_HOST_CHUNKS_MAX * SBM_N_COUNTERS * 8))
+    if (w.theta.ensure(nB * P * 8) || w.sims.ensure(nB * R * 8) || w.resid.ensure(nB * R * 8) ||
+        w.ssr.ensure(nB * 8) || w.sf.ensure((nB * Gn + 1) * 8) || w.status.ensure(nB * E * 4) ||
+        w.counters.ensure(SBM_N_COUNTERS * 8))
         return fail(SBM_E_NOMEM, "device workspace allocation failed");
-    if (with_jac && (p->w_jac.ensure(nB * R * P * 8) || p->w_sfgrad.ensure((nB * Gn * P + 1) * 8) || p->w_grad.ensure(nB * P * 8)))
+    if (with_jac && (w.jac.ensure(nB * R * P * 8) || w.sfgrad.ensure((nB * Gn * P + 1) * 8) || w.grad.ensure(nB * P * 8)))
         return fail(SBM_E_NOMEM, "device workspace allocation failed (Jacobian)");
-    double* d_theta = (double*)p->w_theta.p;
-    double* d_sims = (double*)p->w_sims.p;
-    double* d_jac = with_jac ? (double*)p->w_jac.p : nullptr;
-    unsigned long long* d_cnt = (unsigned long long*)p->w_counters.p;
+    if (!p->copy_stream) RT(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    if (!w.ev_loss) {
+        RT(cudaEventCreateWithFlags(&w.ev_loss, cudaEventDisableTiming));
+        RT(cudaEventCreateWithFlags(&w.ev_copied, cudaEventDisableTiming));
+    }
+    double* d_theta = (double*)w.theta.p;
+    double* d_sims = (double*)w.sims.p;
+    double* d_jac = with_jac ? (double*)w.jac.p : nullptr;
     RT(cudaMemcpyAsync(d_theta, theta_host, nB * P * 8, cudaMemcpyHostToDevice, st));
-    RT(cudaMemsetAsync(d_cnt, 0, (size_t)SBM_HOST_CHUNKS_MAX * SBM_N_COUNTERS * 8, st));
+    RT(cudaMemsetAsync(w.counters.p, 0, SBM_N_COUNTERS * 8, st));
     RT(cudaMemsetAsync(d_sims, 0, nB * R * 8, st));
-    if (nch > 1) {
-        if (!p->copy_stream) {
-            RT(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-            for (int i = 0; i < 2; ++i) RT(cudaStreamCreateWithFlags(&p->cs[i], cudaStreamNonBlocking));
-            RT(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
-            for (int i = 0; i < SBM_HOST_CHUNKS_MAX; ++i) RT(cudaEventCreateWithFlags(&p->ev_chunk[i], cudaEventDisableTiming));
-            for (int i = 0; i < 3; ++i) RT(cudaEventCreateWithFlags(&p->ev_end[i], cudaEventDisableTiming));
-        }
-        RT(cudaEventRecord(p->ev_in, st));
-        for (int i = 0; i < 2; ++i) RT(cudaStreamWaitEvent(p->cs[i], p->ev_in, 0));
-    }
-    for (int c = 0; c < nch; ++c) {
-        const size_t lo = (size_t)bounds[c], hi = (size_t)bounds[c + 1], n = hi - lo;
-        if (!n) continue;
-        cudaStream_t s = nch > 1 ? p->cs[c & 1] : st;
-        cudaStream_t sc = nch > 1 ? p->copy_stream : st;
-        rc = sbm_solve(p, o, (long long)n, d_theta + lo * P, (long long)P, 1, d_sims + lo * R, d_jac ? d_jac + lo * R * P : nullptr,
-                       (int*)p->w_status.p + lo * E, d_cnt + (size_t)c * SBM_N_COUNTERS, s);
-        if (rc) return rc;
-        if (with_jac && model_jac_host) RT(cudaMemcpyAsync(model_jac_host, d_jac, nB * R * P * 8, cudaMemcpyDeviceToHost, s));
-        rc = sbm_loss(p, loss_kind, flags, (long long)n, d_theta + lo * P, (long long)P, 1, d_sims + lo * R,
-                      d_jac ? d_jac + lo * R * P : nullptr, (double*)p->w_resid.p + lo * R, (double*)p->w_ssr.p + lo,
-                      (double*)p->w_sf.p + lo * Gn, with_jac ? (double*)p->w_sfgrad.p + lo * Gn * P : nullptr,
-                      with_jac ? (double*)p->w_grad.p + lo * P : nullptr, s);
-        if (rc) return rc;
-        if (nch > 1) {
-            RT(cudaEventRecord(p->ev_chunk[c], s));
-            RT(cudaStreamWaitEvent(sc, p->ev_chunk[c], 0));
-        }
-        if (with_jac && jac_host) RT(cudaMemcpyAsync(jac_host + lo * R * P, d_jac + lo * R * P, n * R * P * 8, cudaMemcpyDeviceToHost, sc));
-        if (resid_host) RT(cudaMemcpyAsync(resid_host + lo * R, (double*)p->w_resid.p + lo * R, n * R * 8, cudaMemcpyDeviceToHost, sc));
-        if (sims_host) RT(cudaMemcpyAsync(sims_host + lo * R, d_sims + lo * R, n * R * 8, cudaMemcpyDeviceToHost, sc));
-    }
-    // small results in one piece, after everything
-    cudaStream_t sc = nch > 1 ? p->copy_stream : st;
-    if (nch > 1) {
-        // the copy stream already waits for every chunk; the caller's stream waits for all three internal streams
-        for (int i = 0; i < 2; ++i) { RT(cudaEventRecord(p->ev_end[i], p->cs[i])); RT(cudaStreamWaitEvent(sc, p->ev_end[i], 0)); }
-    }
-    if (ssr_host) RT(cudaMemcpyAsync(ssr_host, p->w_ssr.p, nB * 8, cudaMemcpyDeviceToHost, sc));
-    if (sf_host && Gn) RT(cudaMemcpyAsync(sf_host, p->w_sf.p, nB * Gn * 8, cudaMemcpyDeviceToHost, sc));
-    if (status_host) RT(cudaMemcpyAsync(status_host, p->w_status.p, nB * E * 4, cudaMemcpyDeviceToHost, sc));
-    if (with_jac && grad_host) RT(cudaMemcpyAsync(grad_host, p->w_grad.p, nB * P * 8, cudaMemcpyDeviceToHost, sc));
-    unsigned long long cnt_h[SBM_HOST_CHUNKS_MAX * SBM_N_COUNTERS];
-    if (counters_host) RT(cudaMemcpyAsync(cnt_h, d_cnt, sizeof cnt_h, cudaMemcpyDeviceToHost, sc));
-    if (nch > 1) {
-        RT(cudaEventRecord(p->ev_end[2], sc));
-        RT(cudaStreamWaitEvent(st, p->ev_end[2], 0));
-        RT(cudaStreamSynchronize(sc));
-    }
-    RT(cudaStreamSynchronize(st));
-    if (counters_host) {
-        for (int k = 0; k < SBM_N_COUNTERS; ++k) {
-            unsigned long long v = 0;
-            for (int c = 0; c < nch; ++c) v += cnt_h[c * SBM_N_COUNTERS + k];
-            counters_host[k] = v;
-        }
+    rc = sbm_solve(p, o, B, d_theta, (long long)P, 1, d_sims, d_jac, (int*)w.status.p, (unsigned long long*)w.counters.p, stream);
+    if (rc) return rc;
+    if (with_jac && model_jac_host) RT(cudaMemcpyAsync(model_jac_host, d_jac, nB * R * P * 8, cudaMemcpyDeviceToHost, st));
+    rc = sbm_loss(p, loss_kind, flags, B, d_theta, (long long)P, 1, d_sims, d_jac, (double*)w.resid.p, (double*)w.ssr.p,
+                  (double*)w.sf.p, with_jac ? (double*)w.sfgrad.p : nullptr, with_jac ? (double*)w.grad.p : nullptr, stream);
+    if (rc) return rc;
+    // copy-out on the plan's copy stream: the caller's stream is free for the next evaluation (other slot)
+    RT(cudaEventRecord(w.ev_loss, st));
+    cudaStream_t sc = p->copy_stream;
+    RT(cudaStreamWaitEvent(sc, w.ev_loss, 0));
+    if (with_jac && jac_host) RT(cudaMemcpyAsync(jac_host, d_jac, nB * R * P * 8, cudaMemcpyDeviceToHost, sc));
+    if (resid_host) RT(cudaMemcpyAsync(resid_host, w.resid.p, nB * R * 8, cudaMemcpyDeviceToHost, sc));
+    if (sims_host) RT(cudaMemcpyAsync(sims_host, d_sims, nB * R * 8, cudaMemcpyDeviceToHost, sc));
+    if (ssr_host) RT(cudaMemcpyAsync(ssr_host, w.ssr.p, nB * 8, cudaMemcpyDeviceToHost, sc));
+    if (sf_host && Gn) RT(cudaMemcpyAsync(sf_host, w.sf.p, nB * Gn * 8, cudaMemcpyDeviceToHost, sc));
+    if (status_host) RT(cudaMemcpyAsync(status_host, w.status.p, nB * E * 4, cudaMemcpyDeviceToHost, sc));
+    if (with_jac && grad_host) RT(cudaMemcpyAsync(grad_host, w.grad.p, nB * P * 8, cudaMemcpyDeviceToHost, sc));
+    if (counters_host) RT(cudaMemcpyAsync(counters_host, w.counters.p, SBM_N_COUNTERS * 8, cudaMemcpyDeviceToHost, sc));
+    RT(cudaEventRecord(w.ev_copied, sc));
+    w.pending = true;
+    if (wait) {
+        RT(cudaEventSynchronize(w.ev_copied));
+        w.pending = false;
     }
     return 0;
+}
+
+extern "C" int sbm_host_end(sbm_plan* p, int slot)
+{
+    if (!p || slot < 0 || slot > 1) return fail(SBM_E_INVALID, "sbm_host_end: bad argument");
+    std::lock_guard<std::mutex> lk(p->mu);
+    HostSlot& w = p->slots[slot];
+    if (!w.pending) return 0;
+    RT(cudaEventSynchronize(w.ev_copied));
+    w.pending = false;
+    return 0;
+}
+
+static void plan_release_slots(sbm_plan* p)
+{
+    if (!p->slots) return;
+    for (int i = 0; i < 2; ++i) p->slots[i].release();
+    delete[] p->slots;
+    p->slots = nullptr;
 }
 
 extern "C" int sbm_residuals_host(sbm_plan* p, const sbm_solver_opts_t* opts, int loss_kind, long long B,
@@ -805,7 +784,16 @@ extern "C" int sbm_residuals_host(sbm_plan* p, const sbm_solver_opts_t* opts, in
                                   double* sims_host, int* status_host, unsigned long long* counters_host, void* stream)
 {
     return host_eval(p, opts, loss_kind, 0, B, false, theta_host, nullptr, nullptr, resid_host, ssr_host, nullptr, sf_host,
-                     sims_host, status_host, counters_host, stream);
+                     sims_host, status_host, counters_host, stream, 0, true);
+}
+
+extern "C" int sbm_jacobian_host_begin(sbm_plan* p, const sbm_solver_opts_t* opts, int loss_kind, int flags, long long B,
+                                       const double* theta_host, double* jac_host, double* resid_host, double* ssr_host,
+                                       double* grad_host, double* sf_host, double* sims_host, int* status_host,
+                                       unsigned long long* counters_host, void* stream, int slot)
+{
+    return host_eval(p, opts, loss_kind, flags, B, true, theta_host, jac_host, nullptr, resid_host, ssr_host, grad_host,
+                     sf_host, sims_host, status_host, counters_host, stream, slot, false);
 }
 
 extern "C" int sbm_jacobian_host(sbm_plan* p, const sbm_solver_opts_t* opts, int loss_kind, int flags, long long B,
@@ -814,7 +802,7 @@ extern "C" int sbm_jacobian_host(sbm_plan* p, const sbm_solver_opts_t* opts, int
                                  unsigned long long* counters_host, void* stream)
 {
     return host_eval(p, opts, loss_kind, flags, B, true, theta_host, jac_host, model_jac_host, resid_host, ssr_host, grad_host,
-                     sf_host, sims_host, status_host, counters_host, stream);
+                     sf_host, sims_host, status_host, counters_host, stream, 0, true);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -965,6 +965,11 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     if 'SBM_CT_JTM' in _os.environ:
         jtm = int(_os.environ['SBM_CT_JTM']) if jtm_ok else 0
     L.append('#define SBM_CT_JTM %d' % jtm)
+    # lagged step-size control (csrc/kernels/sbm_dp5_ct.cuh, SBM_CT_LAG): needs the model warp with the whole model in one share
+    lag = 1 if (XW_ct == 1 and n_sh == 1 and not regv and not asyn and not jtm) else 0
+    if 'SBM_CT_LAG' in _os.environ:
+        lag = int(_os.environ['SBM_CT_LAG']) if lag else 0
+    L.append('#define SBM_CT_LAG %d' % lag)
     L.append('#if SBM_CT_JTM')
     L.append('#define SBM_JPOS(q, qp) ((((qp) >> 1) * 64) + ((qp) & 1))')
     L.append('#else')

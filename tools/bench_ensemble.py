@@ -28,17 +28,20 @@ exps = [sb.Experiment('EGF_stimulation',
                       initial_conditions=mod.initial_conditions)]
 proj = sb.Project(om, exps, {}, {'ERKPP': ('direct', 24), 'RasT': ('direct', 16)})
 th0 = np.log(nominal)
-# a diagonal stand-in for the Hessian keeps the set-up cheap: (the real J^T J needs the sensitivity kernel of a 25-state,
-# 52-parameter model, which the CTA-transposed layout does not cover yet)
-hess = np.eye(len(th0)) * 2.0e4
-ensembles.ensemble_log_params_batch(proj, th0, hess=hess, steps=1, n_walkers=1024, seeds=1)      # warm-up
+# the sampling matrix comes from the Gauss-Newton Hessian J^T J of the scaled Jacobian at the starting point (reference
+# Ensembles.py:226-258): one sensitivity solve of the 25-state, 52-parameter model (1,325 augmented states, warp-group kernel);
+# singular values below 1e-6 of the largest are raised to it (the reference's sing_val_cutoff)
+J0 = proj.jacobian_batch(th0[None, :])['jac'][0]
+hess = J0.T.dot(J0)
+CUTOFF = 1e-6
+ensembles.ensemble_log_params_batch(proj, th0, hess=hess, steps=1, n_walkers=1024, seeds=1, sing_val_cutoff=CUTOFF)      # warm-up
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.time()
 # independent walkers: every rank runs its own shard with its own random stream, no data-path collective
 ens, fes, ratio = ensembles.ensemble_log_params_batch(proj, th0, hess=hess, steps=steps, n_walkers=W, seeds=2 + rank,
-                                                      skip_elems=steps - 1)
+                                                      skip_elems=steps - 1, sing_val_cutoff=CUTOFF)
 torch.cuda.synchronize()
 dt = torch.tensor([time.time() - t0], dtype=torch.float64, device='cuda')
 acc = torch.tensor([float(ratio.mean())], dtype=torch.float64, device='cuda')
