@@ -98,6 +98,11 @@ __device__ __forceinline__ void sbm_ct_jitter(const unsigned site)
 #ifndef SBM_CTL_FACMAX
 #define SBM_CTL_FACMAX 5.0f
 #endif
+#ifndef SBM_CTL_BOOK_WARP
+#define SBM_CTL_BOOK_WARP 0          /* column warp that runs part B of the bookkeeping (a scheduler without the model warp) */
+#endif
+#define SBM_CTL_TAB_T 64
+#define SBM_CTL_TAB_R 128
 #ifndef SBM_CT_ACCEPT_AT_BEGIN
 #define SBM_CT_ACCEPT_AT_BEGIN 0
 #endif
@@ -1413,6 +1418,9 @@ __device__ __forceinline__ bool sbm_ctl_accepted(const SbmCtShared& sh, const in
     return !(flags & SBM_CTL_F_NORMAL) || err2 <= 1.0;                 // false for NaN
 }
 
+template <int W>
+__device__ __forceinline__ void sbm_ctl_book_b(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane);
+
 // ---- column warp ------------------------------------------------------------------------------------------------
 template <int W, int C, int CW, int XW>
 __device__ __forceinline__ void sbm_ctl_warp(const SbmSolveArgs& a, const SbmCtShared& sh, const int warp, const int lane)
@@ -1474,6 +1482,7 @@ __device__ __forceinline__ void sbm_ctl_warp(const SbmSolveArgs& a, const SbmCtS
                 sh.sqb[warp * 32 + lane] = sq;
                 if (anyinit) { sh.park[warp * 32 + lane] = d0; sh.park[(W + warp) * 32 + lane] = d1; }
             }
+            if (s == 3 && warp == SBM_CTL_BOOK_WARP) sbm_ctl_book_b<W>(a, sh, lane);
 #ifdef SBM_CT_PROF
             cbusy[s] += clock64() - ctprev;
 #endif
@@ -1605,23 +1614,18 @@ __device__ __forceinline__ void sbm_ctl_setup(const SbmSolveArgs& a, const SbmCt
         flags |= SBM_CT_F_EMIT;
         if (status != SBM_OK) flags |= SBM_CT_F_POISON;
         const long long rowbase = sh.trow[lane];
-        const int r0 = __ldg(a.orow_off + kt), r1 = __ldg(a.orow_off + kt + 1);
+        const int r0 = a.orow_off[kt], r1 = a.orow_off[kt + 1];
         sh.em_n[lane] = r1 - r0;
         sh.ktb[lane] = kt;
         for (int q = r0; q < r1 && q - r0 < SBM_CT_EM; ++q) {
-            const unsigned long long mask = __ldg(a.row_mask + q);
-            double acc = 0.0;
-#pragma unroll
-            for (int i = 0; i < N; ++i) acc += ((mask >> i) & 1ull) ? r.ynew[i] : 0.0;                  // utils.py:10-26, 48-68
-            if (status != SBM_OK) acc = __longlong_as_double(0x7ff8000000000000ll);
+            const unsigned long long mask = a.row_mask[q];
             sh.em_mask[(q - r0) * 32 + lane] = mask;
-            sh.em_off[(q - r0) * 32 + lane] = (rowbase + __ldg(a.row_jac + q)) * (long long)a.n_proj;
-            sh.em_soff[(q - r0) * 32 + lane] = rowbase + __ldg(a.row_sim + q);
-            sh.em_val[(q - r0) * 32 + lane] = acc;
+            sh.em_off[(q - r0) * 32 + lane] = (rowbase + a.row_jac[q]) * (long long)a.n_proj;
+            sh.em_soff[(q - r0) * 32 + lane] = rowbase + a.row_sim[q];
         }
         kts = kt + 1;
         if (kts >= kt1) modes = SBM_CT_IDLE;
-        else tks = __ldg(a.tout + kts);
+        else tks = a.tout[kts];
     }
     // ---- step size of a normal next step: the cruise step is one step old (lagged), clipped onto the output time ----
     if (modes == SBM_CT_NORMAL && statuss == SBM_OK) {
@@ -1653,9 +1657,40 @@ __device__ __forceinline__ void sbm_ctl_setup(const SbmSolveArgs& a, const SbmCt
         sh.cta[0] = (alive ? SBM_CT_ALIVE : 0) | (anyemit ? SBM_CT_ANYEMIT : 0) | (anyinit ? SBM_CT_ANYINIT : 0);
 }
 
-// bookkeeping of the step that has just finished (its error is known now); returns the step size of the step in flight
+// Bookkeeping of the step that has just finished (its error is known now), in two parts.  Part A is what the model warp
+// needs before it can evaluate the model at the input of stage 3: the decision, the state column's commit (or the clean-up
+// after a rejection), the step size of the step in flight.  Part B - the controller arithmetic, the output values, the
+// trajectory's bookkeeping - is only needed by the next set-up: column warp 0 runs it in interval 3, where the column
+// warps wait for the model warp anyway (measured: 1.4 k clocks of column work against 2.4 k of the model warp).
 template <int W>
-__device__ __forceinline__ double sbm_ctl_book(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane, const SbmCtlRegs& r)
+__device__ __forceinline__ double sbm_ctl_book_a(const SbmCtShared& sh, const int lane, const SbmCtlRegs& r, double& t)
+{
+    constexpr int N = SBM_N;
+    const int flags = sh.fl[lane];
+    double err2;
+    const bool acc = sbm_ctl_accepted<W>(sh, lane, flags, err2);
+    const int mode = sh.ci[SBM_CTL_I_MODE * 32 + lane];
+    if (mode == SBM_CT_NORMAL && !acc) {
+        // the stage derivatives of the rejected trial (and of the speculative stage 2) may be non-finite: they must not
+        // meet the zero coefficients of the refresh step (0 * Inf)
+#pragma unroll
+        for (int j = 1; j < 7; ++j)
+#pragma unroll
+            for (int i = 0; i < N; ++i) sh.fh[(j * N + i) * 32 + lane] = 0.0;
+    } else if (mode != SBM_CT_IDLE) {
+        // accepted step: y <- trial state; accepted or zero-length step: FSAL, k1 <- k7
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (mode == SBM_CT_NORMAL) sh.yb[i * 32 + lane] = r.ynew[i];
+            sh.fh[i * 32 + lane] = r.f7[i];
+        }
+    }
+    t = acc ? sh.cd[SBM_CTL_D_TS * 32 + lane] : sh.cd[SBM_CTL_D_T * 32 + lane];
+    return acc ? sh.hb[lane] : 0.0;
+}
+
+template <int W>
+__device__ __forceinline__ void sbm_ctl_book_b(const SbmSolveArgs& a, const SbmCtShared& sh, const int lane)
 {
     constexpr int N = SBM_N;
     const int flags = sh.fl[lane];
@@ -1685,42 +1720,29 @@ __device__ __forceinline__ double sbm_ctl_book(const SbmSolveArgs& a, const SbmC
         sh.cnt[2 * 32 + lane] += acc ? 6 : 7;        // after a rejection k1 of the sensitivity columns is re-evaluated
         if (acc) {
             sh.cd[SBM_CTL_D_FACOLD * 32 + lane] = (double)fmaxf(ferr2, 1e-8f);
-#pragma unroll
-            for (int i = 0; i < N; ++i) { sh.yb[i * 32 + lane] = r.ynew[i]; sh.fh[i * 32 + lane] = r.f7[i]; }
             bits &= ~1;
         } else {
             commit = false;
             sh.cnt[1 * 32 + lane] += 1;
             bits = (bits | 1) & ~(2 | 8);
             if (!finite && hnew < 1e-300) status = SBM_ERR_NONFINITE;
-            // the stage derivatives of the rejected trial (and of the speculative stage 2) may be non-finite: they must not
-            // meet the zero coefficients of the refresh step (0 * Inf)
-#pragma unroll
-            for (int j = 1; j < 7; ++j)
-#pragma unroll
-                for (int i = 0; i < N; ++i) sh.fh[(j * N + i) * 32 + lane] = 0.0;
             sh.ci[SBM_CTL_I_MODE * 32 + lane] = SBM_CT_ZERO;
             sh.ci[SBM_CTL_I_BITS * 32 + lane] = bits;
             sh.ci[SBM_CTL_I_STATUS * 32 + lane] = status;
             sh.cd[SBM_CTL_D_HCUR * 32 + lane] = 0.0;
         }
-    } else if (mode == SBM_CT_ZERO) {
-        // a zero-length step re-evaluated F(y) in every stage: FSAL
+    } else if (mode == SBM_CT_ZERO && (bits & 8)) {
+        // initial step size (Hairer, Norsett, Wanner II.4): h0 = 0.01 |y|/|f|; start at the rule's upper bound 100 h0
+        double q0 = sh.sqb[(W + 1) * 32 + lane], q1 = sh.sqb[(W + 2) * 32 + lane];
 #pragma unroll
-        for (int i = 0; i < N; ++i) sh.fh[i * 32 + lane] = r.f7[i];
-        if (bits & 8) {
-            // initial step size (Hairer, Norsett, Wanner II.4): h0 = 0.01 |y|/|f|; start at the rule's upper bound 100 h0
-            double q0 = r.q0, q1 = r.q1;
-#pragma unroll
-            for (int w = 0; w < W; ++w) { q0 += sh.park[w * 32 + lane]; q1 += sh.park[(W + w) * 32 + lane]; }
-            const double inv_naug = 1.0 / (double)(N * (SBM_NF + 1));
-            const double n0 = sqrt(q0 * inv_naug), n1 = sqrt(q1 * inv_naug);
-            const double h0 = (n0 < 1e-5 || n1 < 1e-5) ? 1e-6 : 0.01 * n0 / n1;
-            double h = fmin(100.0 * h0, sh.cd[SBM_CTL_D_TEND * 32 + lane]);
-            if (a.h0 > 0.0) h = fmin(a.h0, sh.cd[SBM_CTL_D_TEND * 32 + lane]);
-            sh.cd[SBM_CTL_D_HCRUISE * 32 + lane] = h;
-            sh.cnt[2 * 32 + lane] += 1;
-        }
+        for (int w = 0; w < W; ++w) { q0 += sh.park[w * 32 + lane]; q1 += sh.park[(W + w) * 32 + lane]; }
+        const double inv_naug = 1.0 / (double)(N * (SBM_NF + 1));
+        const double n0 = sqrt(q0 * inv_naug), n1 = sqrt(q1 * inv_naug);
+        const double h0 = (n0 < 1e-5 || n1 < 1e-5) ? 1e-6 : 0.01 * n0 / n1;
+        double h = fmin(100.0 * h0, sh.cd[SBM_CTL_D_TEND * 32 + lane]);
+        if (a.h0 > 0.0) h = fmin(a.h0, sh.cd[SBM_CTL_D_TEND * 32 + lane]);
+        sh.cd[SBM_CTL_D_HCRUISE * 32 + lane] = h;
+        sh.cnt[2 * 32 + lane] += 1;
     }
     if (commit) {
         // the set-up's assumption holds: its results become the state of the step in flight
@@ -1729,14 +1751,14 @@ __device__ __forceinline__ double sbm_ctl_book(const SbmSolveArgs& a, const SbmC
             for (int q = 0; q < n && q < SBM_CT_EM; ++q) a.sims[sh.em_soff[q * 32 + lane]] = sh.em_val[q * 32 + lane];
             if (n > SBM_CT_EM) {
                 const long long rowbase = sh.trow[lane];
-                const int r0 = __ldg(a.orow_off + sh.ktb[lane]);
+                const int r0 = a.orow_off[sh.ktb[lane]];
                 for (int q = r0 + SBM_CT_EM; q < r0 + n; ++q) {
-                    const unsigned long long mask = __ldg(a.row_mask + q);
+                    const unsigned long long mask = a.row_mask[q];
                     double v = 0.0;
 #pragma unroll
                     for (int i = 0; i < N; ++i) v += ((mask >> i) & 1ull) ? sh.yb[i * 32 + lane] : 0.0;
                     if (flags & SBM_CT_F_POISON) v = __longlong_as_double(0x7ff8000000000000ll);
-                    a.sims[rowbase + __ldg(a.row_sim + q)] = v;
+                    a.sims[rowbase + a.row_sim[q]] = v;
                 }
             }
             if (sh.ci[SBM_CTL_I_MODES * 32 + lane] == SBM_CT_IDLE) {
@@ -1754,7 +1776,24 @@ __device__ __forceinline__ double sbm_ctl_book(const SbmSolveArgs& a, const SbmC
         sh.ci[SBM_CTL_I_STATUS * 32 + lane] = sh.ci[SBM_CTL_I_STATUSS * 32 + lane];
         sh.ci[SBM_CTL_I_BITS * 32 + lane] = (bits & 1) | (bs & (2 | 8 | 16));
     }
-    return sh.cd[SBM_CTL_D_HCUR * 32 + lane];
+}
+
+// values of the rows of an output time the step in flight lands on, from its trial state (their masks were staged by the
+// set-up, which runs before the trial state exists)
+__device__ __forceinline__ void sbm_ctl_stage_values(const SbmCtShared& sh, const int lane, const SbmCtlRegs& r)
+{
+    const int flags = sh.fl[lane];
+    if (flags & SBM_CT_F_EMIT) {
+        const int n = sh.em_n[lane];
+        for (int q = 0; q < n && q < SBM_CT_EM; ++q) {
+            const unsigned long long mask = sh.em_mask[q * 32 + lane];
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < SBM_N; ++i) acc += ((mask >> i) & 1ull) ? r.ynew[i] : 0.0;                  // utils.py:10-26, 48-68
+            if (flags & SBM_CT_F_POISON) acc = __longlong_as_double(0x7ff8000000000000ll);
+            sh.em_val[q * 32 + lane] = acc;
+        }
+    }
 }
 
 template <int W, int C, int XW>
@@ -1781,8 +1820,8 @@ __device__ __forceinline__ void sbm_ctl_model_warp(const SbmSolveArgs& a, const 
     for (;;) {
         if (!(sh.cta[0] & SBM_CT_ALIVE)) break;
         // ---- interval 2: the error of the finished step is known ----
-        const double h = sbm_ctl_book<W>(a, sh, lane, r);
-        const double t = sh.cd[SBM_CTL_D_T * 32 + lane];
+        double t;
+        const double h = sbm_ctl_book_a<W>(sh, lane, r, t);
 #ifdef SBM_CT_PROF
         prof[8] += 1;
         busy[0] += clock64() - tprev;
@@ -1795,6 +1834,9 @@ __device__ __forceinline__ void sbm_ctl_model_warp(const SbmSolveArgs& a, const 
                 for (int i = 0; i < N; ++i) r.ynew[i] = sh.Pb[i * 32 + lane];
             }
             sbm_ctl_model(sh, warp, lane, S, fma(sbm_dp_c[S], h, t));
+            // interval 4 is bound by the column warps (the conversion of k1..k4): the set-up of the next step fits here -
+            // column warp 0 finished the bookkeeping of the previous step in interval 3
+            if (S == 5) sbm_ctl_setup<W>(a, sh, lane, r);
 #ifdef SBM_CT_PROF
             busy[S - 1] += clock64() - tprev;
 #endif
@@ -1803,22 +1845,22 @@ __device__ __forceinline__ void sbm_ctl_model_warp(const SbmSolveArgs& a, const 
             { const long long tn = sbm_ct_clock_after_barrier(sh.cta); prof[S - 1] += tn - tprev; tprev = tn; }
 #endif
         }
-        // ---- interval 7: state column of the step in flight, set-up of the next step, model at the input of its stage 2 ----
+        // ---- interval 7: error of the state column, values of the rows of an output time, model at the input of stage 2 of
+        //      the next step (speculative: assumes that the step in flight is accepted) ----
         {
             double yn[N], sqs = 0.0;
             r.q0 = r.q1 = 0.0;
             sbm_ct_state_column(sh, lane, h, a.rtol, a.atol, yn, r.f7, sqs, r.q0, r.q1);
             sh.sqb[W * 32 + lane] = sqs;
+            sh.sqb[(W + 1) * 32 + lane] = r.q0;
+            sh.sqb[(W + 2) * 32 + lane] = r.q1;
         }
-        sbm_ctl_setup<W>(a, sh, lane, r);
-        __syncwarp();
+        sbm_ctl_stage_values(sh, lane, r);
         {
             const double hs = sh.hb[lane];
-            const int ms = sh.ci[SBM_CTL_I_MODES * 32 + lane];
-            // (a lane that has just fetched starts from y0, which the set-up put into r.ynew; its f7 is zero)
+            // (a lane that has just fetched starts from y0: its committed state, which the stage value of stage 7 repeats)
 #pragma unroll
             for (int i = 0; i < N; ++i) sh.Pb[i * 32 + lane] = fma(hs * DP_A21, r.f7[i], r.ynew[i]);
-            (void)ms;
             sbm_ctl_model(sh, warp, lane, 2, fma(DP_C2, hs, sh.cd[SBM_CTL_D_TS * 32 + lane]));
         }
 #ifdef SBM_CT_PROF
@@ -1975,9 +2017,23 @@ __device__ __forceinline__ void sbm_dp5_ct_impl(const SbmSolveArgs& a)
     }
 #elif SBM_CT_LAG
     static_assert(XW == 1, "the lagged controller needs the dedicated model warp");
-    if (warp >= W) sbm_ctl_model_warp<W, C, XW>(a, sh, warp, lane);
-    else if (warp == W - 1 && CL != C) sbm_ctl_warp<W, C, CL, XW>(a, sh, warp, lane);
-    else sbm_ctl_warp<W, C, C, XW>(a, sh, warp, lane);
+    // The tables of a small plan (output times, rows of every output time: C4 has 20 times x 2 rows) are staged in shared
+    // memory: the set-up of a step that lands on an output time walks orow_off -> row_mask / row_sim / row_jac -> tout, three
+    // dependent loads that cost the model warp - the critical path of the CTA - an L2 round trip each.
+    __shared__ double t_tout[SBM_CTL_TAB_T];
+    __shared__ unsigned long long t_mask[SBM_CTL_TAB_R];
+    __shared__ int t_orow_off[SBM_CTL_TAB_T + 2], t_rsim[SBM_CTL_TAB_R], t_rjac[SBM_CTL_TAB_R];
+    SbmSolveArgs al = a;
+    if (a.n_tout <= SBM_CTL_TAB_T && a.n_orow <= SBM_CTL_TAB_R) {
+        for (int q = threadIdx.x; q < a.n_tout; q += WT * 32) t_tout[q] = a.tout[q];
+        for (int q = threadIdx.x; q <= a.n_tout; q += WT * 32) t_orow_off[q] = a.orow_off[q];
+        for (int q = threadIdx.x; q < a.n_orow; q += WT * 32) { t_mask[q] = a.row_mask[q]; t_rsim[q] = a.row_sim[q]; t_rjac[q] = a.row_jac[q]; }
+        al.tout = t_tout; al.orow_off = t_orow_off; al.row_mask = t_mask; al.row_sim = t_rsim; al.row_jac = t_rjac;
+        SBM_CT_BAR(WT * 32);
+    }
+    if (warp >= W) sbm_ctl_model_warp<W, C, XW>(al, sh, warp, lane);
+    else if (warp == W - 1 && CL != C) sbm_ctl_warp<W, C, CL, XW>(al, sh, warp, lane);
+    else sbm_ctl_warp<W, C, C, XW>(al, sh, warp, lane);
 #else
     if (XW > 0 && warp >= W) sbm_ct_model_warp<W, C, XW>(a, sh, warp, lane);
     else if (warp == W - 1 && CL != C) sbm_ct_warp<W, C, CL, XW>(a, sh, warp, lane);

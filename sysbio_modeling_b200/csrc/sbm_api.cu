@@ -451,6 +451,7 @@ struct sbm_plan {
     unsigned long long* row_mask = nullptr;
     std::vector<void*> owned;
     bool jac_full = false;        // the integrator writes EVERY entry of jac (no memset needed before the launch)
+    int n_grp_rows = 0;           // length of grp_rows
     int sm_count = 0;
     std::mutex mu;                // the *_host entry points share the workspaces below: one call at a time per plan
     cudaStream_t copy_stream = nullptr;      // copy-out of the *_host entry points
@@ -505,6 +506,7 @@ extern "C" int sbm_plan_create(sbm_model* m, const sbm_plan_desc_t* d, sbm_plan*
         // grp_off is a host array: read its last entry for the size of grp_rows
         int n_gr = d->n_groups > 0 ? d->grp_off[d->n_groups] : 0;
         UP(grp_rows, n_gr)
+        p->n_grp_rows = n_gr;
     }
 #undef UP
     {
@@ -565,6 +567,7 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
     a.jac_raw = o->jac_raw;
     if (o->jac_raw && jac && p->d.n_proj != m->desc.n_free) return fail(SBM_E_INVALID, "jac_raw needs a plan with n_proj == n_free");
     a.rtol = o->rtol; a.atol = o->atol; a.h0 = o->h0;
+    a.n_tout = p->d.n_tout; a.n_orow = p->d.n_orow;
 
     // (pmap of a fixed model parameter is -1, so a column is "covered" only through a free parameter; with jac_raw the
     //  columns are the model's free parameters themselves)
@@ -623,7 +626,7 @@ static int loss_common(sbm_plan* p, int loss_kind, int flags, int phase, long lo
     a.sims = sims; a.jac = jac; a.resid = resid; a.ssr = ssr; a.sf = sf; a.sfgrad = sfgrad; a.grad = grad; a.sums = sums;
     a.B = B; a.n_rows = p->d.n_rows; a.n_proj = p->d.n_proj; a.n_groups = p->d.n_groups;
     a.loss_kind = loss_kind; a.flags = flags; a.phase = phase;
-    RT(sbm_launch_loss(a, (cudaStream_t)stream, p->sm_count));
+    RT(sbm_launch_loss(a, (cudaStream_t)stream, p->sm_count, p->n_grp_rows));
     return 0;
 }
 

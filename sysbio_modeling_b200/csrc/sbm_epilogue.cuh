@@ -161,31 +161,53 @@ __device__ __forceinline__ void sbm_tma_store(void* dst_gmem, const void* src_sm
 }
 
 // =================================================================================================================
-// warp-per-set kernel.  Dynamic shared memory per warp (doubles): 2 * tile | sims[n_rows] | resid[n_rows] | w1[n_rows] |
-// w2[n_rows] | meta[n_rows] (ints in double slots) | sf[G] | p1[G] | p2[G] | sfgrad[G * n_proj] ; then 2 mbarriers per
-// warp at the end of the CTA's block.  Everything a row contributes to the column loops (its kind / group, the weights
-// d / sigma^2 and s / sigma^2 of the scale-factor gradient) is formed ONCE per set by the lanes over the rows; the column
-// loops (lane = project column) are then shared-memory loads and FMAs only.
+// warp-per-set kernel.  Dynamic shared memory: per CTA the row tables of the plan (data, 1/sigma, sigma-derived weights,
+// kind | group | aux, rows of every group: constant over the parameter sets, read from global memory once per CTA), then
+// per warp (doubles): 2 * tile | sims[n_rows] | resid[n_rows] | w2[n_rows] | sf[G] | p1[G] | p2[G] | sfgrad[G * n_proj];
+// then 2 mbarriers per warp.  Everything a row contributes to the column loops is formed once per set by the lanes over
+// the rows; the column loops (lane = project column) are shared-memory loads and FMAs only.
 // =================================================================================================================
+struct SbmLossTileShape {
+    int tile_doubles, warp_doubles, cta_doubles, n_grp_rows, warps;
+    size_t smem;
+};
+
 template <bool HAS_JAC>
-__global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a, const int tile_doubles, const int warp_doubles)
+__global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a, const SbmLossTileShape sp)
 {
     extern __shared__ __align__(16) double dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double* base = dyn + (size_t)warp * warp_doubles;
-    double* tile0 = base;
-    double* s_sims = base + 2 * tile_doubles;
-    double* s_res = s_sims + a.n_rows;
-    double* s_w1 = s_res + a.n_rows;
-    double* s_w2 = s_w1 + a.n_rows;
-    int* s_meta = reinterpret_cast<int*>(s_w2 + a.n_rows);          // kind | (group + 1) << 4 | aux << 16
-    double* s_sf = s_w2 + 2 * a.n_rows;
-    double* s_p1 = s_sf + a.n_groups;
-    double* s_p2 = s_p1 + a.n_groups;
-    double* s_sfg = s_p2 + a.n_groups;
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(dyn + (size_t)nwarps * warp_doubles) + 2 * warp;
     const bool is_log = (a.loss_kind == SBM_LOSS_LOG);
     const int R = a.n_rows, P = a.n_proj, G = a.n_groups;
+    // ---- CTA-wide row tables ----
+    double* c_data = dyn;                          // data (log loss: log(data))
+    double* c_isig = c_data + R;                   // 1 / sigma
+    double* c_wd = c_isig + R;                     // weight of J in j1: d / sigma^2 (log loss: 1 / sr^2, completed by 1 / s)
+    double* c_w = c_wd + R;                        // 1 / sigma^2 (log loss: unused)
+    int* c_meta = reinterpret_cast<int*>(c_w + R); // kind | (group + 1) << 4 | aux << 16
+    int* c_grows = c_meta + R + (R & 1);
+    int* c_goff = c_grows + sp.n_grp_rows + (sp.n_grp_rows & 1);
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const double d = a.data[r], sg = a.sigma[r];
+        const int kind = a.row_kind[r];
+        c_meta[r] = kind | ((a.row_group[r] + 1) << 4) | (a.row_aux[r] << 16);
+        c_isig[r] = 1.0 / sg;
+        if (!is_log || kind != SBM_ROW_MEASUREMENT) { c_data[r] = d; const double w = 1.0 / (sg * sg); c_w[r] = w; c_wd[r] = d * w; }
+        else { c_data[r] = log(d); const double sr = sg / d; c_w[r] = 0.0; c_wd[r] = 1.0 / (sr * sr); }
+    }
+    for (int q = threadIdx.x; q < sp.n_grp_rows; q += blockDim.x) c_grows[q] = a.grp_rows[q];
+    for (int g = threadIdx.x; g <= G; g += blockDim.x) c_goff[g] = a.grp_off[g];
+    double* base = dyn + sp.cta_doubles + (size_t)warp * sp.warp_doubles;
+    double* tile0 = base;
+    double* s_sims = base + 2 * sp.tile_doubles;
+    double* s_res = s_sims + R;
+    double* s_w1 = s_res + R;                      // per set: weight of J in j1 (log loss) / unused
+    double* s_w2 = s_w1 + R;                       // per set: weight of J in j2: s / sigma^2
+    double* s_sf = s_w2 + R;
+    double* s_p1 = s_sf + G;
+    double* s_p2 = s_p1 + G;
+    double* s_sfg = s_p2 + G;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(dyn + sp.cta_doubles + (size_t)nwarps * sp.warp_doubles) + 2 * warp;
     const unsigned tile_bytes = (unsigned)(R * P) * 8u;
     const long long stride = (long long)gridDim.x * nwarps;
     long long b = (long long)blockIdx.x * nwarps + warp;
@@ -199,31 +221,29 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
             sbm_tma_load(tile0, a.jac + b * (long long)R * P, tile_bytes, mbar);
         }
     }
+    __syncthreads();                               // row tables complete
     unsigned it = 0;
     for (; b < a.B; b += stride, ++it) {
         const int buf = it & 1;
-        double* tile = tile0 + buf * tile_doubles;
+        double* tile = tile0 + buf * sp.tile_doubles;
         double* sims = a.sims + b * R;
         // ---- next set's Jacobian into the other buffer (its previous contents have been read by the bulk store) ----
         if (HAS_JAC && lane == 0 && b + stride < a.B) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             sbm_mbar_expect_tx(mbar + (buf ^ 1), tile_bytes);
-            sbm_tma_load(tile0 + (buf ^ 1) * tile_doubles, a.jac + (b + stride) * (long long)R * P, tile_bytes, mbar + (buf ^ 1));
+            sbm_tma_load(tile0 + (buf ^ 1) * sp.tile_doubles, a.jac + (b + stride) * (long long)R * P, tile_bytes, mbar + (buf ^ 1));
         }
         // ---- prior rows carry theta itself (base_project.py:427-437); NaN scan (squared_loss_function.py:28-32) ----
         int bad = 0;
         for (int r = lane; r < R; r += 32) {
-            const int kind = a.row_kind[r];
+            const int meta = c_meta[r], kind = meta & 15;
             double s = sims[r];
-            if (kind == SBM_ROW_PARAM_PRIOR) { s = a.theta[b * a.theta_sb + a.row_aux[r] * a.theta_sp]; sims[r] = s; }
+            if (kind == SBM_ROW_PARAM_PRIOR) { s = a.theta[b * a.theta_sb + (meta >> 16) * a.theta_sp]; sims[r] = s; }
             if (kind != SBM_ROW_SF_PRIOR && s != s) bad = 1;
             s_sims[r] = s;
-            const int g = a.row_group[r];
-            s_meta[r] = kind | ((g + 1) << 4) | (a.row_aux[r] << 16);
-            if (HAS_JAC && kind == SBM_ROW_MEASUREMENT && g >= 0) {
-                const double d = a.data[r], sg = a.sigma[r];
-                if (!is_log) { const double w = 1.0 / (sg * sg); s_w1[r] = d * w; s_w2[r] = s * w; }
-                else { const double sr = sg / d; s_w1[r] = 1.0 / (s * sr * sr); s_w2[r] = 0.0; }
+            if (HAS_JAC) {
+                if (!is_log) s_w2[r] = s * c_w[r];
+                else s_w1[r] = c_wd[r] / s;
             }
         }
         const bool allbad = __any_sync(0xffffffffu, bad) != 0;
@@ -233,9 +253,17 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
         for (int g = 0; g < G; ++g) {
             double p1 = 0.0, p2 = 0.0, p3 = 0.0;
             if (a.phase != SBM_LOSS_PHASE_FINISH) {
-                for (int q = a.grp_off[g] + lane; q < a.grp_off[g + 1]; q += 32) {
-                    const int r = a.grp_rows[q];
-                    sbm_sf_terms(is_log, s_sims[r], a.data[r], a.sigma[r], p1, p2, p3);
+                for (int q = c_goff[g] + lane; q < c_goff[g + 1]; q += 32) {
+                    const int r = c_grows[q];
+                    const double sv = s_sims[r];
+                    if (!is_log) {                 // linear_scale_factor.py:27-31
+                        p1 = fma(sv, c_wd[r], p1);
+                        p2 = fma(sv * sv, c_w[r], p2);
+                    } else {                       // log_scale_factor.py:17-27
+                        p1 += c_wd[r];
+                        p2 = fma(c_data[r], c_wd[r], p2);
+                        p3 = fma(log(sv), c_wd[r], p3);
+                    }
                 }
                 p1 = sbm_warp_sum(p1);
                 p2 = sbm_warp_sum(p2);
@@ -261,11 +289,13 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
                     double j1 = 0.0, j2 = 0.0;
                     if (a.phase != SBM_LOSS_PHASE_FINISH) {
                         // j1 += J d / sigma^2, j2 += J s / sigma^2 (log loss: j1 += J / (s sr^2)); the weights come staged
-                        const int q1 = a.grp_off[g + 1];
-                        for (int q = a.grp_off[g]; q < q1; ++q) {
-                            const int r = __ldg(a.grp_rows + q);
+                        const int q1 = c_goff[g + 1];
+                        const double* w1 = is_log ? s_w1 : c_wd;
+#pragma unroll 4
+                        for (int q = c_goff[g]; q < q1; ++q) {
+                            const int r = c_grows[q];
                             const double J = tile[r * P + c];
-                            j1 = fma(J, s_w1[r], j1);
+                            j1 = fma(J, w1[r], j1);
                             j2 = fma(J, s_w2[r], j2);
                         }
                         if (a.phase == SBM_LOSS_PHASE_SUMS) {
@@ -287,17 +317,17 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
         // ---- residuals (squared_loss_function.py:34-40, log_squared_loss_function.py:23-64) and SSR ----
         double acc = 0.0;
         for (int r = lane; r < R; r += 32) {
-            const int meta = s_meta[r];
+            const int meta = c_meta[r];
             const int kind = meta & 15;
             double s = s_sims[r];
             double res;
             if (kind == SBM_ROW_MEASUREMENT) {
                 const int g = ((meta >> 4) & 0xfff) - 1;
                 if (g >= 0) s *= s_sf[g];
-                res = is_log ? (log(s) - log(a.data[r])) / a.sigma[r] : (s - a.data[r]) / a.sigma[r];
+                res = is_log ? (log(s) - c_data[r]) * c_isig[r] : (s - c_data[r]) * c_isig[r];
             } else {
                 if (kind == SBM_ROW_SF_PRIOR) { s = log(s_sf[meta >> 16]); sims[r] = s; s_sims[r] = s; }
-                res = (s - a.data[r]) / a.sigma[r];
+                res = (s - c_data[r]) * c_isig[r];
             }
             if (allbad) res = __longlong_as_double(SBM_INF_BITS);
             a.resid[b * R + r] = res;
@@ -311,13 +341,14 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
         if (HAS_JAC) {
             for (int c = lane; c < P; c += 32) {
                 double gacc = 0.0;
+#pragma unroll 4
                 for (int r = 0; r < R; ++r) {
-                    const int meta = s_meta[r];
+                    const int meta = c_meta[r];
                     double J = sbm_scaled_entry(a, is_log, c, meta & 15, ((meta >> 4) & 0xfff) - 1, meta >> 16, tile[r * P + c],
                                                 s_sims[r], s_sf, s_sfg);
                     if (allbad) J = __longlong_as_double(SBM_INF_BITS);
                     tile[r * P + c] = J;
-                    gacc += J * s_res[r];
+                    gacc = fma(J, s_res[r], gacc);
                 }
                 if (a.grad) a.grad[b * P + c] = gacc;
             }
@@ -466,39 +497,43 @@ __global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_kernel(const SbmLos
 }
 
 // tile kernel launch shape: warps per CTA so that two CTAs share an SM's shared memory
-static inline bool sbm_loss_tile_shape(const SbmLossArgs& a, int& warps, int& tile_doubles, int& warp_doubles, size_t& smem)
+static inline bool sbm_loss_tile_shape(const SbmLossArgs& a, int n_grp_rows, SbmLossTileShape& sp)
 {
     const long long tile = a.jac ? (long long)a.n_rows * a.n_proj : 0;
     if (a.jac && ((tile & 1) || tile * 8 > 40 * 1024)) return false;      // bulk copies move multiples of 16 bytes
     if ((reinterpret_cast<size_t>(a.jac) & 15) != 0) return false;
-    tile_doubles = (int)tile;
-    long long wd = 2 * tile + 5ll * a.n_rows + 3ll * a.n_groups + (long long)a.n_groups * a.n_proj;
+    if (a.n_rows > 2048 || a.n_groups > 4000 || a.n_proj > 32000) return false;
+    sp.tile_doubles = (int)tile;
+    sp.n_grp_rows = n_grp_rows;
+    long long cd = 4ll * a.n_rows + (a.n_rows + 1) / 2 + (n_grp_rows + 1) / 2 + (a.n_groups + 2) / 2 + 2;
+    cd += (cd & 1);
+    long long wd = 2 * tile + 4ll * a.n_rows + 3ll * a.n_groups + (long long)a.n_groups * a.n_proj;
     wd += (wd & 1);                                                      // keep every warp's block 16-byte aligned
-    if (wd * 8 > 100 * 1024) return false;
-    warp_doubles = (int)wd;
-    warps = (int)((108 * 1024) / (wd * 8 + 16));
-    if (warps > 8) warps = 8;
-    if (warps < 1) return false;
-    smem = (size_t)warps * ((size_t)wd * 8 + 16);
+    const long long budget = 110 * 1024 - cd * 8;
+    if (budget < wd * 8 + 16) return false;
+    sp.cta_doubles = (int)cd;
+    sp.warp_doubles = (int)wd;
+    sp.warps = (int)(budget / (wd * 8 + 16));
+    if (sp.warps > 8) sp.warps = 8;
+    sp.smem = (size_t)cd * 8 + (size_t)sp.warps * ((size_t)wd * 8 + 16);
     return true;
 }
 
-static inline cudaError_t sbm_launch_loss(const SbmLossArgs& a, cudaStream_t st, int sm_count)
+static inline cudaError_t sbm_launch_loss(const SbmLossArgs& a, cudaStream_t st, int sm_count, int n_grp_rows)
 {
-    int warps = 0, td = 0, wd = 0;
-    size_t smem = 0;
+    SbmLossTileShape sp;
     static bool attr_set = false;
-    if (!(a.flags & SBM_FLAG_LOSS_GENERIC) && sbm_loss_tile_shape(a, warps, td, wd, smem)) {
+    if (!(a.flags & SBM_FLAG_LOSS_GENERIC) && sbm_loss_tile_shape(a, n_grp_rows, sp)) {
         if (!attr_set) {
             cudaFuncSetAttribute(sbm_loss_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
             cudaFuncSetAttribute(sbm_loss_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
             attr_set = true;
         }
-        long long blocks = (a.B + warps - 1) / warps;
+        long long blocks = (a.B + sp.warps - 1) / sp.warps;
         const long long cap = (long long)(sm_count > 0 ? sm_count : 148) * (a.jac ? 2 : 8);
         if (blocks > cap) blocks = cap;
-        if (a.jac) sbm_loss_tile_kernel<true><<<(unsigned)blocks, warps * 32, smem, st>>>(a, td, wd);
-        else sbm_loss_tile_kernel<false><<<(unsigned)blocks, warps * 32, smem, st>>>(a, td, wd);
+        if (a.jac) sbm_loss_tile_kernel<true><<<(unsigned)blocks, sp.warps * 32, sp.smem, st>>>(a, sp);
+        else sbm_loss_tile_kernel<false><<<(unsigned)blocks, sp.warps * 32, sp.smem, st>>>(a, sp);
         return cudaGetLastError();
     }
     long long blocks = a.B < 1048576 ? a.B : 1048576;

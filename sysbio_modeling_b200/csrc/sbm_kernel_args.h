@@ -48,6 +48,8 @@ typedef struct SbmSolveArgs {
     double                    rtol;
     double                    atol;
     double                    h0;         // initial step; 0 = automatic
+    int                       n_tout;     // lengths of tout / of the row tables (small plans are staged in shared memory)
+    int                       n_orow;
 } SbmSolveArgs;
 
 #endif

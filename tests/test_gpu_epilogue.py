@@ -32,9 +32,14 @@ def test_tile_kernel_matches_generic_kernel(c4_eval):
         proj.loss_generic_kernel = False
     torch.cuda.synchronize()
     assert torch.isfinite(a['jac']).all()
+    # same formulas, different association of the products and sums (the warp-per-set kernel stages d / sigma^2 and
+    # s / sigma^2 per row, multiplies by 1 / sigma, reduces over 32 lanes instead of 128 threads): agreement to rounding,
+    # amplified where the scale-factor gradient cancels (j1 / p2 - 2 p1 j2 / p2^2)
     for k in ('resid', 'ssr', 'sf', 'sfgrad', 'jac', 'grad'):
         scale = b[k].abs().max().item()
-        assert torch.allclose(a[k], b[k], rtol=1e-12, atol=1e-13 * scale), (k, (a[k] - b[k]).abs().max().item())
+        err = (a[k] - b[k]).abs().max().item()
+        print(k, 'max abs diff %.3e of scale %.3e' % (err, scale))
+        assert torch.allclose(a[k], b[k], rtol=1e-9, atol=1e-11 * scale), (k, err, scale)
     # residual-only path (no Jacobian tile)
     ar = _clone(proj.evaluate_device(theta, False))
     proj.loss_generic_kernel = True
@@ -43,7 +48,7 @@ def test_tile_kernel_matches_generic_kernel(c4_eval):
     finally:
         proj.loss_generic_kernel = False
     for k in ('resid', 'ssr', 'sf'):
-        assert torch.allclose(ar[k], br[k], rtol=1e-12, atol=0), k
+        assert torch.allclose(ar[k], br[k], rtol=1e-9, atol=1e-11 * br[k].abs().max().item()), k
 
 
 @pytest.mark.parametrize('generic', [False, True])
