@@ -222,6 +222,25 @@ int sbm_host_end(sbm_plan* p, int slot);
 int sbm_lm_step(long long B, int n_rows, int n_proj, const double* jac, const double* resid, const double* lambda,
                 double* dscale, double* delta, double* pred, double* gmax, int* info, void* stream);
 
+/* ---- batched Metropolis ensemble sampler: the two steps around the objective evaluation ------------------------------------
+ * W lock-step copies of the reference's ensemble_log_params (Ensembles.py:55-178).  Per Monte-Carlo step: sbm_mc_propose,
+ * sbm_solve + sbm_loss on the candidates, sbm_mc_accept - four launches, no host synchronisation.
+ *   sbm_mc_propose   nxt[w] = cur[w] + samp . z  (Ensembles.py:266-270 with the sampling matrix of :226-264);
+ *                    z = normals[W][P] when given, else Philox4x32-10(seed; walker, index, step) + Box-Muller
+ *   sbm_mc_accept    F_new = ssr_new - T x scale-factor entropy (base_project.py:854-892; linear_scale_factor.py:13-18, 63-80
+ *                    by a composite 16-point Gauss-Legendre rule; only groups with a log prior: sf_mu / sf_sig [n_groups],
+ *                    NaN = none, both NULL = no entropy term); accept if u < exp(-(F_new - curF) / T) (Ensembles.py:193-198);
+ *                    accepted walkers: cur <- nxt, curF <- F_new, accepted += 1 (the reference never updates curr_F,
+ *                    :151-154 - not reproduced).  init = 1: no move, curF <- F(cur) from ssr_new / sims_new.
+ *                    ens_out [W][P] / fes_out [W]: where to record this step's positions / free energies (NULL: not recorded).
+ * All pointers are device pointers; u = uniforms[W] when given, else the device generator.                                   */
+int sbm_mc_propose(long long W, int P, const double* samp, const double* cur, double* nxt, const double* normals,
+                   unsigned long long seed, unsigned step, void* stream);
+int sbm_mc_accept(sbm_plan* p, long long W, int init, double temperature, double* cur, const double* nxt, double* curF,
+                  const double* ssr_new, const double* sims_new, const double* sf_mu, const double* sf_sig,
+                  const double* uniforms, unsigned long long seed, unsigned step, double* accepted,
+                  double* ens_out, double* fes_out, void* stream);
+
 /* ---- utilities ----------------------------------------------------------------------------------------- */
 /* DFMA-throughput microbenchmark on the current device: the measured FP64 roofline denominator. */
 int         sbm_fp64_peak(int iters, double* tflops_out, double* ms_out);

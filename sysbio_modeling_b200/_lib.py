@@ -67,7 +67,7 @@ class SolverOpts(ctypes.Structure):
 
 EXPORTS = ['sbm_model_compile', 'sbm_model_info', 'sbm_model_log', 'sbm_model_destroy', 'sbm_plan_create',
            'sbm_plan_destroy', 'sbm_solve', 'sbm_loss', 'sbm_loss_sums', 'sbm_loss_finish', 'sbm_normal_equations',
-           'sbm_residuals_host', 'sbm_jacobian_host', 'sbm_jacobian_host_begin', 'sbm_host_end', 'sbm_lm_step',
+           'sbm_residuals_host', 'sbm_jacobian_host', 'sbm_jacobian_host_begin', 'sbm_host_end', 'sbm_lm_step', 'sbm_mc_propose', 'sbm_mc_accept',
            'sbm_fp64_peak', 'sbm_device_count', 'sbm_last_error', 'sbm_version']
 
 _lib = None
@@ -103,6 +103,9 @@ def lib():
     L.sbm_jacobian_host_begin.argtypes = [vp, ctypes.POINTER(SolverOpts), ci, ci, ll, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci]
     L.sbm_host_end.argtypes = [vp, ci]
     L.sbm_lm_step.argtypes = [ll, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    ull, cu = ctypes.c_ulonglong, ctypes.c_uint
+    L.sbm_mc_propose.argtypes = [ll, ci, vp, vp, vp, vp, ull, cu, vp]
+    L.sbm_mc_accept.argtypes = [vp, ll, ci, cd, vp, vp, vp, vp, vp, vp, vp, vp, ull, cu, vp, vp, vp, vp]
     L.sbm_fp64_peak.argtypes = [ci, _DP, _DP]
     _lib = L
     return L

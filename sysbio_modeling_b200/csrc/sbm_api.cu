@@ -27,6 +27,7 @@
 #include "sbm_kernel_args.h"
 #include "sbm_epilogue.cuh"
 #include "sbm_lm.cuh"
+#include "sbm_sampler.cuh"
 
 // generated at build time from sbm_kernel_args.h + kernels/sbm_ode_kernels.cuh
 extern const char* sbm_embedded_args_header;
@@ -689,6 +690,48 @@ extern "C" int sbm_lm_step(long long B, int n_rows, int n_proj, const double* ja
     a.B = B; a.n_rows = n_rows; a.n_proj = n_proj;
     if (sbm_launch_lm_step(a, (cudaStream_t)stream)) return fail(SBM_E_INVALID, "sbm_lm_step: unsupported shape");
     RT(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched Metropolis sampler: proposal and accept / reject on the device
+// ------------------------------------------------------------------------------------------------
+extern "C" int sbm_mc_propose(long long W, int P, const double* samp, const double* cur, double* nxt, const double* normals,
+                              unsigned long long seed, unsigned step, void* stream)
+{
+    if (!samp || !cur || !nxt) return fail(SBM_E_INVALID, "sbm_mc_propose: null argument");
+    if (W <= 0 || P <= 0 || P > 4096) return fail(SBM_E_INVALID, "sbm_mc_propose: bad sizes");
+    int rc = require_device();
+    if (rc) return rc;
+    int dev = 0, sms = 0;
+    RT(cudaGetDevice(&dev));
+    RT(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SbmMcArgs a;
+    memset(&a, 0, sizeof a);
+    a.W = W; a.P = P; a.samp = samp; a.cur = const_cast<double*>(cur); a.nxt = nxt; a.normals = normals; a.seed = seed; a.step = step;
+    RT(sbm_launch_mc_propose(a, (cudaStream_t)stream, sms));
+    return 0;
+}
+
+extern "C" int sbm_mc_accept(sbm_plan* p, long long W, int init, double temperature, double* cur, const double* nxt, double* curF,
+                             const double* ssr_new, const double* sims_new, const double* sf_mu, const double* sf_sig,
+                             const double* uniforms, unsigned long long seed, unsigned step, double* accepted,
+                             double* ens_out, double* fes_out, void* stream)
+{
+    if (!p || !cur || !curF || !ssr_new || !sims_new || !accepted) return fail(SBM_E_INVALID, "sbm_mc_accept: null argument");
+    if (!init && !nxt) return fail(SBM_E_INVALID, "sbm_mc_accept: null argument");
+    if (W <= 0 || !(temperature > 0.0)) return fail(SBM_E_INVALID, "sbm_mc_accept: bad sizes / temperature");
+    if ((ens_out == nullptr) != (fes_out == nullptr)) return fail(SBM_E_INVALID, "sbm_mc_accept: ens_out and fes_out go together");
+    int rc = require_device();
+    if (rc) return rc;
+    SbmMcArgs a;
+    memset(&a, 0, sizeof a);
+    a.W = W; a.P = p->d.n_proj; a.n_rows = p->d.n_rows; a.n_groups = (sf_mu && sf_sig) ? p->d.n_groups : 0;
+    a.cur = cur; a.nxt = const_cast<double*>(nxt); a.curF = curF; a.ssr_new = ssr_new; a.sims_new = sims_new;
+    a.temperature = temperature; a.data = p->data; a.sigma = p->sigma; a.grp_off = p->grp_off; a.grp_rows = p->grp_rows;
+    a.sf_mu = sf_mu; a.sf_sig = sf_sig; a.uniforms = uniforms; a.seed = seed; a.step = step; a.accepted = accepted;
+    a.ens_out = ens_out; a.fes_out = fes_out; a.init = init;
+    RT(sbm_launch_mc_accept(a, (cudaStream_t)stream, p->sm_count));
     return 0;
 }
 

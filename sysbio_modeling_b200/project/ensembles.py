@@ -1,4 +1,7 @@
 """Batched Metropolis ensemble sampler - the caller that generates SURVEY.md's C5 workload (section 8f rank 3).
+The Monte-Carlo loop runs on the device (csrc/sbm_sampler.cuh: ``sbm_mc_propose`` / ``sbm_mc_accept`` around the
+integrator and the loss epilogue); ``_entropy_device`` below is the torch form of the entropy quadrature, kept as a
+cross-check of the kernel's.
 
 Reference: ``project/Ensembles.py:55-178`` (``ensemble_log_params``: ONE walker, one ``Project.free_energy`` call per
 Monte-Carlo step) with ``_sampling_matrix`` (``:226-264``), ``_trial_move`` (``:266-270``) and ``_accept_move``
@@ -96,15 +99,48 @@ def _entropy_device(proj, sims, temperature):
     return ent
 
 
+def gauss_newton_hessian(p, theta):
+    """Gauss-Newton Hessian of the cost ``0.5 sum r^2`` at ``theta``: ``(J / sigma)^T (J / sigma)``.  The project's scaled
+    Jacobian is NOT divided by sigma (reference ``squared_loss_function.py:76``), the residuals are: the rows
+    are divided here.  (The reference's default ``recalc_func = p.hessian``, ``Ensembles.py:118``, does not exist.)"""
+    out = p.jacobian_batch(np.asarray(theta, dtype=np.float64)[None, :])
+    J = out['jac'][0] / np.asarray(p.plan_tables.sigma)[:, None]
+    return J.T.dot(J)
+
+
+def _sf_prior_arrays(p, dev):
+    """(mu [G], sigma [G]) device tensors of the scale factors' log priors (NaN where a group has none), or (None, None)
+    when no group has a prior: the free energy is then the plain SSR (reference base_project.py:874-892 with an empty sum)."""
+    import torch
+    t = p._plan_tables
+    if t.n_groups == 0:
+        return None, None
+    lf = p._loss_function
+    mu, sg = [], []
+    for key in lf.group_keys():
+        holder = lf._scale_factors[lf.group_members(key)[0]]
+        has = holder.log_prior is not None and holder.log_prior_sigma is not None
+        mu.append(float(holder.log_prior) if has else float('nan'))
+        sg.append(float(holder.log_prior_sigma) if has else float('nan'))
+    if all(np.isnan(x) for x in mu):
+        return None, None
+    return (torch.tensor(mu, dtype=torch.float64, device=dev), torch.tensor(sg, dtype=torch.float64, device=dev))
+
+
 def ensemble_log_params_batch(p, params, hess=None, steps=100, temperature=1.0, step_scale=1.0, sing_val_cutoff=0,
                               seeds=None, skip_elems=0, n_walkers=None, normals=None, uniforms=None, solver=None):
     """W Metropolis walkers in the logarithm of the parameters, in lock-step on the GPU.
+
+    Every Monte-Carlo step is four launches and no host synchronisation: ``sbm_mc_propose`` (proposal ``cur + samp_mat . z``,
+    Philox random numbers generated in the kernel), the integrator and the loss epilogue on the W candidates (the hot
+    path), ``sbm_mc_accept`` (free energy incl. the scale-factor entropy quadrature, Metropolis rule, bookkeeping, recording).
+    Walkers, free energies and the recorded ensemble stay in HBM; one copy to the host when the run ends.
 
     Parameters (reference names, ``Ensembles.py:55-63``; additive: ``n_walkers``, ``normals``, ``uniforms``)
     ----------
     p : Project (CUDA backend)
     params : f8[n_proj] (every walker starts there) or f8[W, n_proj]
-    hess : f8[n_proj, n_proj], optional - default ``J^T J`` of the scaled Jacobian at the (first) starting point
+    hess : f8[n_proj, n_proj], optional - default the Gauss-Newton Hessian at the (first) starting point (``gauss_newton_hessian``)
     steps : Monte-Carlo steps of every walker
     temperature, step_scale, sing_val_cutoff, skip_elems : as in the reference
     seeds : int - seed of the device random generator
@@ -114,49 +150,53 @@ def ensemble_log_params_batch(p, params, hess=None, steps=100, temperature=1.0, 
     Returns ``(ens f8[n_kept, W, n_proj], ens_fes f8[n_kept, W], ratio f8[W])``: the walkers' positions and free energies
     (starting point first, then every ``skip_elems + 1``-th step) and each walker's acceptance ratio.
     """
+    import ctypes
     import torch
     _lib.require_gpu()
+    L = _lib.lib()
+    vp = ctypes.c_void_p
     dev = torch.device('cuda')
     params = np.asarray(params, dtype=np.float64)
     if params.ndim == 1:
         params = np.tile(params[None, :], (int(n_walkers or 1), 1))
     W, P = params.shape
     if hess is None:
-        J = p.jacobian_batch(params[:1])['jac'][0]
-        hess = J.T.dot(J)
+        hess = gauss_newton_hessian(p, params[0])
+    f64 = dict(dtype=torch.float64, device=dev)
     samp = torch.from_numpy(np.ascontiguousarray(sampling_matrix(hess, sing_val_cutoff, temperature, step_scale))).to(dev)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(int(seeds) if seeds is not None else 0)
-    has_sf = p._plan_tables.n_groups > 0 and any(
-        p._loss_function._scale_factors[p._loss_function.group_members(k)[0]].log_prior is not None
-        for k in p._loss_function.group_keys())
-
-    def free_energy(theta, bufs):
-        o = p.evaluate_device(theta, with_jacobian=False, solver=solver, out=bufs)
-        F = o['ssr'].clone()                                  # reference: rss - entropy (base_project.py:888-891)
-        if has_sf:
-            F = F - _entropy_device(p, o['sims'], temperature)
-        return torch.where(torch.isfinite(F), F, torch.full_like(F, float('inf')))
-
+    seed = int(seeds) if seeds is not None else 0
+    sf_mu, sf_sig = _sf_prior_arrays(p, dev)
+    plan = p.device_plan
+    st = torch.cuda.current_stream().cuda_stream
+    steps, every = int(steps), int(skip_elems) + 1
+    n_kept = 1 + steps // every
     cur = torch.from_numpy(np.ascontiguousarray(params)).to(dev)
-    b0, b1 = {}, {}
-    curF = free_energy(cur, b0)
-    ens, fes = [cur.cpu().numpy()], [curF.cpu().numpy()]
-    accepted = torch.zeros((W,), dtype=torch.float64, device=dev)
-    for it in range(int(steps)):
-        if normals is not None:
-            z = torch.from_numpy(np.ascontiguousarray(normals[it])).to(dev)
-            r = torch.from_numpy(np.ascontiguousarray(uniforms[it])).to(dev)
-        else:
-            z = torch.randn((W, P), dtype=torch.float64, device=dev, generator=gen)
-            r = torch.rand((W,), dtype=torch.float64, device=dev, generator=gen)
-        nxt = cur + z @ samp.T                                # _trial_move: samp_mat . randn (Ensembles.py:266-270)
-        nxtF = free_energy(nxt, b1)
-        acc = r < torch.exp(-(nxtF - curF) / temperature)     # _accept_move (Ensembles.py:193-198)
-        cur = torch.where(acc[:, None], nxt, cur)
-        curF = torch.where(acc, nxtF, curF)                   # (the reference forgets this update, :151-154)
-        accepted += acc.to(torch.float64)
-        if (it + 1) % (int(skip_elems) + 1) == 0:
-            ens.append(cur.cpu().numpy())
-            fes.append(curF.cpu().numpy())
-    return np.array(ens), np.array(fes), (accepted / max(int(steps), 1)).cpu().numpy()
+    nxt = torch.empty_like(cur)
+    curF = torch.empty((W,), **f64)
+    accepted = torch.zeros((W,), **f64)
+    ens = torch.empty((n_kept, W, P), **f64)
+    fes = torch.empty((n_kept, W), **f64)
+    if normals is not None:
+        normals_d = torch.from_numpy(np.ascontiguousarray(normals, dtype=np.float64)).to(dev)
+        uniforms_d = torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float64)).to(dev)
+    bufs = {}
+
+    def ptr(x):
+        return vp(x.data_ptr()) if x is not None else None
+
+    def accept(theta_eval, init, it, slot):
+        o = p.evaluate_device(theta_eval, with_jacobian=False, solver=solver, out=bufs)
+        _lib.check(L.sbm_mc_accept(plan.handle, W, int(init), float(temperature), ptr(cur), ptr(nxt), ptr(curF),
+                                   ptr(o['ssr']), ptr(o['sims']), ptr(sf_mu), ptr(sf_sig),
+                                   ptr(uniforms_d[it]) if (normals is not None and not init) else None, seed, it,
+                                   ptr(accepted), ptr(ens[slot]) if slot is not None else None,
+                                   ptr(fes[slot]) if slot is not None else None, vp(st)))
+    accept(cur, True, 0, 0)
+    kept = 1
+    for it in range(steps):
+        _lib.check(L.sbm_mc_propose(W, P, ptr(samp), ptr(cur), ptr(nxt),
+                                    ptr(normals_d[it]) if normals is not None else None, seed, it, vp(st)))
+        rec = (it + 1) % every == 0
+        accept(nxt, False, it, kept if rec else None)
+        kept += 1 if rec else 0
+    return ens.cpu().numpy(), fes.cpu().numpy(), (accepted / max(steps, 1)).cpu().numpy()

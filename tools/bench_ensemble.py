@@ -31,8 +31,7 @@ th0 = np.log(nominal)
 # the sampling matrix comes from the Gauss-Newton Hessian J^T J of the scaled Jacobian at the starting point (reference
 # Ensembles.py:226-258): one sensitivity solve of the 25-state, 52-parameter model (1,325 augmented states, warp-group kernel);
 # singular values below 1e-6 of the largest are raised to it (the reference's sing_val_cutoff)
-J0 = proj.jacobian_batch(th0[None, :])['jac'][0]
-hess = J0.T.dot(J0)
+hess = ensembles.gauss_newton_hessian(proj, th0)
 CUTOFF = 1e-6
 ensembles.ensemble_log_params_batch(proj, th0, hess=hess, steps=1, n_walkers=1024, seeds=1, sing_val_cutoff=CUTOFF)      # warm-up
 torch.cuda.synchronize()
