@@ -22,6 +22,7 @@
 #define SBM_EPILOGUE_CUH
 
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "../../include/sbm_b200.h"
 
 #define SBM_LOSS_PHASE_ALL    0
@@ -168,12 +169,12 @@ __device__ __forceinline__ void sbm_tma_store(void* dst_gmem, const void* src_sm
 // the rows; the column loops (lane = project column) are shared-memory loads and FMAs only.
 // =================================================================================================================
 struct SbmLossTileShape {
-    int tile_doubles, warp_doubles, cta_doubles, n_grp_rows, warps;
+    int tile_doubles, warp_doubles, cta_doubles, n_grp_rows, warps, nbuf;
     size_t smem;
 };
 
 template <bool HAS_JAC>
-__global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a, const SbmLossTileShape sp)
+__global__ void __launch_bounds__(384) sbm_loss_tile_kernel(const SbmLossArgs a, const SbmLossTileShape sp)
 {
     extern __shared__ __align__(16) double dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
     for (int g = threadIdx.x; g <= G; g += blockDim.x) c_goff[g] = a.grp_off[g];
     double* base = dyn + sp.cta_doubles + (size_t)warp * sp.warp_doubles;
     double* tile0 = base;
-    double* s_sims = base + 2 * sp.tile_doubles;
+    double* s_sims = base + sp.nbuf * sp.tile_doubles;
     double* s_res = s_sims + R;
     double* s_w1 = s_res + R;                      // per set: weight of J in j1 (log loss) / unused
     double* s_w2 = s_w1 + R;                       // per set: weight of J in j2: s / sigma^2
@@ -223,12 +224,14 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
     }
     __syncthreads();                               // row tables complete
     unsigned it = 0;
+    const int nbuf = sp.nbuf;
     for (; b < a.B; b += stride, ++it) {
-        const int buf = it & 1;
+        const int buf = (nbuf == 2) ? (it & 1) : 0;
         double* tile = tile0 + buf * sp.tile_doubles;
         double* sims = a.sims + b * R;
-        // ---- next set's Jacobian into the other buffer (its previous contents have been read by the bulk store) ----
-        if (HAS_JAC && lane == 0 && b + stride < a.B) {
+        // ---- two buffers: the next set's Jacobian into the other one (its previous contents have been read by the bulk
+        //      store).  One buffer (more warps per SM instead: their loads overlap): issued at the end of the iteration ----
+        if (HAS_JAC && nbuf == 2 && lane == 0 && b + stride < a.B) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             sbm_mbar_expect_tx(mbar + (buf ^ 1), tile_bytes);
             sbm_tma_load(tile0 + (buf ^ 1) * sp.tile_doubles, a.jac + (b + stride) * (long long)R * P, tile_bytes, mbar + (buf ^ 1));
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
         }
         __syncwarp();
         if (HAS_JAC) {
-            sbm_mbar_wait(mbar + buf, (it >> 1) & 1u);
+            sbm_mbar_wait(mbar + buf, ((nbuf == 2) ? (it >> 1) : it) & 1u);
             // ---- gradient of the scale factors w.r.t. theta (needs the unscaled model Jacobian) ----
             for (int g = 0; g < G; ++g) {
                 for (int c = lane; c < P; c += 32) {
@@ -313,7 +316,13 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
             }
             __syncwarp();
         }
-        if (a.phase == SBM_LOSS_PHASE_SUMS) continue;       // (the tile is untouched: nothing to store back)
+        if (a.phase == SBM_LOSS_PHASE_SUMS) {               // (the tile is untouched: nothing to store back)
+            if (HAS_JAC && nbuf == 1 && lane == 0 && b + stride < a.B) {
+                sbm_mbar_expect_tx(mbar, tile_bytes);
+                sbm_tma_load(tile0, a.jac + (b + stride) * (long long)R * P, tile_bytes, mbar);
+            }
+            continue;
+        }
         // ---- residuals (squared_loss_function.py:34-40, log_squared_loss_function.py:23-64) and SSR ----
         double acc = 0.0;
         for (int r = lane; r < R; r += 32) {
@@ -354,7 +363,14 @@ __global__ void __launch_bounds__(256) sbm_loss_tile_kernel(const SbmLossArgs a,
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) sbm_tma_store(a.jac + b * (long long)R * P, tile, tile_bytes);
+            if (lane == 0) {
+                sbm_tma_store(a.jac + b * (long long)R * P, tile, tile_bytes);
+                if (nbuf == 1 && b + stride < a.B) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    sbm_mbar_expect_tx(mbar, tile_bytes);
+                    sbm_tma_load(tile0, a.jac + (b + stride) * (long long)R * P, tile_bytes, mbar);
+                }
+            }
         }
     }
     if (HAS_JAC && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -507,14 +523,21 @@ static inline bool sbm_loss_tile_shape(const SbmLossArgs& a, int n_grp_rows, Sbm
     sp.n_grp_rows = n_grp_rows;
     long long cd = 4ll * a.n_rows + (a.n_rows + 1) / 2 + (n_grp_rows + 1) / 2 + (a.n_groups + 2) / 2 + 2;
     cd += (cd & 1);
-    long long wd = 2 * tile + 4ll * a.n_rows + 3ll * a.n_groups + (long long)a.n_groups * a.n_proj;
-    wd += (wd & 1);                                                      // keep every warp's block 16-byte aligned
+    // one tile buffer per warp when two would leave fewer than 8 warps per CTA (two CTAs per SM): with 16+ warps per SM the
+    // other warps cover a load; measured on C4 (7 KB tiles): 2 buffers x 7 warps 0.41 ms, see DESIGN.md
     const long long budget = 110 * 1024 - cd * 8;
+    const long long rest = 4ll * a.n_rows + 3ll * a.n_groups + (long long)a.n_groups * a.n_proj;
+    sp.nbuf = 2;
+    if (const char* e = getenv("SBM_LOSS_NBUF")) { int v = atoi(e); if (v == 1 || v == 2) sp.nbuf = v; }
+    else if (tile > 0 && budget / ((2 * tile + rest + 1) * 8 + 16) < 8) sp.nbuf = 1;
+    long long wd = sp.nbuf * tile + rest;
+    wd += (wd & 1);                                                      // keep every warp's block 16-byte aligned
     if (budget < wd * 8 + 16) return false;
     sp.cta_doubles = (int)cd;
     sp.warp_doubles = (int)wd;
     sp.warps = (int)(budget / (wd * 8 + 16));
-    if (sp.warps > 8) sp.warps = 8;
+    const int wmax = getenv("SBM_LOSS_WARPS") ? atoi(getenv("SBM_LOSS_WARPS")) : 12;
+    if (sp.warps > wmax) sp.warps = wmax;
     sp.smem = (size_t)cd * 8 + (size_t)sp.warps * ((size_t)wd * 8 + 16);
     return true;
 }

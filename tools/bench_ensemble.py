@@ -30,9 +30,10 @@ proj = sb.Project(om, exps, {}, {'ERKPP': ('direct', 24), 'RasT': ('direct', 16)
 th0 = np.log(nominal)
 # the sampling matrix comes from the Gauss-Newton Hessian J^T J of the scaled Jacobian at the starting point (reference
 # Ensembles.py:226-258): one sensitivity solve of the 25-state, 52-parameter model (1,325 augmented states, warp-group kernel);
-# singular values below 1e-6 of the largest are raised to it (the reference's sing_val_cutoff)
+# singular values below CUTOFF x the largest are raised to it (the reference's sing_val_cutoff): the quadratic model of a
+# sloppy 52-parameter cost only holds along its stiff directions
 hess = ensembles.gauss_newton_hessian(proj, th0)
-CUTOFF = 1e-6
+CUTOFF = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-2
 ensembles.ensemble_log_params_batch(proj, th0, hess=hess, steps=1, n_walkers=1024, seeds=1, sing_val_cutoff=CUTOFF)      # warm-up
 torch.cuda.synchronize()
 if world > 1:
@@ -51,6 +52,7 @@ if world > 1:
 if rank == 0:
     print(json.dumps({'n_gpus': world, 'walkers_per_gpu': W, 'steps': steps, 'wall_s_max_over_ranks': float(dt),
                       'walker_steps_per_s': world * W * (steps + 1) / float(dt), 'acceptance_mean': float(acc),
-                      'free_energy_finite_rank0': bool(np.isfinite(fes).all())}))
+                      'free_energy_finite_rank0': bool(np.isfinite(fes).all()), 'sing_val_cutoff': CUTOFF,
+                      'hessian': 'Gauss-Newton (J / sigma)^T (J / sigma) at the starting point, warp-group sensitivity kernel'}))
 if world > 1:
     dist.destroy_process_group()
