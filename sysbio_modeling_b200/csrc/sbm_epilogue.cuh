@@ -13,7 +13,8 @@
 //                         J read ONCE and written once (the previous kernel read it twice).  Used whenever the tile
 //                         fits (C4: 40 x 22 doubles = 7 KB), and for residual-only evaluations (no tile at all).
 //   sbm_loss_kernel       one CTA per parameter set, J stays in global memory (two reads, one write): any shape
-//                         (C2: 65,536 rows x 16,384 project columns per set).
+//   sbm_loss_wide_*       few sets with big Jacobians (C2 through the Project: 65,536 rows x 16,384 project columns per
+//                         set): every set spread over the whole grid, six kernels in stream order.
 //
 // Both can stop after the group sums (SBM_LOSS_PHASE_SUMS) or start from given sums (SBM_LOSS_PHASE_FINISH): that is
 // the hook of the experiment shard (distributed.py), which all-reduces the sums over ranks in between
@@ -512,6 +513,236 @@ __global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_kernel(const SbmLos
     }
 }
 
+// =================================================================================================================
+// row-parallel ("wide") path: few parameter sets, big Jacobians (C2 through the Project: 65,536 rows x 16,384 project
+// columns per set, 8.6 GB) - the whole grid works on one set's rows and columns.  Six small kernels in stream order;
+// every sum has a fixed order (per-chunk partials + a final pass), so results do not depend on the schedule.
+//   rows     prior rows <- theta, NaN scan                                          grid (row chunks, B)
+//   sf       group sums p1 p2 p3, scale factors (one warp per group)                grid (group chunks, B)
+//   sfgrad   j1 j2 sums over a group's rows, dB/dtheta                              grid (column blocks, groups, B)
+//   resid    residuals, SSR partials                                                grid (row chunks, B)
+//   jac      scaled Jacobian in place, J^T r partials                               grid (column blocks, row chunks, B)
+//   reduce   SSR and J^T r from the partials                                        grid (B)
+// A CTA of 128 threads is CW columns x (128 / CW) rows, CW = min(128, next power of two >= n_proj): row-major J is read
+// and written coalesced along the columns.
+// =================================================================================================================
+struct SbmLossWide {
+    int cw, ry;              // columns per CTA, rows in parallel per CTA
+    int n_rchunks, rchunk;   // row chunks and their length
+    double* psum;            // [B][G][psum_sg]: p1, p2, p3 (scratch, or the caller's sums buffer)
+    long long psum_sb;       // stride of a set / of a group in psum
+    int psum_sg;
+    double* ssrp;            // [B][n_rchunks]
+    double* gradp;           // [B][n_rchunks][n_proj]
+    int* bad;                // [B]
+};
+
+__global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_wide_rows(const SbmLossArgs a, const SbmLossWide w)
+{
+    const long long b = blockIdx.y;
+    double* sims = a.sims + b * a.n_rows;
+    const int r0 = blockIdx.x * w.rchunk, r1 = min(a.n_rows, r0 + w.rchunk);
+    int bad = 0;
+    for (int r = r0 + threadIdx.x; r < r1; r += SBM_LOSS_THREADS) {
+        const int kind = a.row_kind[r];
+        if (kind == SBM_ROW_PARAM_PRIOR) sims[r] = a.theta[b * a.theta_sb + a.row_aux[r] * a.theta_sp];
+        if (kind != SBM_ROW_SF_PRIOR) { const double s = sims[r]; if (s != s) bad = 1; }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(w.bad + b, 1);
+}
+
+__global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_wide_sf(const SbmLossArgs a, const SbmLossWide w)
+{
+    const long long b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const bool is_log = (a.loss_kind == SBM_LOSS_LOG);
+    const double* sims = a.sims + b * a.n_rows;
+    for (int g = blockIdx.x * (SBM_LOSS_THREADS / 32) + (threadIdx.x >> 5); g < a.n_groups; g += gridDim.x * (SBM_LOSS_THREADS / 32)) {
+        double* ps = w.psum + b * w.psum_sb + (long long)g * w.psum_sg;
+        double p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        if (a.phase != SBM_LOSS_PHASE_FINISH) {
+            for (int q = a.grp_off[g] + lane; q < a.grp_off[g + 1]; q += 32) {
+                const int r = a.grp_rows[q];
+                sbm_sf_terms(is_log, sims[r], a.data[r], a.sigma[r], p1, p2, p3);
+            }
+            p1 = sbm_warp_sum(p1);
+            p2 = sbm_warp_sum(p2);
+            p3 = sbm_warp_sum(p3);
+            if (lane == 0) { ps[0] = p1; ps[1] = p2; ps[2] = p3; }
+        } else {
+            p1 = ps[0]; p2 = ps[1]; p3 = ps[2];
+        }
+        if (lane == 0 && a.phase != SBM_LOSS_PHASE_SUMS) a.sf[b * a.n_groups + g] = sbm_sf_value(is_log, p1, p2, p3);
+    }
+}
+
+__global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_wide_sfgrad(const SbmLossArgs a, const SbmLossWide w)
+{
+    __shared__ double red1[SBM_LOSS_THREADS], red2[SBM_LOSS_THREADS];
+    const long long b = blockIdx.z;
+    const int P = a.n_proj, G = a.n_groups;
+    const int tx = threadIdx.x % w.cw, ty = threadIdx.x / w.cw;
+    const int c = blockIdx.x * w.cw + tx;
+    const bool is_log = (a.loss_kind == SBM_LOSS_LOG);
+    const double* sims = a.sims + b * a.n_rows;
+    const double* jac = a.jac + b * (long long)a.n_rows * P;
+    for (int g = blockIdx.y; g < G; g += gridDim.y) {
+        const double* ps = w.psum + b * w.psum_sb + (long long)g * w.psum_sg;
+        double* sums = a.sums ? a.sums + (b * G + g) * (long long)(3 + 2 * P) : nullptr;
+        double j1 = 0.0, j2 = 0.0;
+        if (a.phase != SBM_LOSS_PHASE_FINISH) {
+            if (c < P) {
+                const int q1 = a.grp_off[g + 1];
+#pragma unroll 4
+                for (int q = a.grp_off[g] + ty; q < q1; q += w.ry) {
+                    const int r = a.grp_rows[q];
+                    sbm_sfgrad_terms(is_log, jac[(long long)r * P + c], sims[r], a.data[r], a.sigma[r], j1, j2);
+                }
+            }
+            if (w.ry > 1) {
+                __syncthreads();
+                red1[threadIdx.x] = j1; red2[threadIdx.x] = j2;
+                __syncthreads();
+                if (ty == 0) { j1 = 0.0; j2 = 0.0; for (int k = 0; k < w.ry; ++k) { j1 += red1[k * w.cw + tx]; j2 += red2[k * w.cw + tx]; } }
+            }
+            if (a.phase == SBM_LOSS_PHASE_SUMS && ty == 0 && c < P) { sums[3 + c] = j1; sums[3 + P + c] = j2; }
+        } else if (ty == 0 && c < P) {
+            j1 = sums[3 + c]; j2 = sums[3 + P + c];
+        }
+        if (a.phase != SBM_LOSS_PHASE_SUMS && ty == 0 && c < P)
+            a.sfgrad[(b * G + g) * (long long)P + c] = sbm_sfgrad_value(is_log, a.sf[b * G + g], ps[0], ps[1], j1, j2);
+    }
+}
+
+__global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_wide_resid(const SbmLossArgs a, const SbmLossWide w)
+{
+    __shared__ double red[SBM_LOSS_THREADS / 32];
+    const long long b = blockIdx.y;
+    const bool is_log = (a.loss_kind == SBM_LOSS_LOG);
+    double* sims = a.sims + b * a.n_rows;
+    const double* sf = a.sf + b * a.n_groups;
+    const bool allbad = w.bad[b] != 0;
+    const int r0 = blockIdx.x * w.rchunk, r1 = min(a.n_rows, r0 + w.rchunk);
+    double acc = 0.0;
+    for (int r = r0 + threadIdx.x; r < r1; r += SBM_LOSS_THREADS) {
+        const int kind = a.row_kind[r];
+        double s = sims[r];
+        double res;
+        if (kind == SBM_ROW_MEASUREMENT) {
+            const int g = a.row_group[r];
+            if (g >= 0) s *= sf[g];
+            res = is_log ? (log(s) - log(a.data[r])) / a.sigma[r] : (s - a.data[r]) / a.sigma[r];
+        } else {
+            if (kind == SBM_ROW_SF_PRIOR) { s = log(sf[a.row_aux[r]]); sims[r] = s; }
+            res = (s - a.data[r]) / a.sigma[r];
+        }
+        if (allbad) res = __longlong_as_double(SBM_INF_BITS);
+        a.resid[b * a.n_rows + r] = res;
+        acc += res * res;
+    }
+    acc = sbm_block_sum(acc, red);
+    if (threadIdx.x == 0) w.ssrp[b * w.n_rchunks + blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_wide_jac(const SbmLossArgs a, const SbmLossWide w)
+{
+    __shared__ double red[SBM_LOSS_THREADS];
+    const long long b = blockIdx.z;
+    const int P = a.n_proj;
+    const int tx = threadIdx.x % w.cw, ty = threadIdx.x / w.cw;
+    const int c = blockIdx.x * w.cw + tx;
+    const bool is_log = (a.loss_kind == SBM_LOSS_LOG);
+    const double* sims = a.sims + b * a.n_rows;
+    const double* resid = a.resid + b * a.n_rows;
+    const double* sf = a.sf + b * a.n_groups;
+    const double* sfgrad = a.sfgrad + b * (long long)a.n_groups * P;
+    double* jac = a.jac + b * (long long)a.n_rows * P;
+    const bool allbad = w.bad[b] != 0;
+    const int r0 = blockIdx.y * w.rchunk, r1 = min(a.n_rows, r0 + w.rchunk);
+    double gacc = 0.0;
+    if (c < P) {
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += w.ry) {
+            double J = sbm_scaled_entry(a, is_log, c, a.row_kind[r], a.row_group[r], a.row_aux[r], jac[(long long)r * P + c], sims[r], sf, sfgrad);
+            if (allbad) J = __longlong_as_double(SBM_INF_BITS);
+            jac[(long long)r * P + c] = J;
+            gacc = fma(J, resid[r], gacc);
+        }
+    }
+    if (w.ry > 1) {
+        red[threadIdx.x] = gacc;
+        __syncthreads();
+        if (ty == 0) { gacc = 0.0; for (int k = 0; k < w.ry; ++k) gacc += red[k * w.cw + tx]; }
+    }
+    if (ty == 0 && c < P) w.gradp[(b * w.n_rchunks + blockIdx.y) * (long long)P + c] = gacc;
+}
+
+__global__ void __launch_bounds__(SBM_LOSS_THREADS) sbm_loss_wide_reduce(const SbmLossArgs a, const SbmLossWide w)
+{
+    const long long b = blockIdx.y;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int k = 0; k < w.n_rchunks; ++k) acc += w.ssrp[b * w.n_rchunks + k];
+        a.ssr[b] = 0.5 * acc;                          // base_project.py:807-827
+    }
+    if (a.jac && a.grad) {
+        const int c = blockIdx.x * SBM_LOSS_THREADS + threadIdx.x;
+        if (c < a.n_proj) {
+            double acc = 0.0;
+            for (int k = 0; k < w.n_rchunks; ++k) acc += w.gradp[(b * w.n_rchunks + k) * (long long)a.n_proj + c];
+            a.grad[b * a.n_proj + c] = acc;            // base_project.py:805
+        }
+    }
+}
+
+static inline cudaError_t sbm_launch_loss_wide(const SbmLossArgs& a, cudaStream_t st, int sm_count)
+{
+    SbmLossWide w;
+    const int P = a.n_proj, G = a.n_groups, R = a.n_rows;
+    w.cw = 1;
+    while (w.cw < P && w.cw < SBM_LOSS_THREADS) w.cw <<= 1;
+    w.ry = SBM_LOSS_THREADS / w.cw;
+    const int colblocks = (P + w.cw - 1) / w.cw;
+    // row chunks: enough CTAs for ~8 per SM over (column blocks x sets), chunks of at least 4 row groups
+    long long want = (8ll * (sm_count > 0 ? sm_count : 148) + colblocks * a.B - 1) / (colblocks * a.B);
+    if (want < 1) want = 1;
+    if (want > 1024) want = 1024;
+    w.rchunk = (int)((R + want - 1) / want);
+    if (w.rchunk < 4 * w.ry) w.rchunk = 4 * w.ry;
+    if (w.rchunk > R) w.rchunk = R;
+    w.n_rchunks = (R + w.rchunk - 1) / w.rchunk;
+    const bool own_psum = (a.sums == nullptr);
+    const size_t n_ps = own_psum ? (size_t)a.B * (G > 0 ? G : 0) * 3 : 0;
+    const size_t n_ssrp = (size_t)a.B * w.n_rchunks;
+    const size_t n_gradp = a.jac ? (size_t)a.B * w.n_rchunks * P : 0;
+    const size_t n_bad = ((size_t)a.B + 1) / 2;
+    double* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync(&scratch, (n_ps + n_ssrp + n_gradp + n_bad + 1) * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    w.psum = own_psum ? scratch : a.sums;
+    w.psum_sg = own_psum ? 3 : 3 + 2 * P;
+    w.psum_sb = (long long)G * w.psum_sg;
+    w.ssrp = scratch + n_ps;
+    w.gradp = w.ssrp + n_ssrp;
+    w.bad = reinterpret_cast<int*>(w.gradp + n_gradp);
+    cudaMemsetAsync(w.bad, 0, n_bad * sizeof(double), st);
+    const unsigned Bz = (unsigned)a.B;
+    sbm_loss_wide_rows<<<dim3(w.n_rchunks, Bz), SBM_LOSS_THREADS, 0, st>>>(a, w);
+    if (G > 0) {
+        const int gblocks = (G + SBM_LOSS_THREADS / 32 - 1) / (SBM_LOSS_THREADS / 32);
+        sbm_loss_wide_sf<<<dim3(gblocks < 4096 ? gblocks : 4096, Bz), SBM_LOSS_THREADS, 0, st>>>(a, w);
+        if (a.jac) sbm_loss_wide_sfgrad<<<dim3(colblocks, G < 16384 ? G : 16384, Bz), SBM_LOSS_THREADS, 0, st>>>(a, w);
+    }
+    if (a.phase != SBM_LOSS_PHASE_SUMS) {
+        sbm_loss_wide_resid<<<dim3(w.n_rchunks, Bz), SBM_LOSS_THREADS, 0, st>>>(a, w);
+        if (a.jac) sbm_loss_wide_jac<<<dim3(colblocks, w.n_rchunks, Bz), SBM_LOSS_THREADS, 0, st>>>(a, w);
+        sbm_loss_wide_reduce<<<dim3((a.jac && a.grad) ? (P + SBM_LOSS_THREADS - 1) / SBM_LOSS_THREADS : 1, Bz), SBM_LOSS_THREADS, 0, st>>>(a, w);
+    }
+    e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    return e;
+}
+
 // tile kernel launch shape: warps per CTA so that two CTAs share an SM's shared memory
 static inline bool sbm_loss_tile_shape(const SbmLossArgs& a, int n_grp_rows, SbmLossTileShape& sp)
 {
@@ -559,6 +790,10 @@ static inline cudaError_t sbm_launch_loss(const SbmLossArgs& a, cudaStream_t st,
         else sbm_loss_tile_kernel<false><<<(unsigned)blocks, sp.warps * 32, sp.smem, st>>>(a, sp);
         return cudaGetLastError();
     }
+    // few sets with big Jacobians: spread each set over the grid (SBM_LOSS_WIDE=0 / 1 overrides the choice)
+    bool wide = a.B < 2ll * (sm_count > 0 ? sm_count : 148) && (long long)a.n_rows * a.n_proj >= 32768 && a.B < 65536;
+    if (const char* e = getenv("SBM_LOSS_WIDE")) wide = (atoi(e) != 0) && a.B < 65536;
+    if (wide) return sbm_launch_loss_wide(a, st, sm_count);
     long long blocks = a.B < 1048576 ? a.B : 1048576;
     size_t gs = (size_t)(3 * (a.n_groups > 0 ? a.n_groups : 1)) * sizeof(double);
     sbm_loss_kernel<<<(unsigned)blocks, SBM_LOSS_THREADS, gs, st>>>(a);

@@ -108,3 +108,85 @@ def test_normal_equations(c4_eval):
         A, g, rr = engine.unpack_normal_equations(engine.normal_equations_device(J, r), P)
         assert torch.allclose(A, torch.einsum('bri,brj->bij', J, J), rtol=1e-12, atol=1e-12)
         assert torch.allclose(g, torch.einsum('bri,br->bi', J, r), rtol=1e-12, atol=1e-12)
+
+
+def _eval_with_env(proj, theta, with_jac, wide):
+    """One evaluation through the kernels that keep J in global memory: wide = '1' the row-parallel kernels
+    (sbm_loss_wide_*), '0' the CTA-per-set kernel."""
+    import os
+    import torch
+    old = os.environ.get('SBM_LOSS_WIDE')
+    os.environ['SBM_LOSS_WIDE'] = wide
+    proj.loss_generic_kernel = True
+    try:
+        o = _clone(proj.evaluate_device(theta, with_jac))
+        torch.cuda.synchronize()
+    finally:
+        proj.loss_generic_kernel = False
+        if old is None:
+            del os.environ['SBM_LOSS_WIDE']
+        else:
+            os.environ['SBM_LOSS_WIDE'] = old
+    return o
+
+
+def _assert_close_outputs(a, b, keys):
+    import torch
+    for k in keys:
+        if k not in a or a[k] is None or a[k].numel() == 0:
+            continue
+        scale = max(b[k].abs().max().item(), 1e-300)
+        err = (a[k] - b[k]).abs().max().item()
+        print(k, 'max abs diff %.3e of scale %.3e' % (err, scale))
+        assert torch.allclose(a[k], b[k], rtol=1e-10, atol=1e-12 * scale), (k, err, scale)
+
+
+def test_row_parallel_kernels_match_cta_per_set_kernel(c4_eval, golden):
+    """The wide path (few sets, big Jacobians: C2 through the Project) on shapes the other kernels also take: C4 (two
+    scale-factor groups, 22 columns -> 32 x 4 thread shape), the reference's two-measurement project with parameter
+    priors, and the 1-state project with the log loss and a scale-factor prior."""
+    import torch
+    from fixtures import project_1state, project_mm_two_measures
+    from sysbio_modeling_b200 import LogSquareLossFunction
+    proj, theta = c4_eval
+    keys = ('resid', 'ssr', 'sf', 'sfgrad', 'jac', 'grad', 'sims')
+    _assert_close_outputs(_eval_with_env(proj, theta, True, '1'), _eval_with_env(proj, theta, True, '0'), keys)
+    _assert_close_outputs(_eval_with_env(proj, theta, False, '1'), _eval_with_env(proj, theta, False, '0'), ('resid', 'ssr', 'sf'))
+    rng = np.random.default_rng(3)
+    p2, _ = project_mm_two_measures(golden)
+    th = torch.from_numpy(np.log(0.01) + 0.2 * rng.standard_normal((5, p2.n_project_params))).cuda()
+    _assert_close_outputs(_eval_with_env(p2, th, True, '1'), _eval_with_env(p2, th, True, '0'), keys)
+    p3, _ = project_1state(loss=LogSquareLossFunction)
+    p3.set_scale_factor_log_prior('Variable_1', np.log(3.5), 0.4)
+    th = torch.from_numpy(np.log(0.01) + 0.2 * rng.standard_normal((3, p3.n_project_params))).cuda()
+    _assert_close_outputs(_eval_with_env(p3, th, True, '1'), _eval_with_env(p3, th, True, '0'), keys)
+    # a NaN simulation poisons the whole set (squared_loss_function.py:28-32), the other sets are untouched
+    thb = th.clone()
+    thb[1, 0] = float('nan')
+    a, b = _eval_with_env(p3, thb, True, '1'), _eval_with_env(p3, thb, True, '0')
+    assert torch.isinf(a['resid'][1]).all() and torch.isinf(b['resid'][1]).all()
+    assert torch.isfinite(a['resid'][0]).all() and torch.isfinite(a['resid'][2]).all()
+
+
+def test_c2_project_wide_jacobian_block_structure_and_gradient():
+    """C2 through the Project at reduced size (256 experiments x 16 rows, 1,024 project columns: the shape the
+    row-parallel kernels are chosen for by default), with and without the scale-factor group shared by every experiment:
+    J^T r from the kernels equals J^T r formed from their outputs, an experiment's rows touch its own four columns only
+    (no groups) and the default choice equals the CTA-per-set kernel."""
+    import torch
+    from tools import workloads as wl
+    E = 256
+    for shared in (False, True):
+        proj, _ = wl.c2_project(E, shared_scale_factor=shared)
+        th = torch.from_numpy(wl.c2_theta(E, 2)).cuda()
+        o = _clone(proj.evaluate_device(th, True))
+        torch.cuda.synchronize()
+        assert o['jac'].shape == (2, 16 * E, 4 * E)
+        g = torch.einsum('brc,br->bc', o['jac'], o['resid'])
+        assert torch.allclose(o['grad'], g, rtol=1e-10, atol=1e-10 * g.abs().max().item())
+        assert torch.allclose(o['ssr'], 0.5 * (o['resid'] ** 2).sum(1), rtol=1e-12)
+        if not shared:
+            assert torch.count_nonzero(o['jac'][:, :16, 4:]) == 0
+            assert torch.count_nonzero(o['jac'][:, :16, :4]) > 0
+        b = _eval_with_env(proj, th, True, '0')
+        _assert_close_outputs(o, b, ('resid', 'ssr', 'sf', 'sfgrad', 'jac', 'grad') if shared else ('resid', 'ssr', 'jac', 'grad'))
