@@ -576,11 +576,13 @@ def main():
     if world > 1:
         dist.barrier()
 
-    if rank == 0 and world == 1:
+    if rank == 0:
+        # (at N > 1 too: rank 0's first 8 sets; the other ranks have left the timed region and wait in the teardown)
         try:
             line['parity'] = parity_check(proj, make_oracle, theta_np[:8], gpu_first)
         except Exception as exc:                      # the bench line must survive a broken checker
             line['parity'] = {'error': repr(exc)}
+    if rank == 0 and world == 1:
         if not args.no_configs:
             del hb, flush
             for k in list(bufs.keys()):
