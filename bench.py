@@ -222,7 +222,7 @@ def _time_eval(proj, theta, with_jac, solver, reps):
     best = None
     for _ in range(reps):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        opts = proj._opts('dp5' if with_jac else solver)
+        opts = proj._opts(proj._jac_solver() if with_jac else solver)
         bufs['sims'].zero_()
         bufs['counters'].zero_()
         ev[0].record()
@@ -265,6 +265,15 @@ def extra_configs(peak_tf, quick=False):
                  'steps_per_solve': cnt['steps'] / B3, 'lu_per_solve': cnt['lu'] / B3, 'failed': failed,
                  'algorithmic_flops': flops, 'flops_per_step': f_step, 'tflops': flops / ms_i / 1e9,
                  'frac_fp64_peak': flops / ms_i / 1e9 / peak_tf}
+    # (beyond the config: the stiff model's scaled Jacobian through RODAS4 with forward sensitivities, 3 x 3 columns)
+    try:
+        Bj = B3 // 8
+        (ms_ij, ms_lj), cntj, failedj = _time_eval(proj, th[:Bj].contiguous(), True, 'rodas4', 2)
+        out['c3'].update({'jacobian_sets': Bj, 'jacobian_evals_per_sec': Bj / (ms_ij + ms_lj) * 1e3,
+                          'sbm_rodas4_sens_ms': ms_ij, 'jacobian_steps_per_solve': cntj['steps'] / Bj,
+                          'jacobian_failed': failedj})
+    except Exception as exc:
+        out['c3']['jacobian_error'] = repr(exc)
     del th
     # ---- C5: EGFR-scale network (25 states, 52 parameters), 131,072 walkers, SSR only, plain DP5 ----
     B5 = 16384 if quick else 131072

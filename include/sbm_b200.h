@@ -29,7 +29,8 @@ extern "C" {
 
 /* solvers */
 #define SBM_SOLVER_DP5    0   /* adaptive Dormand-Prince 5(4), non-stiff                           */
-#define SBM_SOLVER_RODAS4 1   /* Rosenbrock RODAS4 with per-trajectory dense LU, stiff, states only */
+#define SBM_SOLVER_RODAS4 1   /* Rosenbrock RODAS4 with per-trajectory dense LU, stiff; at most 12 states.  With a Jacobian
+                                 buffer: forward sensitivities through the same LU (autonomous models only) */
 
 /* loss functions (reference project/loss_functions/squared_loss/) */
 #define SBM_LOSS_SQUARE     0 /* squared_loss_function.py:27-80                                     */

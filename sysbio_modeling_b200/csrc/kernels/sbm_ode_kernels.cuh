@@ -712,6 +712,279 @@ __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// RODAS4 with forward sensitivities (stiff models whose Jacobian the optimiser needs: the reference's LSODA switches to BDF
+// on the augmented system, ode_model.py:122-123).  One thread per trajectory, autonomous models of at most 12 states.
+//
+// The augmented system z = [y | S_1 .. S_NF], S_j' = J(y) S_j + G_j(y), has the block lower-triangular Jacobian
+//     dF/dz = [ J  0 ... ; B_1  J ... ; ... ],   B_j = d(J S_j + G_j)/dy,
+// so every Rosenbrock stage is solved by block forward substitution with ONE LU of E = I/(h gamma) - J per step:
+//     E u_i(y)   = rhs_i(y)
+//     E u_i(S_j) = rhs_i(S_j) + B_j u_i(y),       B_j u = DJ(u) S_j + DG(u)[:, j]     (sbm_dJG: exact, emitted from SymPy)
+// A Rosenbrock method (unlike a W-method) keeps its order only with the exact Jacobian, hence the exact B_j.  The error
+// estimate (u_6) and the step-size control run over the whole augmented state, as in the Dormand-Prince kernels.
+// The stage loop is not unrolled: one copy of the model code, coefficient tables in constant memory; the increments of the
+// sensitivity columns live in local memory (indexed by column at run time).
+// ---------------------------------------------------------------------------------------------
+#if SBM_AUTONOMOUS && defined(SBM_HAS_DJG)
+__constant__ double sbm_ro_a[6][5] = {
+    {0.0, 0.0, 0.0, 0.0, 0.0},
+    {RO_A21, 0.0, 0.0, 0.0, 0.0},
+    {RO_A31, RO_A32, 0.0, 0.0, 0.0},
+    {RO_A41, RO_A42, RO_A43, 0.0, 0.0},
+    {RO_A51, RO_A52, RO_A53, RO_A54, 0.0},
+    {RO_A51, RO_A52, RO_A53, RO_A54, 1.0}};
+__constant__ double sbm_ro_c[6][5] = {
+    {0.0, 0.0, 0.0, 0.0, 0.0},
+    {RO_C21, 0.0, 0.0, 0.0, 0.0},
+    {RO_C31, RO_C32, 0.0, 0.0, 0.0},
+    {RO_C41, RO_C42, RO_C43, 0.0, 0.0},
+    {RO_C51, RO_C52, RO_C53, RO_C54, 0.0},
+    {RO_C61, RO_C62, RO_C63, RO_C64, RO_C65}};
+
+template <int BLOCK>
+__device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
+{
+    constexpr int N = SBM_N, NF = SBM_NF;
+    __shared__ double sp[BLOCK * SBM_NPP];
+    const int tid = threadIdx.x;
+    const long long traj = (long long)blockIdx.x * BLOCK + tid;
+    if (traj >= a.B * (long long)a.E) return;
+    const int e = (int)(traj % a.E);
+    const long long b = traj / a.E;
+
+    double* p = sp + tid * SBM_NPP;
+    for (int m = 0; m < SBM_NP; ++m) {
+        const int c = a.pmap[e * SBM_NP + m];
+        p[m] = (c >= 0) ? exp(a.theta[b * a.theta_sb + c * a.theta_sp]) : a.pfix[e * SBM_NP + m];
+    }
+
+    double y[N], Y[N], f0[N], fi[N];
+    double ky[6][N];
+    double S[NF][N], U[6][NF][N];
+    double Jv0[SBM_NJ], Gv0[SBM_NG], Jvi[SBM_NJ], Gvi[SBM_NG], DJv[SBM_NJ], DGv[SBM_NG];
+    double A[N * N];
+    int piv[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = a.y0[e * N + i];
+    for (int j = 0; j < NF; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) S[j][i] = 0.0;
+
+    const double rtol = a.rtol, atol = a.atol;
+    const int kt0 = a.tout_off[e], kt1 = a.tout_off[e + 1];
+    const double tend = (kt1 > kt0) ? a.tout[kt1 - 1] : 0.0;
+    unsigned nstep = 0, nrej = 0, nrhs = 0, nlu = 0;
+    int status = SBM_OK;
+    double t = 0.0;
+
+    // initial step from the local rate of change of the states (as sbm_rodas4_impl)
+    double h;
+    {
+        sbm_f(t, y, p, f0);
+        nrhs++;
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sk = atol + rtol * fabs(y[i]);
+            d0 = fma(y[i] / sk, y[i] / sk, d0);
+            d1 = fma(f0[i] / sk, f0[i] / sk, d1);
+        }
+        d0 = sqrt(d0 / N); d1 = sqrt(d1 / N);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, tend);
+#pragma unroll
+        for (int i = 0; i < N; ++i) Y[i] = fma(h0, f0[i], y[i]);
+        sbm_f(t + h0, Y, p, fi);
+        nrhs++;
+        double d2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sk = atol + rtol * fabs(y[i]);
+            const double q = (fi[i] - f0[i]) / sk;
+            d2 = fma(q, q, d2);
+        }
+        d2 = sqrt(d2 / N) / h0;
+        const double dm = fmax(d1, d2);
+        const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.25);
+        // the sensitivities start at zero and grow from G: a cautious first step (the controller opens it up quickly)
+        h = 0.01 * fmin(fmin(100.0 * h0, h1), tend);
+        if (a.h0 > 0.0) h = fmin(a.h0, tend);
+    }
+
+    bool last_rejected = false, first = true, poison = false;
+    double hacc = h, erracc = 1e-2;
+    unsigned naccept = 0;
+    const double inv_naug = 1.0 / (double)(N * (NF + 1));
+
+    for (int kt = kt0; kt < kt1; ++kt) {
+        const double tk = a.tout[kt];
+        while (status == SBM_OK && t < tk) {
+            const double hprop = h;
+            bool clipped = false;
+            if (t + 1.01 * h >= tk) { h = tk - t; clipped = true; }
+            if (nstep >= (unsigned)a.max_steps) { status = SBM_ERR_MAXSTEPS; break; }
+            if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) { status = SBM_ERR_UNDERFLOW; break; }
+            nstep++;
+
+            sbm_fJG<1>(t, y, p, f0, Jv0, Gv0);
+            sbm_jac_dense(t, y, p, A);
+            const double fac = 1.0 / (h * RO_GAMMA);
+#pragma unroll
+            for (int q = 0; q < N * N; ++q) A[q] = -A[q];
+#pragma unroll
+            for (int i = 0; i < N; ++i) A[i * N + i] += fac;
+            const bool lu_ok = sbm_lu_factor(A, piv);
+            nlu++;
+            const double hi = 1.0 / h;
+
+#pragma unroll 1
+            for (int st = 0; st < 6; ++st) {
+                double ca[5], cc[5];
+#pragma unroll
+                for (int l = 0; l < 5; ++l) { ca[l] = sbm_ro_a[st][l]; cc[l] = hi * sbm_ro_c[st][l]; }
+                // ---- state block ----
+                double r[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    double v = y[i], w = 0.0;
+                    for (int l = 0; l < st; ++l) { v = fma(ca[l], ky[l][i], v); w = fma(cc[l], ky[l][i], w); }
+                    Y[i] = v;
+                    r[i] = w;
+                }
+                const double* Jp = Jv0;
+                const double* Gp = Gv0;
+                const double* fp = f0;
+                if (st > 0) {
+                    sbm_fJG<1>(t, Y, p, fi, Jvi, Gvi);
+                    Jp = Jvi; Gp = Gvi; fp = fi;
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) r[i] += fp[i];
+                sbm_lu_solve(A, piv, r);
+#pragma unroll
+                for (int i = 0; i < N; ++i) ky[st][i] = r[i];
+                // ---- sensitivity blocks: same LU, right-hand side + B_j u_i(y) ----
+                sbm_dJG(t, y, p, r, DJv, DGv);
+                for (int j = 0; j < NF; ++j) {
+                    double Sj[N], w[N], r1[N], r2[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        double v = S[j][i], ww = 0.0;
+                        for (int l = 0; l < st; ++l) { v = fma(ca[l], U[l][j][i], v); ww = fma(cc[l], U[l][j][i], ww); }
+                        Sj[i] = v;
+                        w[i] = ww;
+                    }
+                    sbm_col(fp, Jp, Gp, Sj, j + 1, r1);
+                    sbm_col(fp, DJv, DGv, S[j], j + 1, r2);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) w[i] += r1[i] + r2[i];
+                    sbm_lu_solve(A, piv, w);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) U[st][j][i] = w[i];
+                }
+            }
+            nrhs += 6;
+
+            // new state = stage value of stage 6 + u_6; u_6 is the error estimate.  (Y holds the stage value of stage 6.)
+            double sq = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                Y[i] += ky[5][i];
+                const double sk = atol + rtol * fmax(fabs(y[i]), fabs(Y[i]));
+                const double q = ky[5][i] * sbm_rcp(sk);
+                sq = fma(q, q, sq);
+            }
+            for (int j = 0; j < NF; ++j) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    double v = S[j][i];
+#pragma unroll
+                    for (int l = 0; l < 5; ++l) v = fma(sbm_ro_a[5][l], U[l][j][i], v);
+                    const double u6 = U[5][j][i];
+                    v += u6;
+                    const double sk = atol + rtol * fmax(fabs(S[j][i]), fabs(v));
+                    const double q = u6 * sbm_rcp(sk);
+                    sq = fma(q, q, sq);
+                    U[5][j][i] = v;                    // the slot now holds the candidate S_j(t + h)
+                }
+            }
+            const double err = sqrt(sq * inv_naug);
+
+            if (lu_ok && err <= 1.0) {
+                double facr = fmax(1.0 / 6.0, fmin(5.0, pow(fmax(err, 1e-300), 0.25) / 0.9));
+                if (naccept >= 1) {
+                    double facgus = (hacc / h) * pow(err * err / erracc, 0.25) / 0.9;
+                    facgus = fmax(1.0 / 6.0, fmin(5.0, facgus));
+                    facr = fmax(facr, facgus);
+                }
+                hacc = h;
+                erracc = fmax(1e-2, err);
+                naccept++;
+                t = clipped ? tk : t + h;
+#pragma unroll
+                for (int i = 0; i < N; ++i) y[i] = Y[i];
+                for (int j = 0; j < NF; ++j)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) S[j][i] = U[5][j][i];
+                double hnew = h / facr;
+                if (last_rejected) hnew = fmin(hnew, h);
+                if (clipped) hnew = fmax(hnew, hprop);
+                h = hnew;
+                last_rejected = false;
+                first = false;
+            } else {
+                nrej++;
+                if (lu_ok && err == err && err < 1e300) {
+                    const double facr = fmax(1.0 / 6.0, fmin(5.0, pow(err, 0.25) / 0.9));
+                    h = first ? 0.1 * h : h / facr;
+                } else {
+                    h *= 0.5;
+                    if (h < 1e-300) { status = SBM_ERR_NONFINITE; break; }
+                }
+                last_rejected = true;
+            }
+        }
+        if (status != SBM_OK) poison = true;
+        // ---- observable rows of this output time: value and d/dtheta row (chain rule to log-parameters, base_project.py:443-488) ----
+        const int r0 = a.orow_off[kt], r1 = a.orow_off[kt + 1];
+        for (int r = r0; r < r1; ++r) {
+            const unsigned long long mask = a.row_mask[r];
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc += ((mask >> i) & 1ull) ? y[i] : 0.0;
+            if (poison) acc = __longlong_as_double(0x7ff8000000000000ll);
+            a.sims[b * a.n_rows + a.row_sim[r]] = acc;
+            if (a.jac != nullptr) {
+                for (int j = 0; j < NF; ++j) {
+                    const int m = sbm_free_idx[j];
+                    const int pc = a.jac_raw ? j : a.pmap[e * SBM_NP + m];
+                    if (pc < 0) continue;
+                    double v = 0.0;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) v += ((mask >> i) & 1ull) ? S[j][i] : 0.0;
+                    v *= a.jac_raw ? 1.0 : p[m];
+                    if (poison) v = __longlong_as_double(0x7ff8000000000000ll);
+                    double* dst = a.jac + ((b * a.n_rows + a.row_jac[r]) * (long long)a.n_proj + pc);
+                    if (a.jac_atomic) atomicAdd(dst, v); else *dst = v;
+                }
+            }
+        }
+    }
+
+    a.status[traj] = status;
+    atomicAdd(a.counters + SBM_CNT_STEPS, (unsigned long long)nstep);
+    atomicAdd(a.counters + SBM_CNT_REJECT, (unsigned long long)nrej);
+    atomicAdd(a.counters + SBM_CNT_RHS, (unsigned long long)nrhs);
+    atomicAdd(a.counters + SBM_CNT_LU, (unsigned long long)nlu);
+    atomicAdd(a.counters + SBM_CNT_TRAJ, 1ull);
+}
+
+#define SBM_DEFINE_RODAS4_SENS(NAME, BLOCK)                                                 \
+    extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \
+    { sbm_rodas4_sens_impl<BLOCK>(a); }
+#endif  /* SBM_AUTONOMOUS && SBM_HAS_DJG */
+
+// ---------------------------------------------------------------------------------------------
 // kernel entry points are instantiated by the host (sbm_api.cu appends SBM_DEFINE_* lines)
 // ---------------------------------------------------------------------------------------------
 #define SBM_DEFINE_DP5(NAME, G, C, SENS, BLOCK)                                             \

@@ -143,6 +143,7 @@ struct sbm_model {
     int ctW = 0, ctC = 0, ctCS = 0, ctXW = 0, ct_tmem_cols = 0, ct_dyn_smem = 0, ct_ctas_per_sm = 0, sm_count = 0;
     bool ct_ok = false;
     bool has_rodas = true;
+    bool has_rodas_sens = false; // RODAS4 with sensitivities: autonomous model, the emitter provided sbm_dJG
     int layout = 0;              // 0 auto, 1 lane-per-column groups, 2 CTA-transposed
     std::string source;          // full NVRTC translation unit (kept for diagnostics)
     std::string log;
@@ -151,7 +152,7 @@ struct sbm_model {
     bool loaded = false;
     int device = -1;             // device whose context holds `mod` (one module per model; see ensure_loaded)
     CUmodule mod = nullptr;
-    KernelSlot dp5_plain, dp5_sens, dp5_ct, rodas4;
+    KernelSlot dp5_plain, dp5_sens, dp5_ct, rodas4, rodas4_sens;
     std::mutex mu;
 };
 
@@ -261,6 +262,9 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     // the Rosenbrock kernel keeps the dense Jacobian and its LU in registers: fine up to ~12 states, hopeless beyond
     m->has_rodas = desc->n_vars <= 12;
     if (m->has_rodas) src << "SBM_DEFINE_RODAS4(sbm_rodas4_plain, " << m->block_plain << ")\n";
+    m->has_rodas_sens = m->has_rodas && desc->n_free >= 1 && strstr(model_src, "#define SBM_HAS_DJG 1") != nullptr &&
+                        strstr(model_src, "#define SBM_AUTONOMOUS 1") != nullptr;
+    if (m->has_rodas_sens) src << "SBM_DEFINE_RODAS4_SENS(sbm_rodas4_sens, " << m->block_plain << ")\n";
     m->source = src.str();
 
     const std::string archopt = "--gpu-architecture=" + m->arch;
@@ -357,6 +361,7 @@ static int ensure_loaded(sbm_model* m)
         if ((r = slot_load(m, m->dp5_plain, "sbm_dp5_plain"))) return r;
         if ((r = slot_load(m, m->dp5_sens, "sbm_dp5_sens"))) return r;
         if (m->has_rodas && (r = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return r;
+        if (m->has_rodas_sens && (r = slot_load(m, m->rodas4_sens, "sbm_rodas4_sens"))) return r;
         DRV(driver().cuFuncSetAttribute_(m->dp5_sens.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
         DRV(driver().cuFuncSetAttribute_(m->dp5_plain.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_plain));
         RT(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -550,7 +555,8 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
     if (!m) return fail(SBM_E_INVALID, "sbm_solve: this is a loss-only plan (created without a model)");
     int rc = ensure_loaded(m);
     if (rc) return rc;
-    if (o->solver == SBM_SOLVER_RODAS4 && jac) return fail(SBM_E_INVALID, "RODAS4 kernel integrates states only (no sensitivities)");
+    if (o->solver == SBM_SOLVER_RODAS4 && jac && !m->has_rodas_sens)
+        return fail(SBM_E_INVALID, "RODAS4 with sensitivities needs an autonomous model with at most 12 states and a free parameter");
     if (o->solver != SBM_SOLVER_DP5 && o->solver != SBM_SOLVER_RODAS4) return fail(SBM_E_INVALID, "unknown solver");
     if (o->solver == SBM_SOLVER_RODAS4 && !m->has_rodas)
         return fail(SBM_E_INVALID, "RODAS4 kernel (in-register dense LU) supports at most 12 states");
@@ -580,7 +586,8 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
     long long threads;
     int block = m->block_plain, dyn = 0;
     long long blocks = -1;
-    if (o->solver == SBM_SOLVER_RODAS4) { ks = &m->rodas4; threads = ntraj; }
+    if (o->solver == SBM_SOLVER_RODAS4 && jac) { ks = &m->rodas4_sens; threads = ntraj; }
+    else if (o->solver == SBM_SOLVER_RODAS4) { ks = &m->rodas4; threads = ntraj; }
     else if (jac && m->ct_ok && m->layout != 1) {
         // persistent CTAs, 32 trajectories in flight each, refilled from a global queue
         ks = &m->dp5_ct; block = (m->ctW + m->ctXW) * 32; dyn = m->ct_dyn_smem; threads = 0;

@@ -31,7 +31,7 @@ class OdeModel(ModelABC):
     symbolic : SymbolicModel, optional - skip tracing.
     fixed_params : parameters without sensitivity columns (reference ``sympy_tools.py:137-139``).
     rtol, atol : tolerances; defaults are the reference's hard-coded 1e-10 (``ode_model.py:122-123``).
-    solver : 'dp5' (non-stiff) or 'rodas4' (stiff, states only).
+    solver : 'dp5' (non-stiff) or 'rodas4' (stiff; with sensitivities for autonomous models of at most 12 states).
     """
 
     def __init__(self, model, sens_model, n_vars, param_order, model_name='Model', use_jit=True,
@@ -133,7 +133,8 @@ class OdeModel(ModelABC):
         jac = torch.zeros((1, plan.t.n_rows, NF), dtype=torch.float64, device=dev) if with_sens else None
         status = torch.zeros((1, nb), dtype=torch.int32, device=dev)
         counters = torch.zeros(_lib.SBM_N_COUNTERS, dtype=torch.int64, device=dev)
-        solver = self.solver if not with_sens else 'dp5'
+        # sensitivities: Dormand-Prince, or RODAS4 with forward sensitivities when the model was declared stiff
+        solver = self.solver if (not with_sens or str(self.solver).lower() in ('rodas4', 'rodas')) else 'dp5'
         opts = plan.opts(solver, self.rtol, self.atol, self.max_steps, jac_raw=True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()

@@ -339,6 +339,11 @@ class Project(object):
             self._device_plan = engine.DevicePlan(self._model.compiled, self._plan_tables)
         return self._device_plan
 
+    def _jac_solver(self):
+        """Integrator of the sensitivity path: the project's stiff choice carries over to the Jacobian (RODAS4 with forward
+        sensitivities, autonomous models of at most 12 states - the C ABI refuses other models), otherwise Dormand-Prince."""
+        return 'rodas4' if str(self.solver).lower() in ('rodas4', 'rodas') else 'dp5'
+
     def _opts(self, solver=None):
         return engine.DevicePlan.opts(solver or self.solver, self.rtol, self.atol, self.max_steps)
 
@@ -548,14 +553,14 @@ class Project(object):
         """Reference :731-771.  One sensitivity-augmented solve per experiment (its state column doubles as
         the plain simulation, so the reference's extra ``_sim_experiments`` pass is not repeated)."""
         theta = np.asarray(project_param_vector, dtype=np.float64)
-        out = self.device_plan.jacobian_host(theta[None, :], self._opts('dp5'), self._loss_name(), self._flags())
+        out = self.device_plan.jacobian_host(theta[None, :], self._opts(self._jac_solver()), self._loss_name(), self._flags())
         self._store_last(theta, out, True)
         return pd.DataFrame(out['jac'][0], index=self._index, columns=self.get_ordered_project_params())
 
     def calc_rss_gradient(self, project_param_vector, *args):
         """Reference :773-805: (J^T r) - formed in the loss epilogue from the same solve."""
         theta = np.asarray(project_param_vector, dtype=np.float64)
-        out = self.device_plan.jacobian_host(theta[None, :], self._opts('dp5'), self._loss_name(), self._flags())
+        out = self.device_plan.jacobian_host(theta[None, :], self._opts(self._jac_solver()), self._loss_name(), self._flags())
         self._store_last(theta, out, True)
         return pd.Series(out['grad'][0], index=self.get_ordered_project_params())
 
@@ -603,7 +608,7 @@ class Project(object):
 
     def jacobian_batch(self, thetas):
         """thetas f8[B, n_proj] -> dict(jac [B, n_rows, n_proj], model_jac, resid, ssr, grad [B, n_proj], ...)."""
-        out = self.device_plan.jacobian_host(np.asarray(thetas, dtype=np.float64), self._opts('dp5'),
+        out = self.device_plan.jacobian_host(np.asarray(thetas, dtype=np.float64), self._opts(self._jac_solver()),
                                              self._loss_name(), self._flags())
         self._warn_failed(out['status'])
         return out
@@ -639,7 +644,7 @@ class Project(object):
             jac = buf('jac', (B, t.n_rows, t.n_proj))
             sfgrad = buf('sfgrad', (B, max(t.n_groups, 1), t.n_proj))
             grad = buf('grad', (B, t.n_proj))
-        opts = self._opts('dp5' if with_jacobian else solver)
+        opts = self._opts(self._jac_solver() if with_jacobian else solver)
         plan.solve_device(theta, opts, sims, jac, status, counters)
         plan.loss_device(theta, sims, jac, resid, ssr, sf, sfgrad, grad, loss=self._loss_name(), flags=self._flags())
         return o

@@ -1007,6 +1007,30 @@ def emit_cuda(sm, pow_via_explog=True, ct_cols=0):
     L.append('}')
     L.append('')
 
+    # --- directional derivative of the non-zeros of J and G along a state direction u (same sparse layout as sbm_fJG):
+    #     DJv[q] = sum_l dJ_q/dy_l u[l],  DGv[q] = sum_l dG_q/dy_l u[l].  The Rosenbrock kernel with sensitivities needs it: the
+    #     Jacobian of the augmented system [y | S_j] has the off-diagonal blocks B_j = d(J S_j + G_j)/dy, and a Rosenbrock
+    #     method keeps its order only with the exact Jacobian (B_j u = DJ(u) S_j + DG(u)[:, j]).
+    if sm.autonomous and N <= 12 and NF >= 1:
+        usyms = [sp.Symbol('u[%d]' % l, real=True) for l in range(N)]
+
+        def ddir(e):
+            e = sp.sympify(e)
+            return sum((sp.diff(e, v) * usyms[l] for l, v in enumerate(sm.var_syms) if e.has(v)), sp.Integer(0))
+        dJ_x = [X(ddir(sm.J[k])) for k in jkeys]
+        dG_x = [X(ddir(sm.G[k])) for k in gkeys]
+        rep, red = sp.cse(dJ_x + dG_x, symbols=sp.numbered_symbols('h_'), optimizations='basic')
+        outs = [('DJv[%d]' % q, red[q]) for q in range(len(jkeys))]
+        outs += [('DGv[%d]' % q, red[len(jkeys) + q]) for q in range(len(gkeys))]
+        L.append('#define SBM_HAS_DJG 1')
+        L.append('__device__ __forceinline__ void sbm_dJG(const double t, const double* __restrict__ y,')
+        L.append('        const double* __restrict__ p, const double* __restrict__ u,')
+        L.append('        double* __restrict__ DJv, double* __restrict__ DGv)')
+        L.append('{')
+        _emit_block(L, rep, outs, pr)
+        L.append('}')
+        L.append('')
+
     src = '\n'.join(L)
     flops_sens = flops_fJG + NF * flops_col + len(gkeys)
     return CudaModelSource(source=src, n_vars=N, n_params=NP, n_free=NF, free_idx=list(sm.free_idx),
