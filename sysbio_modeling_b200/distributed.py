@@ -276,7 +276,7 @@ class _CudaExperimentEvaluator(object):
         jac = torch.empty((B, t.n_rows, t.n_proj), **f64) if with_jacobian else None
         status = torch.zeros((B, t.E), dtype=torch.int32, device=dev)
         counters = torch.zeros((_lib.SBM_N_COUNTERS,), dtype=torch.int64, device=dev)
-        plan.solve_device(theta, proj._opts(proj._jac_solver() if with_jacobian else None), sims, jac, status, counters)
+        plan.solve_device(theta, proj._opts(proj._jac_solver(theta) if with_jacobian else proj._concrete_solver(False, theta)), sims, jac, status, counters)
         sums = torch.zeros((B, max(t.n_groups, 1), 3 + 2 * t.n_proj), **f64)
         if t.n_groups:
             plan.loss_sums_device(theta, sims, jac, sums, loss=proj._loss_name(), flags=proj._flags())

@@ -57,12 +57,15 @@ class Project(object):
             raise ValueError("Loss Function %s does not support scale factors" % type(loss_function))
         else:
             self._loss_function = loss_function
-        # solver options (reference hard-codes rtol = atol = 1e-10, ode_model.py:122-123)
+        # solver options (reference hard-codes rtol = atol = 1e-10, ode_model.py:122-123).  solver: 'dp5' (explicit), 'rodas4'
+        # (stiff: states, and sensitivities for autonomous models of at most 12 states) or 'auto' (_concrete_solver)
         self.solver = solver
         self.rtol = rtol if rtol is not None else getattr(model, 'rtol', 1e-10)
         self.atol = atol if atol is not None else getattr(model, 'atol', 1e-10)
         self.max_steps = max_steps
         self.reference_jac_rows = bool(reference_jac_rows)
+        self._auto_choice = {}                 # solver='auto': decision per path (False: states only, True: sensitivities)
+        self.auto_solver_report = {}
         self.prior_jacobian_unit = bool(prior_jacobian_unit)
 
         self._parameter_priors = OrderedDict()
@@ -339,10 +342,61 @@ class Project(object):
             self._device_plan = engine.DevicePlan(self._model.compiled, self._plan_tables)
         return self._device_plan
 
-    def _jac_solver(self):
+    def _jac_solver(self, thetas=None):
         """Integrator of the sensitivity path: the project's stiff choice carries over to the Jacobian (RODAS4 with forward
         sensitivities, autonomous models of at most 12 states - the C ABI refuses other models), otherwise Dormand-Prince."""
-        return 'rodas4' if str(self.solver).lower() in ('rodas4', 'rodas') else 'dp5'
+        return self._concrete_solver(True, thetas)
+
+    def _concrete_solver(self, with_jac, thetas=None, requested=None):
+        """'dp5' / 'rodas4' for this call.  ``solver='auto'`` (the reference's LSODA switches between Adams and BDF by itself,
+        ode_model.py:122-123) is decided ONCE per project and path by measurement: the first parameter sets that come in (at
+        most 64) are integrated with both kernels under a bounded step budget, and the faster one that fails nowhere is kept
+        (``auto_solver_report``).  A stiff model exhausts the explicit kernel's budget and selects the Rosenbrock kernel."""
+        s = str(requested or self.solver).lower()
+        if s in ('rodas', 'rodas4'):
+            return 'rodas4'
+        if s != 'auto':
+            return 'dp5' if with_jac else s
+        if with_jac in self._auto_choice:
+            return self._auto_choice[with_jac]
+        if thetas is None:
+            return 'dp5'
+        import torch
+        _lib.require_gpu()
+        plan, t = self.device_plan, self._plan_tables
+        th = thetas if isinstance(thetas, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(np.atleast_2d(np.asarray(thetas, dtype=np.float64))))
+        th = th[:64].to('cuda').contiguous()
+        n = th.shape[0]
+        f64 = dict(dtype=torch.float64, device=th.device)
+        report = {}
+        for cand in ('dp5', 'rodas4'):
+            sims = torch.zeros((n, t.n_rows), **f64)
+            jac = torch.empty((n, t.n_rows, t.n_proj), **f64) if with_jac else None
+            status = torch.zeros((n, t.E), dtype=torch.int32, device=th.device)
+            counters = torch.zeros(_lib.SBM_N_COUNTERS, dtype=torch.int64, device=th.device)
+            opts = engine.DevicePlan.opts(cand, self.rtol, self.atol, 50000)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            try:
+                plan.solve_device(th, opts, sims, jac, status, counters)           # (first call: module load)
+                sims.zero_()
+                ev0.record()
+                plan.solve_device(th, opts, sims, jac, status, counters)
+                ev1.record()
+                torch.cuda.synchronize()
+            except _lib.SbmError as exc:                                            # kernel not available for this model
+                report[cand] = {'available': False, 'why': str(exc)}
+                continue
+            report[cand] = {'available': True, 'ms': ev0.elapsed_time(ev1), 'failed': int((status != 0).sum().item())}
+        ok = [c for c in report if report[c]['available'] and report[c]['failed'] == 0]
+        if ok:
+            choice = min(ok, key=lambda c: report[c]['ms'])
+        else:
+            avail = [c for c in report if report[c]['available']] or ['dp5']
+            choice = min(avail, key=lambda c: report[c]['failed'])
+        self._auto_choice[with_jac] = choice
+        self.auto_solver_report[with_jac] = dict(report, choice=choice, sets=n)
+        return choice
 
     def _opts(self, solver=None):
         return engine.DevicePlan.opts(solver or self.solver, self.rtol, self.atol, self.max_steps)
@@ -542,7 +596,7 @@ class Project(object):
     def residuals(self, project_param_vector):
         """Reference :708-729.  One plain solve per experiment + loss epilogue, all on the GPU."""
         theta = np.asarray(project_param_vector, dtype=np.float64)
-        out = self.device_plan.residuals_host(theta[None, :], self._opts(), self._loss_name())
+        out = self.device_plan.residuals_host(theta[None, :], self._opts(self._concrete_solver(False, theta)), self._loss_name())
         self._store_last(theta, out, False)
         res = out['resid'][0]
         if np.isinf(res).all() and len(res):
@@ -553,21 +607,21 @@ class Project(object):
         """Reference :731-771.  One sensitivity-augmented solve per experiment (its state column doubles as
         the plain simulation, so the reference's extra ``_sim_experiments`` pass is not repeated)."""
         theta = np.asarray(project_param_vector, dtype=np.float64)
-        out = self.device_plan.jacobian_host(theta[None, :], self._opts(self._jac_solver()), self._loss_name(), self._flags())
+        out = self.device_plan.jacobian_host(theta[None, :], self._opts(self._jac_solver(theta)), self._loss_name(), self._flags())
         self._store_last(theta, out, True)
         return pd.DataFrame(out['jac'][0], index=self._index, columns=self.get_ordered_project_params())
 
     def calc_rss_gradient(self, project_param_vector, *args):
         """Reference :773-805: (J^T r) - formed in the loss epilogue from the same solve."""
         theta = np.asarray(project_param_vector, dtype=np.float64)
-        out = self.device_plan.jacobian_host(theta[None, :], self._opts(self._jac_solver()), self._loss_name(), self._flags())
+        out = self.device_plan.jacobian_host(theta[None, :], self._opts(self._jac_solver(theta)), self._loss_name(), self._flags())
         self._store_last(theta, out, True)
         return pd.Series(out['grad'][0], index=self.get_ordered_project_params())
 
     def calc_sum_square_residuals(self, project_param_vector):
         """Reference :807-827: 0.5 * sum(residuals^2)."""
         theta = np.asarray(project_param_vector, dtype=np.float64)
-        out = self.device_plan.residuals_host(theta[None, :], self._opts(), self._loss_name())
+        out = self.device_plan.residuals_host(theta[None, :], self._opts(self._concrete_solver(False, theta)), self._loss_name())
         self._store_last(theta, out, False)
         return float(out['ssr'][0])
 
@@ -598,8 +652,8 @@ class Project(object):
     # ---- additive batch API -------------------------------------------------------------------
     def residuals_batch(self, thetas, solver=None):
         """thetas f8[B, n_proj] -> dict(resid [B, n_rows], ssr [B], sf [B, G], sims, status [B, E], counters)."""
-        out = self.device_plan.residuals_host(np.asarray(thetas, dtype=np.float64), self._opts(solver),
-                                              self._loss_name())
+        out = self.device_plan.residuals_host(np.asarray(thetas, dtype=np.float64),
+                                              self._opts(self._concrete_solver(False, thetas, solver)), self._loss_name())
         self._warn_failed(out['status'])
         return out
 
@@ -608,7 +662,7 @@ class Project(object):
 
     def jacobian_batch(self, thetas):
         """thetas f8[B, n_proj] -> dict(jac [B, n_rows, n_proj], model_jac, resid, ssr, grad [B, n_proj], ...)."""
-        out = self.device_plan.jacobian_host(np.asarray(thetas, dtype=np.float64), self._opts(self._jac_solver()),
+        out = self.device_plan.jacobian_host(np.asarray(thetas, dtype=np.float64), self._opts(self._jac_solver(thetas)),
                                              self._loss_name(), self._flags())
         self._warn_failed(out['status'])
         return out
@@ -644,7 +698,7 @@ class Project(object):
             jac = buf('jac', (B, t.n_rows, t.n_proj))
             sfgrad = buf('sfgrad', (B, max(t.n_groups, 1), t.n_proj))
             grad = buf('grad', (B, t.n_proj))
-        opts = self._opts(self._jac_solver() if with_jacobian else solver)
+        opts = self._opts(self._jac_solver(theta) if with_jacobian else self._concrete_solver(False, theta, solver))
         plan.solve_device(theta, opts, sims, jac, status, counters)
         plan.loss_device(theta, sims, jac, resid, ssr, sf, sfgrad, grad, loss=self._loss_name(), flags=self._flags())
         return o

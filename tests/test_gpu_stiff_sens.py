@@ -118,3 +118,34 @@ def test_rodas4_sens_agrees_with_dormand_prince_on_the_mapk_model():
     assert np.all(np.abs(y1 - y2) <= 1e-6 * (1 + np.abs(y2)))
     scale = np.abs(S2).max(axis=(1, 2), keepdims=True)          # per set and parameter
     assert (np.abs(S1 - S2) / scale).max() < 1e-5, (np.abs(S1 - S2) / scale).max()
+
+
+def test_solver_auto_picks_by_measurement():
+    """``Project(solver='auto')``: the stiff Robertson project ends up on the Rosenbrock kernels (the explicit kernel
+    exhausts its probe budget), the non-stiff Michaelis-Menten project on Dormand-Prince; results equal the explicit choice."""
+    import sysbio_modeling_b200 as sb
+    from sysbio_modeling_b200 import model_files
+    from tools import workloads as wl
+    from fixtures import project_mm_two_measures
+    import json, os
+    ref, _ = wl.c3_project(rtol=1e-8, atol=1e-12)
+    om = sb.OdeModel.from_model_file(model_files.path('robertson'), rtol=1e-8, atol=1e-12)
+    mapping = {k: ('direct', v) for k, v in wl.C3_OBS.items()}
+    auto = sb.Project(om, wl.c3_experiments(ref.workload_data), {}, mapping, solver='auto', rtol=1e-8, atol=1e-12)
+    sm, nominal, y0 = wl.nominal_of('robertson')
+    thetas = wl.make_thetas(nominal, 32, 3, 0.4)
+    a, b = auto.residuals_batch(thetas), ref.residuals_batch(thetas)
+    assert auto.auto_solver_report[False]['choice'] == 'rodas4', auto.auto_solver_report
+    assert auto.auto_solver_report[False]['dp5']['failed'] > 0            # the explicit kernel ran out of steps
+    assert np.array_equal(a['resid'], b['resid'])
+    ja, jb = auto.jacobian_batch(thetas), ref.jacobian_batch(thetas)
+    assert auto.auto_solver_report[True]['choice'] == 'rodas4'
+    assert np.array_equal(ja['jac'], jb['jac'])
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden.json')) as fh:
+        golden = json.load(fh)
+    p_dp, _ = project_mm_two_measures(golden)
+    p_auto, _ = project_mm_two_measures(golden, solver='auto')
+    th = np.log(0.01) + 0.2 * np.random.default_rng(3).standard_normal((16, p_dp.n_project_params))
+    ra, rb = p_auto.jacobian_batch(th), p_dp.jacobian_batch(th)
+    assert p_auto.auto_solver_report[True]['choice'] == 'dp5', p_auto.auto_solver_report
+    assert np.array_equal(ra['jac'], rb['jac']) and np.array_equal(ra['resid'], rb['resid'])

@@ -143,3 +143,31 @@ def test_ct_layout_and_primal_shares_cover_every_output_once():
         assert g_idx == sorted(j * ne + i for (i, j) in sm.G.keys())
         XW = int(re.search(r'#define SBM_CT_XW (\d+)', src).group(1))
         assert body.count('case ') == W + XW
+
+
+def test_directional_derivative_of_J_and_G_for_the_rosenbrock_sensitivity_kernel():
+    """``sbm_dJG`` (DJv[q] = sum_l dJ_q/dy_l u_l, same for G) is emitted for autonomous models of at most 12 states, and its
+    formula - re-derived here from the symbolic model - equals a central difference of J and G along the direction."""
+    src = emit_cuda(symbolic_model_from_file(model_files.path('robertson'))).source
+    assert '#define SBM_HAS_DJG 1' in src and 'sbm_dJG(' in src
+    assert 'sbm_dJG(' not in emit_cuda(symbolic_model_from_file(model_files.path('egfr_signalling'))).source   # 25 states
+    sm = symbolic_model_from_file(model_files.path('mapk_kholodenko'))
+    src = emit_cuda(sm).source
+    assert src.count('DJv[') == len(sm.J) and src.count('DGv[') == len(sm.G)
+    rng = np.random.default_rng(0)
+    mod = model_files.module('mapk_kholodenko')
+    yv = np.array(mod.initial_conditions) * (1 + 0.1 * rng.random(8))
+    pv = np.array([mod.nominal[k] for k in sm.param_order])
+    u = rng.standard_normal(8)
+    usyms = sp.symbols('u0:8', real=True)
+    args = list(sm.var_syms) + list(sm.param_syms)
+    for table in (sm.J, sm.G):
+        keys = sorted(table.keys())
+        val = sp.lambdify(args, [table[k] for k in keys], 'numpy')
+        dirs = [sum(sp.diff(table[k], v) * usyms[l] for l, v in enumerate(sm.var_syms)) for k in keys]
+        dval = sp.lambdify(args + list(usyms), dirs, 'numpy')
+        eps = 1e-5
+        fd = (np.array(val(*(list(yv + eps * u) + list(pv))), dtype=float) -
+              np.array(val(*(list(yv - eps * u) + list(pv))), dtype=float)) / (2 * eps)
+        an = np.array(dval(*(list(yv) + list(pv) + list(u))), dtype=float)
+        assert np.allclose(an, fd, rtol=1e-6, atol=1e-9 * (1 + np.abs(fd).max()))
