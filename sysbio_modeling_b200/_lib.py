@@ -61,7 +61,7 @@ class PlanDesc(ctypes.Structure):
 
 class SolverOpts(ctypes.Structure):
     _fields_ = [('solver', ctypes.c_int), ('max_steps', ctypes.c_int), ('jac_raw', ctypes.c_int),
-                ('reserved', ctypes.c_int), ('rtol', ctypes.c_double),
+                ('dense_output', ctypes.c_int), ('rtol', ctypes.c_double),
                 ('atol', ctypes.c_double), ('h0', ctypes.c_double)]
 
 

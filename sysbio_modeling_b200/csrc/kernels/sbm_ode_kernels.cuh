@@ -70,6 +70,13 @@
 #define DP_E5 (-17253.0/339200.0)
 #define DP_E6 (22.0/525.0)
 #define DP_E7 (-1.0/40.0)
+// continuous extension of order 4 (Hairer, Norsett, Wanner II.6; dopri5.f CONTD5)
+#define DP_D1 (-12715105075.0/11282082432.0)
+#define DP_D3 (87487479700.0/32700410799.0)
+#define DP_D4 (-10690763975.0/1880347072.0)
+#define DP_D5 (701980252875.0/199316789632.0)
+#define DP_D6 (-1453857185.0/822651844.0)
+#define DP_D7 (69997945.0/29380423.0)
 
 // ---------------------------------------------------------------------------------------------
 // group helpers
@@ -159,7 +166,7 @@ __constant__ int sbm_dp_out[8] = {0, 1, 1, 2, 3, 4, 5, 1};     // logical k-slot
 // would wait for its slowest group anyway), lets every shuffle use the constant full mask, and keeps
 // a single copy of the generated model code in the loop body.
 // ---------------------------------------------------------------------------------------------
-template <int G, int C, int SENS, int BLOCK>
+template <int G, int C, int SENS, int BLOCK, int DENSE = 0>
 __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
 {
     constexpr int N = SBM_N;
@@ -244,7 +251,10 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
             hprop = h;
             clipped = false;
             if (stepping) {
-                if (t + 1.01 * h >= tk) { h = tk - t; clipped = true; }
+                // dense output (states only): steps are clipped onto the LAST output time only; the others are read off the
+                // continuous extension of the accepted step that passes them
+                const double tclip = DENSE ? tend : tk;
+                if (t + 1.01 * h >= tclip) { h = tclip - t; clipped = true; }
                 if (nstep >= (unsigned)a.max_steps) status = SBM_ERR_MAXSTEPS;
                 else if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) status = SBM_ERR_UNDERFLOW;
             }
@@ -373,7 +383,30 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
                     float fac = __powf(ferr, 0.2f - 0.04f * 0.75f) / __powf(facold, 0.04f);
                     fac = fmaxf(0.1f, fminf(5.0f, fac / 0.9f));
                     facold = fmaxf(ferr, 1e-4f);
-                    t = clipped ? tk : t + h;
+                    if (DENSE) {
+                        const double tn = clipped ? tend : t + h;
+                        while (kt < kt1 - 1 && tk <= tn) {
+                            const double th = (tk - t) / h, th1 = 1.0 - th;
+                            double xi[C][N];
+#pragma unroll
+                            for (int i = 0; i < N; ++i) {
+                                const double k1v = K.get(s0, 0, i), k3v = K.get(2, 0, i), k4v = K.get(3, 0, i);
+                                const double k5v = K.get(4, 0, i), k6v = K.get(5, 0, i), k7v = K.get(s1, 0, i);
+                                const double yd = xn[0][i] - x[0][i];
+                                const double bs = fma(h, k1v, -yd);
+                                const double r4 = yd - h * k7v - bs;
+                                const double r5 = h * fma(DP_D7, k7v, fma(DP_D6, k6v, fma(DP_D5, k5v, fma(DP_D4, k4v,
+                                                  fma(DP_D3, k3v, DP_D1 * k1v)))));
+                                xi[0][i] = fma(th, fma(th1, fma(th, fma(th1, r5, r4), bs), yd), x[0][i]);
+#pragma unroll
+                                for (int c = 1; c < C; ++c) xi[c][i] = 0.0;
+                            }
+                            sbm_emit_rows<G, C, SENS>(a, b, kt, xi, cid, pcol, pscale, false);
+                            kt++;
+                            tk = a.tout[kt];
+                        }
+                    }
+                    t = clipped ? (DENSE ? tend : tk) : t + h;
 #pragma unroll
                     for (int c = 0; c < C; ++c)
 #pragma unroll
@@ -990,6 +1023,12 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
 #define SBM_DEFINE_DP5(NAME, G, C, SENS, BLOCK)                                             \
     extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \
     { sbm_dp5_impl<G, C, SENS, BLOCK>(a); }
+
+// states only, output times read off the continuous extension (a kernel of its own: the interpolation keeps three state
+// vectors live, which costs the 25-state model of C5 its spill-free register allocation)
+#define SBM_DEFINE_DP5_DENSE(NAME, BLOCK)                                                   \
+    extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \
+    { sbm_dp5_impl<1, 1, 0, BLOCK, 1>(a); }
 
 #define SBM_DEFINE_RODAS4(NAME, BLOCK)                                                      \
     extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \

@@ -152,7 +152,7 @@ struct sbm_model {
     bool loaded = false;
     int device = -1;             // device whose context holds `mod` (one module per model; see ensure_loaded)
     CUmodule mod = nullptr;
-    KernelSlot dp5_plain, dp5_sens, dp5_ct, rodas4, rodas4_sens;
+    KernelSlot dp5_plain, dp5_plain_dense, dp5_sens, dp5_ct, rodas4, rodas4_sens;
     std::mutex mu;
 };
 
@@ -258,6 +258,7 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     src << sbm_embedded_args_header << "\n" << model_src << "\n" << sbm_embedded_kernels << "\n";
     if (m->ct_ok) src << "SBM_DEFINE_DP5_CT(sbm_dp5_ct, " << m->ctW << ", " << m->ctC << ", " << m->ctXW << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_plain, 1, 1, 0, " << m->block_plain << ")\n";
+    src << "SBM_DEFINE_DP5_DENSE(sbm_dp5_plain_dense, " << m->block_plain << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_sens, " << m->G << ", " << m->C << ", 1, " << m->block << ")\n";
     // the Rosenbrock kernel keeps the dense Jacobian and its LU in registers: fine up to ~12 states, hopeless beyond
     m->has_rodas = desc->n_vars <= 12;
@@ -359,11 +360,13 @@ static int ensure_loaded(sbm_model* m)
     rc = [&]() -> int {
         int r;
         if ((r = slot_load(m, m->dp5_plain, "sbm_dp5_plain"))) return r;
+        if ((r = slot_load(m, m->dp5_plain_dense, "sbm_dp5_plain_dense"))) return r;
         if ((r = slot_load(m, m->dp5_sens, "sbm_dp5_sens"))) return r;
         if (m->has_rodas && (r = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return r;
         if (m->has_rodas_sens && (r = slot_load(m, m->rodas4_sens, "sbm_rodas4_sens"))) return r;
         DRV(driver().cuFuncSetAttribute_(m->dp5_sens.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
         DRV(driver().cuFuncSetAttribute_(m->dp5_plain.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_plain));
+        DRV(driver().cuFuncSetAttribute_(m->dp5_plain_dense.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_plain));
         RT(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev));
         if (m->ct_ok) {
             if ((r = slot_load(m, m->dp5_ct, "sbm_dp5_ct"))) return r;
@@ -575,6 +578,7 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
     if (o->jac_raw && jac && p->d.n_proj != m->desc.n_free) return fail(SBM_E_INVALID, "jac_raw needs a plan with n_proj == n_free");
     a.rtol = o->rtol; a.atol = o->atol; a.h0 = o->h0;
     a.n_tout = p->d.n_tout; a.n_orow = p->d.n_orow;
+    a.dense = (o->dense_output == 1 || (o->dense_output == 0 && (long long)p->d.n_tout >= 256ll * p->d.E)) ? 1 : 0;
 
     // (pmap of a fixed model parameter is -1, so a column is "covered" only through a free parameter; with jac_raw the
     //  columns are the model's free parameters themselves)
@@ -599,7 +603,7 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
         RT(cudaMemsetAsync(counters + SBM_CNT_QUEUE, 0, sizeof(unsigned long long), st));
     }
     else if (jac) { ks = &m->dp5_sens; threads = ntraj * m->G; block = m->block; dyn = m->dyn_smem; }
-    else { ks = &m->dp5_plain; threads = ntraj; dyn = m->dyn_smem_plain; }
+    else { ks = a.dense ? &m->dp5_plain_dense : &m->dp5_plain; threads = ntraj; dyn = m->dyn_smem_plain; }
     if (blocks < 0) blocks = (threads + block - 1) / block;
     if (blocks > 2147483647ll) return fail(SBM_E_INVALID, "batch too large for one launch");
     void* params[] = {&a};

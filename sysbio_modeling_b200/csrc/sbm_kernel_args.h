@@ -50,6 +50,7 @@ typedef struct SbmSolveArgs {
     double                    h0;         // initial step; 0 = automatic
     int                       n_tout;     // lengths of tout / of the row tables (small plans are staged in shared memory)
     int                       n_orow;
+    int                       dense;      // 1: states-only Dormand-Prince reads output times off the continuous extension
 } SbmSolveArgs;
 
 #endif

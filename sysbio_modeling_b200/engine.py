@@ -127,10 +127,10 @@ class DevicePlan(object):
         return self._h
 
     @staticmethod
-    def opts(solver='dp5', rtol=1e-10, atol=1e-10, max_steps=0, h0=0.0, jac_raw=False):
+    def opts(solver='dp5', rtol=1e-10, atol=1e-10, max_steps=0, h0=0.0, jac_raw=False, dense_output=0):
         o = SolverOpts()
         o.solver = SOLVERS[solver] if isinstance(solver, str) else int(solver)
-        o.max_steps, o.jac_raw, o.reserved = int(max_steps), int(bool(jac_raw)), 0
+        o.max_steps, o.jac_raw, o.dense_output = int(max_steps), int(bool(jac_raw)), int(dense_output)
         o.rtol, o.atol, o.h0 = float(rtol), float(atol), float(h0)
         return o
 

@@ -44,6 +44,9 @@ class OdeModel(ModelABC):
         self.use_jac = True
         self.jit_type = jit_type
         self.rtol, self.atol, self.solver, self.max_steps = rtol, atol, solver, max_steps
+        # states-only Dormand-Prince on a dense time grid: 0 = automatic (continuous extension from 256 output times per
+        # trajectory on: the reference's 1000-node grids), 1 = always, 2 = every step lands on its output time
+        self.dense_output = 0
         if symbolic is None:
             if model is None:
                 raise ValueError('either a model callable or a SymbolicModel is required')
@@ -135,7 +138,7 @@ class OdeModel(ModelABC):
         counters = torch.zeros(_lib.SBM_N_COUNTERS, dtype=torch.int64, device=dev)
         # sensitivities: Dormand-Prince, or RODAS4 with forward sensitivities when the model was declared stiff
         solver = self.solver if (not with_sens or str(self.solver).lower() in ('rodas4', 'rodas')) else 'dp5'
-        opts = plan.opts(solver, self.rtol, self.atol, self.max_steps, jac_raw=True)
+        opts = plan.opts(solver, self.rtol, self.atol, self.max_steps, jac_raw=True, dense_output=self.dense_output)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         plan.solve_device(theta, opts, sims, jac, status, counters)
