@@ -130,7 +130,7 @@ typedef struct sbm_solver_opts_t {
     int    max_steps;     /* per trajectory; <=0 -> 500000                                             */
     int    jac_raw;       /* 1: jac = raw dy/dp_free, [B][n_rows][n_free], no log-parameter chain rule
                              (the OdeModel.calc_jacobian convention, model/ode_model.py:83-126)        */
-    int    dense_output;  /* states-only Dormand-Prince kernel: 1 = output times are read off the 4th-order continuous
+    int    dense_output;  /* states-only kernels (Dormand-Prince, RODAS4): 1 = output times are read off the continuous
                              extension of the step that passes them (no step is clipped except onto the last time), 2 = every
                              step lands on its output time, 0 = automatic: dense when a trajectory has >= 256 output times (the
                              reference's 1000-node grids, base_project.py:419-420) */

@@ -480,6 +480,17 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
 #define RO_C63 (-31.52159432874371)
 #define RO_C64 16.31930543123136
 #define RO_C65 (-6.058818238834054)
+// dense output (rodas.f, RODAS4: D21..D25, D31..D35)
+#define RO_D21 10.12623508344586
+#define RO_D22 (-7.487995877610167)
+#define RO_D23 (-34.80091861555747)
+#define RO_D24 (-7.992771707568823)
+#define RO_D25 1.025137723295662
+#define RO_D31 (-0.6762803392801253)
+#define RO_D32 6.087714651680015
+#define RO_D33 16.43084320892478
+#define RO_D34 24.76722511418386
+#define RO_D35 (-6.594389125716872)
 
 // in-register LU, partial pivoting by predicated row swaps (all indices compile-time after unrolling)
 __device__ __forceinline__ bool sbm_lu_factor(double (&A)[SBM_N * SBM_N], int (&piv)[SBM_N])
@@ -538,7 +549,7 @@ __device__ __forceinline__ void sbm_lu_solve(const double (&A)[SBM_N * SBM_N], c
     }
 }
 
-template <int BLOCK>
+template <int BLOCK, int DENSE = 0>
 __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
 {
     constexpr int N = SBM_N;
@@ -611,7 +622,10 @@ __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
     double hacc = h, erracc = 1e-2;
     unsigned naccept = 0;
 
-    for (int kt = kt0; kt < kt1; ++kt) {
+    // DENSE: one pass to the last output time; the others are read off the continuous extension of the step that passes
+    // them (Hairer & Wanner's RODAS, CONTRO) - kd is the next output time to be written
+    int kd = kt0;
+    for (int kt = DENSE ? (kt1 > kt0 ? kt1 - 1 : kt1) : kt0; kt < kt1; ++kt) {
         const double tk = a.tout[kt];
         while (status == SBM_OK && t < tk) {
             const double hprop = h;
@@ -711,6 +725,21 @@ __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
                 hacc = h;
                 erracc = fmax(1e-2, err);
                 naccept++;
+                if (DENSE) {
+                    const double tn = clipped ? tk : t + h;
+                    while (kd < kt1 - 1 && a.tout[kd] <= tn) {
+                        const double th = (a.tout[kd] - t) / h, th1 = 1.0 - th;
+                        double yi[1][N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            const double c1 = fma(RO_D25, k5[i], fma(RO_D24, k4[i], fma(RO_D23, k3[i], fma(RO_D22, k2[i], RO_D21 * k1[i]))));
+                            const double c2 = fma(RO_D35, k5[i], fma(RO_D34, k4[i], fma(RO_D33, k3[i], fma(RO_D32, k2[i], RO_D31 * k1[i]))));
+                            yi[0][i] = fma(th, fma(th1, fma(th, c2, c1), yn[0][i]), th1 * y[0][i]);
+                        }
+                        sbm_emit_rows<1, 1, 0>(a, b, kd, yi, cid, pcol, pscale, false);
+                        kd++;
+                    }
+                }
                 t = clipped ? tk : t + h;
 #pragma unroll
                 for (int i = 0; i < N; ++i) y[0][i] = yn[0][i];
@@ -733,6 +762,10 @@ __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
             }
         }
         if (status != SBM_OK) poison = true;
+        if (DENSE) {
+            // a failed trajectory flushes what it has not written as NaN
+            for (; poison && kd < kt; ++kd) sbm_emit_rows<1, 1, 0>(a, b, kd, y, cid, pcol, pscale, true);
+        }
         sbm_emit_rows<1, 1, 0>(a, b, kt, y, cid, pcol, pscale, poison);
     }
 
@@ -1033,3 +1066,6 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
 #define SBM_DEFINE_RODAS4(NAME, BLOCK)                                                      \
     extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \
     { sbm_rodas4_impl<BLOCK>(a); }
+#define SBM_DEFINE_RODAS4_DENSE(NAME, BLOCK)                                                \
+    extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \
+    { sbm_rodas4_impl<BLOCK, 1>(a); }

@@ -152,7 +152,7 @@ struct sbm_model {
     bool loaded = false;
     int device = -1;             // device whose context holds `mod` (one module per model; see ensure_loaded)
     CUmodule mod = nullptr;
-    KernelSlot dp5_plain, dp5_plain_dense, dp5_sens, dp5_ct, rodas4, rodas4_sens;
+    KernelSlot dp5_plain, dp5_plain_dense, dp5_sens, dp5_ct, rodas4, rodas4_dense, rodas4_sens;
     std::mutex mu;
 };
 
@@ -263,6 +263,7 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     // the Rosenbrock kernel keeps the dense Jacobian and its LU in registers: fine up to ~12 states, hopeless beyond
     m->has_rodas = desc->n_vars <= 12;
     if (m->has_rodas) src << "SBM_DEFINE_RODAS4(sbm_rodas4_plain, " << m->block_plain << ")\n";
+    if (m->has_rodas) src << "SBM_DEFINE_RODAS4_DENSE(sbm_rodas4_plain_dense, " << m->block_plain << ")\n";
     m->has_rodas_sens = m->has_rodas && desc->n_free >= 1 && strstr(model_src, "#define SBM_HAS_DJG 1") != nullptr &&
                         strstr(model_src, "#define SBM_AUTONOMOUS 1") != nullptr;
     if (m->has_rodas_sens) src << "SBM_DEFINE_RODAS4_SENS(sbm_rodas4_sens, " << m->block_plain << ")\n";
@@ -363,6 +364,7 @@ static int ensure_loaded(sbm_model* m)
         if ((r = slot_load(m, m->dp5_plain_dense, "sbm_dp5_plain_dense"))) return r;
         if ((r = slot_load(m, m->dp5_sens, "sbm_dp5_sens"))) return r;
         if (m->has_rodas && (r = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return r;
+        if (m->has_rodas && (r = slot_load(m, m->rodas4_dense, "sbm_rodas4_plain_dense"))) return r;
         if (m->has_rodas_sens && (r = slot_load(m, m->rodas4_sens, "sbm_rodas4_sens"))) return r;
         DRV(driver().cuFuncSetAttribute_(m->dp5_sens.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
         DRV(driver().cuFuncSetAttribute_(m->dp5_plain.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_plain));
@@ -591,7 +593,7 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
     int block = m->block_plain, dyn = 0;
     long long blocks = -1;
     if (o->solver == SBM_SOLVER_RODAS4 && jac) { ks = &m->rodas4_sens; threads = ntraj; }
-    else if (o->solver == SBM_SOLVER_RODAS4) { ks = &m->rodas4; threads = ntraj; }
+    else if (o->solver == SBM_SOLVER_RODAS4) { ks = a.dense ? &m->rodas4_dense : &m->rodas4; threads = ntraj; }
     else if (jac && m->ct_ok && m->layout != 1) {
         // persistent CTAs, 32 trajectories in flight each, refilled from a global queue
         ks = &m->dp5_ct; block = (m->ctW + m->ctXW) * 32; dyn = m->ct_dyn_smem; threads = 0;
