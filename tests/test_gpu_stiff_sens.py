@@ -149,3 +149,35 @@ def test_solver_auto_picks_by_measurement():
     ra, rb = p_auto.jacobian_batch(th), p_dp.jacobian_batch(th)
     assert p_auto.auto_solver_report[True]['choice'] == 'dp5', p_auto.auto_solver_report
     assert np.array_equal(ra['jac'], rb['jac']) and np.array_equal(ra['resid'], rb['resid'])
+
+
+def test_rodas4_sens_failure_status_and_shared_columns():
+    """A step budget that cannot be met: status MAXSTEPS, NaN rows -> inf residuals (squared_loss_function.py:28-32) on that
+    set only; and two experiments that share every parameter (their rows accumulate into the same project columns)."""
+    import sysbio_modeling_b200 as sb
+    from sysbio_modeling_b200 import model_files
+    from tools import workloads as wl
+    ref, _ = wl.c3_project(rtol=1e-8, atol=1e-12)
+    sm, nominal, y0 = wl.nominal_of('robertson')
+    thetas = wl.make_thetas(nominal, 8, 3, 0.3)
+    ref.max_steps = 5
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        out = ref.jacobian_batch(thetas)
+    assert (out['status'] == 1).all()                         # SBM_ERR_MAXSTEPS
+    assert np.isinf(out['resid']).all()
+    ref.max_steps = 0
+    out = ref.jacobian_batch(thetas)
+    assert (out['status'] == 0).all() and np.isfinite(out['jac']).all()
+    # two identical experiments under different names: same parameters (all Global), twice the rows
+    om = sb.OdeModel.from_model_file(model_files.path('robertson'), solver='rodas4', rtol=1e-8, atol=1e-12)
+    mapping = {k: ('direct', v) for k, v in wl.C3_OBS.items()}
+    e1 = wl.c3_experiments(ref.workload_data)[0]
+    e2 = wl.c3_experiments(ref.workload_data)[0]
+    e2.name = 'Robertson_again'
+    both = sb.Project(om, [e1, e2], {}, mapping, solver='rodas4', rtol=1e-8, atol=1e-12)
+    o2 = both.jacobian_batch(thetas)
+    assert o2['jac'].shape == (8, 48, 3)
+    assert np.allclose(o2['jac'][:, :24], out['jac'], rtol=1e-12, atol=0) and np.allclose(o2['jac'][:, 24:], out['jac'], rtol=1e-12, atol=0)
+    assert np.allclose(o2['grad'], 2 * out['grad'], rtol=1e-10, atol=1e-12 * np.abs(out['grad']).max())
