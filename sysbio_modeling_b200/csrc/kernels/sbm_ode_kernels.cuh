@@ -492,6 +492,14 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
 #define RO_D34 24.76722511418386
 #define RO_D35 (-6.594389125716872)
 
+// x^(1/4) for the Rosenbrock step-size controller: single precision is plenty for a step-size factor that is clamped to
+// [1/6, 5] (the double-precision pow() was ~250 FP64 instructions per step, a fifth of the kernel's FP64 work on C3)
+__device__ __forceinline__ double sbm_root4(const double x)
+{
+    const float v = fminf(fmaxf((float)x, 1e-36f), 1e36f);
+    return (double)sqrtf(sqrtf(v));
+}
+
 // in-register LU, partial pivoting by predicated row swaps (all indices compile-time after unrolling)
 __device__ __forceinline__ bool sbm_lu_factor(double (&A)[SBM_N * SBM_N], int (&piv)[SBM_N])
 {
@@ -509,7 +517,15 @@ __device__ __forceinline__ bool sbm_lu_factor(double (&A)[SBM_N * SBM_N], int (&
         piv[k] = r;
 #pragma unroll
         for (int i = k + 1; i < N; ++i) {
-            if (r == i) {
+            if (N <= 6) {
+                const bool sw = (r == i);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const double ak = A[k * N + j], ai = A[i * N + j];
+                    A[k * N + j] = sw ? ai : ak;
+                    A[i * N + j] = sw ? ak : ai;
+                }
+            } else if (r == i) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) { const double tmp = A[k * N + j]; A[k * N + j] = A[i * N + j]; A[i * N + j] = tmp; }
             }
@@ -534,9 +550,17 @@ __device__ __forceinline__ void sbm_lu_solve(const double (&A)[SBM_N * SBM_N], c
     constexpr int N = SBM_N;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
+        // (small systems: the swap as selects - written as a branch, ptxas turns the chain into a dynamically indexed copy of b
+        //  in local memory: 8 % of the executed instructions of C3 were STL / LDL, profiles/r02_rodas4_plain.txt)
 #pragma unroll
-        for (int i = k + 1; i < N; ++i)
-            if (piv[k] == i) { const double tmp = b[k]; b[k] = b[i]; b[i] = tmp; }
+        for (int i = k + 1; i < N; ++i) {
+            if (N <= 6) {
+                const bool sw = (piv[k] == i);
+                const double bk = b[k], bi = b[i];
+                b[k] = sw ? bi : bk;
+                b[i] = sw ? bk : bi;
+            } else if (piv[k] == i) { const double tmp = b[k]; b[k] = b[i]; b[i] = tmp; }
+        }
 #pragma unroll
         for (int i = k + 1; i < N; ++i) b[i] = fma(-A[i * N + k], b[k], b[i]);
     }
@@ -644,14 +668,14 @@ __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
 #pragma unroll
             for (int i = 0; i < N; ++i) ft[i] = 0.0;
 #endif
-            const double fac = 1.0 / (h * RO_GAMMA);
+            const double hi = sbm_rcp(h);
+            const double fac = hi * (1.0 / RO_GAMMA);
 #pragma unroll
             for (int q = 0; q < N * N; ++q) A[q] = -A[q];
 #pragma unroll
             for (int i = 0; i < N; ++i) A[i * N + i] += fac;
             const bool lu_ok = sbm_lu_factor(A, piv);
             nlu++;
-            const double hi = 1.0 / h;
 
             // stage 1
 #pragma unroll
@@ -712,13 +736,13 @@ __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
                 const double q = k6[i] * sbm_rcp(sk);
                 sq = fma(q, q, sq);
             }
-            const double err = sqrt(sq / N);
+            const double err = sqrt(sq * (1.0 / N));
 
             if (lu_ok && err <= 1.0) {
                 // accept; Gustafsson predictive controller as in Hairer's RODAS
-                double facr = fmax(1.0 / 6.0, fmin(5.0, pow(fmax(err, 1e-300), 0.25) / 0.9));
+                double facr = fmax(1.0 / 6.0, fmin(5.0, sbm_root4(err) / 0.9));
                 if (naccept >= 1) {
-                    double facgus = (hacc / h) * pow(err * err / erracc, 0.25) / 0.9;
+                    double facgus = (hacc / h) * sbm_root4(err * err / erracc) / 0.9;
                     facgus = fmax(1.0 / 6.0, fmin(5.0, facgus));
                     facr = fmax(facr, facgus);
                 }
@@ -752,7 +776,7 @@ __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
             } else {
                 nrej++;
                 if (lu_ok && err == err && err < 1e300) {
-                    const double facr = fmax(1.0 / 6.0, fmin(5.0, pow(err, 0.25) / 0.9));
+                    const double facr = fmax(1.0 / 6.0, fmin(5.0, sbm_root4(err) / 0.9));
                     h = first ? 0.1 * h : h / facr;
                 } else {
                     h *= 0.5;
@@ -894,14 +918,14 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
 
             sbm_fJG<1>(t, y, p, f0, Jv0, Gv0);
             sbm_jac_dense(t, y, p, A);
-            const double fac = 1.0 / (h * RO_GAMMA);
+            const double hi = sbm_rcp(h);
+            const double fac = hi * (1.0 / RO_GAMMA);
 #pragma unroll
             for (int q = 0; q < N * N; ++q) A[q] = -A[q];
 #pragma unroll
             for (int i = 0; i < N; ++i) A[i * N + i] += fac;
             const bool lu_ok = sbm_lu_factor(A, piv);
             nlu++;
-            const double hi = 1.0 / h;
 
 #pragma unroll 1
             for (int st = 0; st < 6; ++st) {
@@ -977,9 +1001,9 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
             const double err = sqrt(sq * inv_naug);
 
             if (lu_ok && err <= 1.0) {
-                double facr = fmax(1.0 / 6.0, fmin(5.0, pow(fmax(err, 1e-300), 0.25) / 0.9));
+                double facr = fmax(1.0 / 6.0, fmin(5.0, sbm_root4(err) / 0.9));
                 if (naccept >= 1) {
-                    double facgus = (hacc / h) * pow(err * err / erracc, 0.25) / 0.9;
+                    double facgus = (hacc / h) * sbm_root4(err * err / erracc) / 0.9;
                     facgus = fmax(1.0 / 6.0, fmin(5.0, facgus));
                     facr = fmax(facr, facgus);
                 }
@@ -1001,7 +1025,7 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
             } else {
                 nrej++;
                 if (lu_ok && err == err && err < 1e300) {
-                    const double facr = fmax(1.0 / 6.0, fmin(5.0, pow(err, 0.25) / 0.9));
+                    const double facr = fmax(1.0 / 6.0, fmin(5.0, sbm_root4(err) / 0.9));
                     h = first ? 0.1 * h : h / facr;
                 } else {
                     h *= 0.5;
