@@ -275,7 +275,7 @@ def extra_configs(peak_tf, quick=False):
     except Exception as exc:
         out['c3']['jacobian_error'] = repr(exc)
     del th
-    # ---- C5: EGFR-scale network (25 states, 52 parameters), 131,072 walkers, SSR only, plain DP5 ----
+    # ---- C5: EGFR-scale network (25 states, 52 parameters), 131,072 walkers, SSR only, states-only DP5 in push form ----
     B5 = 16384 if quick else 131072
     proj, _ = wl.c5_project()
     sm, nominal, _ = wl.nominal_of('egfr_signalling')
@@ -286,7 +286,7 @@ def extra_configs(peak_tf, quick=False):
     out['c5'] = {'workload': 'C5 EGFR-scale network (25 states, 52 parameters), %d walkers, 2 observables x 12 times, SSR only, '
                              'DP5 rtol = atol = 1e-10' % B5,
                  'solves_per_sec': B5 / ms_i * 1e3, 'residual_evals_per_sec': B5 / (ms_i + ms_l) * 1e3,
-                 'sbm_dp5_plain_ms': ms_i, 'sbm_loss_ms': ms_l, 'steps_per_solve': cnt['steps'] / B5, 'failed': failed,
+                 'sbm_dp5_push_ms': ms_i, 'sbm_loss_ms': ms_l, 'steps_per_solve': cnt['steps'] / B5, 'failed': failed,
                  'algorithmic_flops': flops, 'flops_per_rhs': cs.flops_f, 'tflops': flops / ms_i / 1e9,
                  'frac_fp64_peak': flops / ms_i / 1e9 / peak_tf}
     del th

@@ -492,6 +492,242 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
 #define RO_D34 24.76722511418386
 #define RO_D35 (-6.594389125716872)
 
+// ---------------------------------------------------------------------------------------------
+// States-only Dormand-Prince 5(4) in PUSH form, one thread per trajectory (round 2; C5: 25 states, 131,072 walkers).
+//
+// sbm_dp5_impl keeps the six stage derivatives in shared memory and forms every stage input from all of them: per stage
+// 6 N loads + 6 N FMAs + 12 N selects around a model of ~6 N flops, and 6 N doubles of shared memory per thread (C5: 38 KB
+// per warp, one warp per scheduler).  Here every stage derivative is pushed into the accumulators of the later stages as
+// soon as it exists (the tableau of sbm_dp5_ct.cuh): four vectors V1..V4 in shared memory, the state in registers -
+//   stage 2: w = y + h a21 V1 (V1 = k1)            V2 <- k2
+//   stage 3: w = y + h (a31 V1 + a32 V2)            V3 <- k3
+//   stage 4: w = y + h (a41 V1 + a42 V2 + a43 V3)   V1 <- input of stage 5, V2 / V3 <- partial inputs of stages 6 / 7,
+//                                                   V4 <- partial error estimate (all from k1..k4)
+//   stage 5: w = V1    V2, V3, V4 += (a65, a75, e5) h k5
+//   stage 6: w = V2    V3, V4 += (a76, e6) h k6
+//   stage 7: w = V3 = the 5th-order solution;  V1 <- k7 (FSAL),  V4 += e7 h k7 = the error estimate
+// 17 vector loads and 14 vector stores per step instead of 36 + 6, no selects, 4 N doubles of shared memory per thread.
+// After a rejected step k1 is evaluated again (V1 holds k7 of the rejected trial).  Output times: every step lands on
+// its output time (the dense variant needs all stage derivatives: sbm_dp5_plain_dense).
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK>
+__device__ __forceinline__ void sbm_dp5_push_impl(const SbmSolveArgs& a)
+{
+    constexpr int N = SBM_N;
+    __shared__ double sp[BLOCK * SBM_NPP];
+    extern __shared__ double sbm_dyn[];            // [4 or 5][N][BLOCK]: V1..V4 (and the state y when it is not in registers)
+    const int tid = threadIdx.x;
+    const long long traj = (long long)blockIdx.x * BLOCK + tid;
+    if (traj >= a.B * (long long)a.E) return;
+    const int e = (int)(traj % a.E);
+    const long long b = traj / a.E;
+    double* p = sp + tid * SBM_NPP;
+    for (int m = 0; m < SBM_NP; ++m) {
+        const int c = a.pmap[e * SBM_NP + m];
+        p[m] = (c >= 0) ? exp(a.theta[b * a.theta_sb + c * a.theta_sp]) : a.pfix[e * SBM_NP + m];
+    }
+    double* V = sbm_dyn + tid;
+    // keeps ptxas from hoisting all 3 N loads of an update above its FMA chains (the live ranges cost 1.7 KB of spills)
+#ifndef SBM_PUSH_FENCE_EVERY
+#define SBM_PUSH_FENCE_EVERY 2
+#endif
+#define SBM_PUSH_FENCE(i) do { if (SBM_PUSH_FENCE_EVERY > 0 && ((i) % SBM_PUSH_FENCE_EVERY) == SBM_PUSH_FENCE_EVERY - 1) asm volatile("" ::: "memory"); } while (0)
+#define SBM_PV(v, i) V[((v) * N + (i)) * BLOCK]
+    const int cid[1] = {0};
+    const int pcol[1] = {-1};
+    const double pscale[1] = {0.0};
+    // the state in registers while three state-sized arrays fit the register file, in shared memory beyond
+#if SBM_N <= 25 && !defined(SBM_PUSH_YSMEM)
+    double yreg[N];
+#define SBM_PY(i) yreg[i]
+#else
+#define SBM_PY(i) SBM_PV(4, i)
+#endif
+    double w[N], out[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { SBM_PY(i) = a.y0[e * N + i]; w[i] = a.y0[e * N + i]; }
+
+    const double rtol = a.rtol, atol = a.atol;
+    const int kt0 = a.tout_off[e], kt1 = a.tout_off[e + 1];
+    const double tend = (kt1 > kt0) ? a.tout[kt1 - 1] : 1.0;
+    unsigned nstep = 0, nrej = 0, nrhs = 0;
+    int status = SBM_OK;
+    double t = 0.0, h;
+    // ---- k1 and the initial step size (Hairer, Norsett, Wanner II.4) ----
+    {
+        sbm_f(t, w, p, out);
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            SBM_PV(0, i) = out[i];
+            const double isk = sbm_rcp(atol + rtol * fabs(w[i]));
+            d0 = fma(w[i] * isk, w[i] * isk, d0);
+            d1 = fma(out[i] * isk, out[i] * isk, d1);
+        }
+        d0 = sqrt(d0 * (1.0 / N)); d1 = sqrt(d1 * (1.0 / N));
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, tend);
+#pragma unroll
+        for (int i = 0; i < N; ++i) w[i] = fma(h0, out[i], w[i]);
+        sbm_f(t + h0, w, p, out);
+        double d2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double q = (out[i] - SBM_PV(0, i)) * sbm_rcp(atol + rtol * fabs(SBM_PY(i)));
+            d2 = fma(q, q, d2);
+        }
+        d2 = sqrt(d2 * (1.0 / N)) / h0;
+        const double dm = fmax(d1, d2);
+#ifdef SBM_PUSH_X1
+        const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : (double)__powf((float)(0.01 / dm), 0.2f);
+#else
+        const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
+#endif
+        h = fmin(fmin(100.0 * h0, h1), tend);
+        if (a.h0 > 0.0) h = fmin(a.h0, tend);
+        nrhs += 2;
+    }
+    float facold = 1e-4f;
+    bool last_rejected = false, k1_stale = false, poison = false;
+
+    for (int kt = kt0; kt < kt1; ++kt) {
+        const double tk = a.tout[kt];
+        while (status == SBM_OK && t < tk) {
+            const double hprop = h;
+            bool clipped = false;
+            if (t + 1.01 * h >= tk) { h = tk - t; clipped = true; }
+            if (nstep >= (unsigned)a.max_steps) { status = SBM_ERR_MAXSTEPS; break; }
+            if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) { status = SBM_ERR_UNDERFLOW; break; }
+            nstep++;
+#ifndef SBM_PUSH_X3
+            if (k1_stale) {                                   // after a rejection: V1 holds k7 of the rejected trial
+#pragma unroll
+                for (int i = 0; i < N; ++i) w[i] = SBM_PY(i);
+                sbm_f(t, w, p, out);
+#pragma unroll
+                for (int i = 0; i < N; ++i) SBM_PV(0, i) = out[i];
+                nrhs++;
+                k1_stale = false;
+            }
+#endif
+            double sq = 0.0;
+#ifdef SBM_PUSH_X2
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+            for (int S = 2; S <= 7; ++S) {
+                // ---- stage input ----
+                if (S == 2) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) w[i] = fma(h * DP_A21, SBM_PV(0, i), SBM_PY(i));
+                } else if (S == 3) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) w[i] = fma(h, fma(DP_A32, SBM_PV(1, i), DP_A31 * SBM_PV(0, i)), SBM_PY(i));
+                } else if (S == 4) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i)
+                        w[i] = fma(h, fma(DP_A43, SBM_PV(2, i), fma(DP_A42, SBM_PV(1, i), DP_A41 * SBM_PV(0, i))), SBM_PY(i));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) w[i] = SBM_PV(S - 5, i);
+                }
+                sbm_f(fma(sbm_dp_c[S], h, t), w, p, out);
+                // ---- what the stage does with its derivative ----
+                if (S == 2) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) SBM_PV(1, i) = out[i];
+                } else if (S == 3) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) SBM_PV(2, i) = out[i];
+                } else if (S == 4) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const double k1v = SBM_PV(0, i), k2v = SBM_PV(1, i), k3v = SBM_PV(2, i), k4v = out[i];
+                        SBM_PV(0, i) = fma(h, fma(DP_A54, k4v, fma(DP_A53, k3v, fma(DP_A52, k2v, DP_A51 * k1v))), SBM_PY(i));
+                        SBM_PV(1, i) = fma(h, fma(DP_A64, k4v, fma(DP_A63, k3v, fma(DP_A62, k2v, DP_A61 * k1v))), SBM_PY(i));
+                        SBM_PV(2, i) = fma(h, fma(DP_A74, k4v, fma(DP_A73, k3v, DP_A71 * k1v)), SBM_PY(i));
+                        SBM_PV(3, i) = h * fma(DP_E4, k4v, fma(DP_E3, k3v, DP_E1 * k1v));
+                        SBM_PUSH_FENCE(i);
+                    }
+                } else if (S == 5) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const double hk = h * out[i];
+                        SBM_PV(1, i) = fma(DP_A65, hk, SBM_PV(1, i));
+                        SBM_PV(2, i) = fma(DP_A75, hk, SBM_PV(2, i));
+                        SBM_PV(3, i) = fma(DP_E5, hk, SBM_PV(3, i));
+                        SBM_PUSH_FENCE(i);
+                    }
+                } else if (S == 6) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const double hk = h * out[i];
+                        SBM_PV(2, i) = fma(DP_A76, hk, SBM_PV(2, i));
+                        SBM_PV(3, i) = fma(DP_E6, hk, SBM_PV(3, i));
+                        SBM_PUSH_FENCE(i);
+                    }
+                } else {
+                    // w = the 5th-order solution, out = k7
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        SBM_PV(0, i) = out[i];
+                        const double er = fma(h * DP_E7, out[i], SBM_PV(3, i));
+                        const double q = er * sbm_rcp(atol + rtol * fmax(fabs(SBM_PY(i)), fabs(w[i])));
+                        sq = fma(q, q, sq);
+                    }
+                }
+            }
+            nrhs += 6;
+            const double err = sqrt(sq * (1.0 / N));
+            if (err <= 1.0) {
+                // accept; PI controller (DOPRI5: beta = 0.04, safe = 0.9, fac in [0.2, 10])
+                const float ferr = fmaxf((float)err, 1e-30f);
+                float fac = __powf(ferr, 0.2f - 0.04f * 0.75f) / __powf(facold, 0.04f);
+                fac = fmaxf(0.1f, fminf(5.0f, fac / 0.9f));
+                facold = fmaxf(ferr, 1e-4f);
+                t = clipped ? tk : t + h;
+#pragma unroll
+                for (int i = 0; i < N; ++i) SBM_PY(i) = w[i];
+                double hnew = h / (double)fac;
+                if (last_rejected) hnew = fmin(hnew, h);
+                if (clipped) hnew = fmax(hnew, hprop);       // a clipped step must not shrink the cruise step
+                h = hnew;
+                last_rejected = false;
+            } else {
+                nrej++;
+                last_rejected = true;
+                k1_stale = true;
+                if (err == err && err < 1e300) {
+                    const float ferr = (float)fmin(err, 1e30);
+                    h = h / (double)fminf(5.0f, __powf(ferr, 0.2f - 0.04f * 0.75f) / 0.9f);
+                } else {
+                    h *= 0.1;                                // NaN/Inf in the trial state: retreat hard
+                    if (h < 1e-300) { status = SBM_ERR_NONFINITE; break; }
+                }
+            }
+        }
+        if (status != SBM_OK) poison = true;
+        {
+            double y[1][N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) y[0][i] = SBM_PY(i);
+            sbm_emit_rows<1, 1, 0>(a, b, kt, y, cid, pcol, pscale, poison);
+        }
+    }
+#undef SBM_PV
+#undef SBM_PY
+    a.status[traj] = status;
+    atomicAdd(a.counters + SBM_CNT_STEPS, (unsigned long long)nstep);
+    atomicAdd(a.counters + SBM_CNT_REJECT, (unsigned long long)nrej);
+    atomicAdd(a.counters + SBM_CNT_RHS, (unsigned long long)nrhs);
+    atomicAdd(a.counters + SBM_CNT_TRAJ, 1ull);
+}
+
+#define SBM_DEFINE_DP5_PUSH(NAME, BLOCK)                                                    \
+    extern "C" __global__ void __launch_bounds__(BLOCK) NAME(const SbmSolveArgs a)          \
+    { sbm_dp5_push_impl<BLOCK>(a); }
+
 // x^(1/4) for the Rosenbrock step-size controller: single precision is plenty for a step-size factor that is clamped to
 // [1/6, 5] (the double-precision pow() was ~250 FP64 instructions per step, a fifth of the kernel's FP64 work on C3)
 __device__ __forceinline__ double sbm_root4(const double x)

@@ -137,8 +137,8 @@ struct KernelSlot {
 struct sbm_model {
     sbm_model_desc_t desc{};
     std::string arch;
-    int G = 1, C = 1, block = 128, block_plain = 128;
-    int dyn_smem = 0, dyn_smem_plain = 0;
+    int G = 1, C = 1, block = 128, block_plain = 128, block_push = 128;
+    int dyn_smem = 0, dyn_smem_plain = 0, dyn_smem_push = 0;
     // CTA-transposed sensitivity kernel (kernels/sbm_dp5_ct.cuh): W sensitivity warps x C columns + 1 state warp
     int ctW = 0, ctC = 0, ctCS = 0, ctXW = 0, ct_tmem_cols = 0, ct_dyn_smem = 0, ct_ctas_per_sm = 0, sm_count = 0;
     bool ct_ok = false;
@@ -152,7 +152,7 @@ struct sbm_model {
     bool loaded = false;
     int device = -1;             // device whose context holds `mod` (one module per model; see ensure_loaded)
     CUmodule mod = nullptr;
-    KernelSlot dp5_plain, dp5_plain_dense, dp5_sens, dp5_ct, rodas4, rodas4_dense, rodas4_sens;
+    KernelSlot dp5_plain, dp5_plain_dense, dp5_push, dp5_sens, dp5_ct, rodas4, rodas4_dense, rodas4_sens;
     std::mutex mu;
 };
 
@@ -204,6 +204,8 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     const int npp8 = (desc->n_params | 1) * 8;
     m->block = pick_block(6 * m->C * desc->n_vars * 8 + (npp8 + m->G - 1) / m->G);
     m->block_plain = pick_block(6 * desc->n_vars * 8 + npp8);
+    const int push_nv = desc->n_vars <= 25 ? 4 : 5;    // the push-form kernel keeps the state in registers up to 25 states
+    m->block_push = pick_block(push_nv * desc->n_vars * 8 + npp8);
     if (desc->block_threads > 0) m->block = desc->block_threads;
     if (m->G < 1 || m->G > 32 || (m->G & (m->G - 1)) || m->G * m->C < desc->n_free + 1 || (m->block % 32) || m->block > 1024) {
         delete m;
@@ -211,6 +213,7 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     }
     m->dyn_smem = 6 * m->C * desc->n_vars * m->block * 8;
     m->dyn_smem_plain = 6 * desc->n_vars * m->block_plain * 8;
+    m->dyn_smem_push = push_nv * desc->n_vars * m->block_push * 8;
     if (m->dyn_smem > 200 * 1024 || m->dyn_smem_plain > 200 * 1024) {
         delete m;
         return fail(SBM_E_INVALID, "stage vectors do not fit in shared memory for this group shape");
@@ -259,6 +262,7 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     if (m->ct_ok) src << "SBM_DEFINE_DP5_CT(sbm_dp5_ct, " << m->ctW << ", " << m->ctC << ", " << m->ctXW << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_plain, 1, 1, 0, " << m->block_plain << ")\n";
     src << "SBM_DEFINE_DP5_DENSE(sbm_dp5_plain_dense, " << m->block_plain << ")\n";
+    src << "SBM_DEFINE_DP5_PUSH(sbm_dp5_push, " << m->block_push << ")\n";
     src << "SBM_DEFINE_DP5(sbm_dp5_sens, " << m->G << ", " << m->C << ", 1, " << m->block << ")\n";
     // the Rosenbrock kernel keeps the dense Jacobian and its LU in registers: fine up to ~12 states, hopeless beyond
     m->has_rodas = desc->n_vars <= 12;
@@ -362,6 +366,8 @@ static int ensure_loaded(sbm_model* m)
         int r;
         if ((r = slot_load(m, m->dp5_plain, "sbm_dp5_plain"))) return r;
         if ((r = slot_load(m, m->dp5_plain_dense, "sbm_dp5_plain_dense"))) return r;
+        if ((r = slot_load(m, m->dp5_push, "sbm_dp5_push"))) return r;
+        DRV(driver().cuFuncSetAttribute_(m->dp5_push.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem_push));
         if ((r = slot_load(m, m->dp5_sens, "sbm_dp5_sens"))) return r;
         if (m->has_rodas && (r = slot_load(m, m->rodas4, "sbm_rodas4_plain"))) return r;
         if (m->has_rodas && (r = slot_load(m, m->rodas4_dense, "sbm_rodas4_plain_dense"))) return r;
@@ -605,7 +611,16 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
         RT(cudaMemsetAsync(counters + SBM_CNT_QUEUE, 0, sizeof(unsigned long long), st));
     }
     else if (jac) { ks = &m->dp5_sens; threads = ntraj * m->G; block = m->block; dyn = m->dyn_smem; }
-    else { ks = a.dense ? &m->dp5_plain_dense : &m->dp5_plain; threads = ntraj; dyn = m->dyn_smem_plain; }
+    else if (a.dense) { ks = &m->dp5_plain_dense; threads = ntraj; dyn = m->dyn_smem_plain; }
+    else {
+        // states only: the push-form kernel (4 stage accumulators in shared memory instead of 6 stage derivatives; measured
+        // against the flat stage loop of sbm_dp5_plain: C5 51.1 vs 68.5 ms, C4 31.0 vs 31.8 ms, the 2-state MM model 1.12 vs
+        // 1.65 ms).  SBM_PLAIN_PUSH=0 selects the flat loop (experiments, cross-checks)
+        bool push = true;
+        if (const char* e = getenv("SBM_PLAIN_PUSH")) push = atoi(e) != 0;
+        if (push) { ks = &m->dp5_push; threads = ntraj; block = m->block_push; dyn = m->dyn_smem_push; }
+        else { ks = &m->dp5_plain; threads = ntraj; dyn = m->dyn_smem_plain; }
+    }
     if (blocks < 0) blocks = (threads + block - 1) / block;
     if (blocks > 2147483647ll) return fail(SBM_E_INVALID, "batch too large for one launch");
     void* params[] = {&a};

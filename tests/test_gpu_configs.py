@@ -429,3 +429,33 @@ def test_c5_egfr_sensitivities_vs_lsoda_and_fd():
         Pm[0, j] -= h
         fd = (om.simulate_batch(Pp, t, y0)[0] - om.simulate_batch(Pm, t, y0)[0]) / (2 * h)
         assert np.allclose(S[0, :, :, j], fd, rtol=2e-4, atol=2e-4 * max(np.abs(fd).max(), 1e-12))
+
+
+def test_push_form_kernel_matches_flat_stage_loop():
+    """States-only Dormand-Prince: the push-form kernel (default) against the flat stage loop (SBM_PLAIN_PUSH=0) on the
+    EGFR-scale model - same tableau, same controller: same step counts, results equal to rounding."""
+    import os
+    import sysbio_modeling_b200 as sb
+    from sysbio_modeling_b200 import model_files
+    from tools import workloads as wl
+    sm, nominal, y0 = wl.nominal_of('egfr_signalling')
+    P = np.exp(wl.make_thetas(nominal, 64, 5, 0.1))
+    t = np.concatenate([[0.0], wl.C5_T])
+    om = sb.OdeModel.from_model_file(model_files.path('egfr_signalling'), rtol=1e-9, atol=1e-9)
+    om.dense_output = 2
+    old = os.environ.get('SBM_PLAIN_PUSH')
+    try:
+        os.environ['SBM_PLAIN_PUSH'] = '1'
+        ya = om.simulate_batch(P, t, y0)
+        ca = dict(om.last_counters)
+        assert (om.last_status == 0).all()
+        os.environ['SBM_PLAIN_PUSH'] = '0'
+        yb = om.simulate_batch(P, t, y0)
+        cb = dict(om.last_counters)
+    finally:
+        if old is None:
+            os.environ.pop('SBM_PLAIN_PUSH', None)
+        else:
+            os.environ['SBM_PLAIN_PUSH'] = old
+    assert abs(ca['steps'] - cb['steps']) <= 2 and abs(ca['rejects'] - cb['rejects']) <= 2, (ca, cb)
+    assert np.all(np.abs(ya - yb) <= 1e-9 * (1 + np.abs(yb)))
