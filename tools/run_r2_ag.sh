@@ -1,0 +1,17 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+L=gpurun_out/r2ag.log; : > $L
+timeout 900 python - >> $L 2>&1 <<PY
+import sys, torch, numpy as np
+sys.path.insert(0, '.')
+import bench
+from tools import workloads as wl
+for name, mk, nom, B in (('c4', lambda: wl.c4_project()[0], 'mapk_kholodenko', 65536), ('c5', lambda: wl.c5_project()[0], 'egfr_signalling', 131072)):
+    proj = mk()
+    sm, nominal, _ = wl.nominal_of(nom)
+    th = torch.from_numpy(wl.make_thetas(nominal, B, 5, 0.1)).cuda()
+    (ms_i, ms_l), cnt, failed = bench._time_eval(proj, th, False, 'dp5', 2)
+    print(name, 'states-only ms', round(ms_i, 2), 'solves/s', round(B / ms_i * 1e3), 'steps/solve', cnt['steps'] / B, 'failed', failed)
+PY
+timeout 900 python -m pytest tests/test_gpu_configs.py tests/test_gpu_parity.py tests/test_gpu_bench_parity.py -m gpu -q -x 2>&1 | tail -3 >> $L
+cat $L
