@@ -1067,6 +1067,17 @@ __constant__ double sbm_ro_c[6][5] = {
     {RO_C51, RO_C52, RO_C53, RO_C54, 0.0},
     {RO_C61, RO_C62, RO_C63, RO_C64, RO_C65}};
 
+// small systems (Robertson: 3 states x 3 parameters): stages and columns unrolled, so that the stage increments of the state
+// and of the sensitivity columns are register arrays with compile-time indices instead of local memory
+#if SBM_N * SBM_NF <= 12
+#define SBM_RO_UNROLL_ST 6
+#define SBM_RO_UNROLL_J SBM_NF
+#define SBM_RO_UNROLL_L 5
+#else
+#define SBM_RO_UNROLL_ST 1
+#define SBM_RO_UNROLL_J 1
+#define SBM_RO_UNROLL_L 1
+#endif
 template <int BLOCK>
 __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
 {
@@ -1092,6 +1103,7 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
     int piv[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = a.y0[e * N + i];
+#pragma unroll SBM_RO_UNROLL_J
     for (int j = 0; j < NF; ++j)
 #pragma unroll
         for (int i = 0; i < N; ++i) S[j][i] = 0.0;
@@ -1163,7 +1175,7 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
             const bool lu_ok = sbm_lu_factor(A, piv);
             nlu++;
 
-#pragma unroll 1
+#pragma unroll SBM_RO_UNROLL_ST
             for (int st = 0; st < 6; ++st) {
                 double ca[5], cc[5];
 #pragma unroll
@@ -1173,6 +1185,7 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     double v = y[i], w = 0.0;
+#pragma unroll SBM_RO_UNROLL_L
                     for (int l = 0; l < st; ++l) { v = fma(ca[l], ky[l][i], v); w = fma(cc[l], ky[l][i], w); }
                     Y[i] = v;
                     r[i] = w;
@@ -1191,12 +1204,14 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
                 for (int i = 0; i < N; ++i) ky[st][i] = r[i];
                 // ---- sensitivity blocks: same LU, right-hand side + B_j u_i(y) ----
                 sbm_dJG(t, y, p, r, DJv, DGv);
+#pragma unroll SBM_RO_UNROLL_J
                 for (int j = 0; j < NF; ++j) {
                     double Sj[N], w[N], r1[N], r2[N];
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
                         double v = S[j][i], ww = 0.0;
-                        for (int l = 0; l < st; ++l) { v = fma(ca[l], U[l][j][i], v); ww = fma(cc[l], U[l][j][i], ww); }
+#pragma unroll SBM_RO_UNROLL_L
+                    for (int l = 0; l < st; ++l) { v = fma(ca[l], U[l][j][i], v); ww = fma(cc[l], U[l][j][i], ww); }
                         Sj[i] = v;
                         w[i] = ww;
                     }
@@ -1220,6 +1235,7 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
                 const double q = ky[5][i] * sbm_rcp(sk);
                 sq = fma(q, q, sq);
             }
+#pragma unroll SBM_RO_UNROLL_J
             for (int j = 0; j < NF; ++j) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
@@ -1249,6 +1265,7 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
                 t = clipped ? tk : t + h;
 #pragma unroll
                 for (int i = 0; i < N; ++i) y[i] = Y[i];
+#pragma unroll SBM_RO_UNROLL_J
                 for (int j = 0; j < NF; ++j)
 #pragma unroll
                     for (int i = 0; i < N; ++i) S[j][i] = U[5][j][i];
@@ -1281,6 +1298,7 @@ __device__ __forceinline__ void sbm_rodas4_sens_impl(const SbmSolveArgs& a)
             if (poison) acc = __longlong_as_double(0x7ff8000000000000ll);
             a.sims[b * a.n_rows + a.row_sim[r]] = acc;
             if (a.jac != nullptr) {
+#pragma unroll SBM_RO_UNROLL_J
                 for (int j = 0; j < NF; ++j) {
                     const int m = sbm_free_idx[j];
                     const int pc = a.jac_raw ? j : a.pmap[e * SBM_NP + m];
