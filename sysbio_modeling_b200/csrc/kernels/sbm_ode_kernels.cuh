@@ -447,50 +447,96 @@ __device__ __forceinline__ void sbm_dp5_impl(const SbmSolveArgs& a)
 // Rosenbrock RODAS4 (Hairer & Wanner, stiff; L-stable, order 4(3)), one thread per trajectory,
 // dense LU with partial pivoting held in registers.  States only (no sensitivity columns).
 // ---------------------------------------------------------------------------------------------
-#define RO_GAMMA 0.25
-#define RO_C2 0.386
-#define RO_C3 0.21
-#define RO_C4 0.63
-#define RO_D1 0.25
-#define RO_D2 (-0.1043)
-#define RO_D3 0.1035
-#define RO_D4 (-0.03620000000000023)
-#define RO_A21 1.544
-#define RO_A31 0.9466785280815826
-#define RO_A32 0.2557011698983284
-#define RO_A41 3.314825187068521
-#define RO_A42 2.896124015972201
-#define RO_A43 0.9986419139977817
-#define RO_A51 1.221224509226641
-#define RO_A52 6.019134481288629
-#define RO_A53 12.53708332932087
-#define RO_A54 (-0.6878860361058950)
-#define RO_C21 (-5.6688)
-#define RO_C31 (-2.430093356833875)
-#define RO_C32 (-0.2063599157091915)
-#define RO_C41 (-0.1073529058151375)
-#define RO_C42 (-9.594562251023355)
-#define RO_C43 (-20.47028614809616)
-#define RO_C51 7.496443313967647
-#define RO_C52 (-10.24680431464352)
-#define RO_C53 (-33.99990352819905)
-#define RO_C54 11.70890893206160
-#define RO_C61 8.083246795921522
-#define RO_C62 (-7.981132988064893)
-#define RO_C63 (-31.52159432874371)
-#define RO_C64 16.31930543123136
-#define RO_C65 (-6.058818238834054)
+#define RO_GAMMA_V 0.25
+#define RO_C2_V 0.386
+#define RO_C3_V 0.21
+#define RO_C4_V 0.63
+#define RO_D1_V 0.25
+#define RO_D2_V (-0.1043)
+#define RO_D3_V 0.1035
+#define RO_D4_V (-0.03620000000000023)
+#define RO_A21_V 1.544
+#define RO_A31_V 0.9466785280815826
+#define RO_A32_V 0.2557011698983284
+#define RO_A41_V 3.314825187068521
+#define RO_A42_V 2.896124015972201
+#define RO_A43_V 0.9986419139977817
+#define RO_A51_V 1.221224509226641
+#define RO_A52_V 6.019134481288629
+#define RO_A53_V 12.53708332932087
+#define RO_A54_V (-0.6878860361058950)
+#define RO_C21_V (-5.6688)
+#define RO_C31_V (-2.430093356833875)
+#define RO_C32_V (-0.2063599157091915)
+#define RO_C41_V (-0.1073529058151375)
+#define RO_C42_V (-9.594562251023355)
+#define RO_C43_V (-20.47028614809616)
+#define RO_C51_V 7.496443313967647
+#define RO_C52_V (-10.24680431464352)
+#define RO_C53_V (-33.99990352819905)
+#define RO_C54_V 11.70890893206160
+#define RO_C61_V 8.083246795921522
+#define RO_C62_V (-7.981132988064893)
+#define RO_C63_V (-31.52159432874371)
+#define RO_C64_V 16.31930543123136
+#define RO_C65_V (-6.058818238834054)
 // dense output (rodas.f, RODAS4: D21..D25, D31..D35)
-#define RO_D21 10.12623508344586
-#define RO_D22 (-7.487995877610167)
-#define RO_D23 (-34.80091861555747)
-#define RO_D24 (-7.992771707568823)
-#define RO_D25 1.025137723295662
-#define RO_D31 (-0.6762803392801253)
-#define RO_D32 6.087714651680015
-#define RO_D33 16.43084320892478
-#define RO_D34 24.76722511418386
-#define RO_D35 (-6.594389125716872)
+#define RO_D21_V 10.12623508344586
+#define RO_D22_V (-7.487995877610167)
+#define RO_D23_V (-34.80091861555747)
+#define RO_D24_V (-7.992771707568823)
+#define RO_D25_V 1.025137723295662
+#define RO_D31_V (-0.6762803392801253)
+#define RO_D32_V 6.087714651680015
+#define RO_D33_V 16.43084320892478
+#define RO_D34_V 24.76722511418386
+#define RO_D35_V (-6.594389125716872)
+// the Rosenbrock coefficients as FMA operands straight from the constant bank (literal doubles are materialised with two
+// moves each: UMOV + IMAD were 20 % of the executed instructions of sbm_rodas4_plain, profiles/r02_rodas4_plain_final.txt)
+__constant__ double sbm_roc[43] = {RO_GAMMA_V, RO_C2_V, RO_C3_V, RO_C4_V, RO_D1_V, RO_D2_V, RO_D3_V, RO_D4_V, RO_A21_V, RO_A31_V, RO_A32_V, RO_A41_V, RO_A42_V, RO_A43_V, RO_A51_V, RO_A52_V, RO_A53_V, RO_A54_V, RO_C21_V, RO_C31_V, RO_C32_V, RO_C41_V, RO_C42_V, RO_C43_V, RO_C51_V, RO_C52_V, RO_C53_V, RO_C54_V, RO_C61_V, RO_C62_V, RO_C63_V, RO_C64_V, RO_C65_V, RO_D21_V, RO_D22_V, RO_D23_V, RO_D24_V, RO_D25_V, RO_D31_V, RO_D32_V, RO_D33_V, RO_D34_V, RO_D35_V};
+#define RO_GAMMA sbm_roc[0]
+#define RO_C2 sbm_roc[1]
+#define RO_C3 sbm_roc[2]
+#define RO_C4 sbm_roc[3]
+#define RO_D1 sbm_roc[4]
+#define RO_D2 sbm_roc[5]
+#define RO_D3 sbm_roc[6]
+#define RO_D4 sbm_roc[7]
+#define RO_A21 sbm_roc[8]
+#define RO_A31 sbm_roc[9]
+#define RO_A32 sbm_roc[10]
+#define RO_A41 sbm_roc[11]
+#define RO_A42 sbm_roc[12]
+#define RO_A43 sbm_roc[13]
+#define RO_A51 sbm_roc[14]
+#define RO_A52 sbm_roc[15]
+#define RO_A53 sbm_roc[16]
+#define RO_A54 sbm_roc[17]
+#define RO_C21 sbm_roc[18]
+#define RO_C31 sbm_roc[19]
+#define RO_C32 sbm_roc[20]
+#define RO_C41 sbm_roc[21]
+#define RO_C42 sbm_roc[22]
+#define RO_C43 sbm_roc[23]
+#define RO_C51 sbm_roc[24]
+#define RO_C52 sbm_roc[25]
+#define RO_C53 sbm_roc[26]
+#define RO_C54 sbm_roc[27]
+#define RO_C61 sbm_roc[28]
+#define RO_C62 sbm_roc[29]
+#define RO_C63 sbm_roc[30]
+#define RO_C64 sbm_roc[31]
+#define RO_C65 sbm_roc[32]
+#define RO_D21 sbm_roc[33]
+#define RO_D22 sbm_roc[34]
+#define RO_D23 sbm_roc[35]
+#define RO_D24 sbm_roc[36]
+#define RO_D25 sbm_roc[37]
+#define RO_D31 sbm_roc[38]
+#define RO_D32 sbm_roc[39]
+#define RO_D33 sbm_roc[40]
+#define RO_D34 sbm_roc[41]
+#define RO_D35 sbm_roc[42]
 
 // ---------------------------------------------------------------------------------------------
 // States-only Dormand-Prince 5(4) in PUSH form, one thread per trajectory (round 2; C5: 25 states, 131,072 walkers).
@@ -1054,18 +1100,18 @@ __device__ __forceinline__ void sbm_rodas4_impl(const SbmSolveArgs& a)
 #if SBM_AUTONOMOUS && defined(SBM_HAS_DJG)
 __constant__ double sbm_ro_a[6][5] = {
     {0.0, 0.0, 0.0, 0.0, 0.0},
-    {RO_A21, 0.0, 0.0, 0.0, 0.0},
-    {RO_A31, RO_A32, 0.0, 0.0, 0.0},
-    {RO_A41, RO_A42, RO_A43, 0.0, 0.0},
-    {RO_A51, RO_A52, RO_A53, RO_A54, 0.0},
-    {RO_A51, RO_A52, RO_A53, RO_A54, 1.0}};
+    {RO_A21_V, 0.0, 0.0, 0.0, 0.0},
+    {RO_A31_V, RO_A32_V, 0.0, 0.0, 0.0},
+    {RO_A41_V, RO_A42_V, RO_A43_V, 0.0, 0.0},
+    {RO_A51_V, RO_A52_V, RO_A53_V, RO_A54_V, 0.0},
+    {RO_A51_V, RO_A52_V, RO_A53_V, RO_A54_V, 1.0}};
 __constant__ double sbm_ro_c[6][5] = {
     {0.0, 0.0, 0.0, 0.0, 0.0},
-    {RO_C21, 0.0, 0.0, 0.0, 0.0},
-    {RO_C31, RO_C32, 0.0, 0.0, 0.0},
-    {RO_C41, RO_C42, RO_C43, 0.0, 0.0},
-    {RO_C51, RO_C52, RO_C53, RO_C54, 0.0},
-    {RO_C61, RO_C62, RO_C63, RO_C64, RO_C65}};
+    {RO_C21_V, 0.0, 0.0, 0.0, 0.0},
+    {RO_C31_V, RO_C32_V, 0.0, 0.0, 0.0},
+    {RO_C41_V, RO_C42_V, RO_C43_V, 0.0, 0.0},
+    {RO_C51_V, RO_C52_V, RO_C53_V, RO_C54_V, 0.0},
+    {RO_C61_V, RO_C62_V, RO_C63_V, RO_C64_V, RO_C65_V}};
 
 // small systems (Robertson: 3 states x 3 parameters): stages and columns unrolled, so that the stage increments of the state
 // and of the sensitivity columns are register arrays with compile-time indices instead of local memory
