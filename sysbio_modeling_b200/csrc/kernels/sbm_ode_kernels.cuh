@@ -560,18 +560,13 @@ template <int BLOCK>
 __device__ __forceinline__ void sbm_dp5_push_impl(const SbmSolveArgs& a)
 {
     constexpr int N = SBM_N;
+    constexpr unsigned FULL = 0xffffffffu;
     __shared__ double sp[BLOCK * SBM_NPP];
     extern __shared__ double sbm_dyn[];            // [4 or 5][N][BLOCK]: V1..V4 (and the state y when it is not in registers)
-    const int tid = threadIdx.x;
-    const long long traj = (long long)blockIdx.x * BLOCK + tid;
-    if (traj >= a.B * (long long)a.E) return;
-    const int e = (int)(traj % a.E);
-    const long long b = traj / a.E;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long ntraj = a.B * (long long)a.E;
+    unsigned long long* queue = a.counters + SBM_CNT_QUEUE;
     double* p = sp + tid * SBM_NPP;
-    for (int m = 0; m < SBM_NP; ++m) {
-        const int c = a.pmap[e * SBM_NP + m];
-        p[m] = (c >= 0) ? exp(a.theta[b * a.theta_sb + c * a.theta_sp]) : a.pfix[e * SBM_NP + m];
-    }
     double* V = sbm_dyn + tid;
     // keeps ptxas from hoisting all 3 N loads of an update above its FMA chains (the live ranges cost 1.7 KB of spills)
 #ifndef SBM_PUSH_FENCE_EVERY
@@ -583,85 +578,124 @@ __device__ __forceinline__ void sbm_dp5_push_impl(const SbmSolveArgs& a)
     const int pcol[1] = {-1};
     const double pscale[1] = {0.0};
     // the state in registers while three state-sized arrays fit the register file, in shared memory beyond
-#if SBM_N <= 25 && !defined(SBM_PUSH_YSMEM)
+#ifndef SBM_PUSH_YREG_MAX
+#define SBM_PUSH_YREG_MAX 25
+#endif
+#if SBM_N <= SBM_PUSH_YREG_MAX
     double yreg[N];
 #define SBM_PY(i) yreg[i]
 #else
 #define SBM_PY(i) SBM_PV(4, i)
 #endif
     double w[N], out[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) { SBM_PY(i) = a.y0[e * N + i]; w[i] = a.y0[e * N + i]; }
-
     const double rtol = a.rtol, atol = a.atol;
-    const int kt0 = a.tout_off[e], kt1 = a.tout_off[e + 1];
-    const double tend = (kt1 > kt0) ? a.tout[kt1 - 1] : 1.0;
-    unsigned nstep = 0, nrej = 0, nrhs = 0;
-    int status = SBM_OK;
-    double t = 0.0, h;
-    // ---- k1 and the initial step size (Hairer, Norsett, Wanner II.4) ----
-    {
-        sbm_f(t, w, p, out);
-        double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            SBM_PV(0, i) = out[i];
-            const double isk = sbm_rcp(atol + rtol * fabs(w[i]));
-            d0 = fma(w[i] * isk, w[i] * isk, d0);
-            d1 = fma(out[i] * isk, out[i] * isk, d1);
-        }
-        d0 = sqrt(d0 * (1.0 / N)); d1 = sqrt(d1 * (1.0 / N));
-        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        h0 = fmin(h0, tend);
-#pragma unroll
-        for (int i = 0; i < N; ++i) w[i] = fma(h0, out[i], w[i]);
-        sbm_f(t + h0, w, p, out);
-        double d2 = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double q = (out[i] - SBM_PV(0, i)) * sbm_rcp(atol + rtol * fabs(SBM_PY(i)));
-            d2 = fma(q, q, d2);
-        }
-        d2 = sqrt(d2 * (1.0 / N)) / h0;
-        const double dm = fmax(d1, d2);
-#ifdef SBM_PUSH_X1
-        const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : (double)__powf((float)(0.01 / dm), 0.2f);
-#else
-        const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
-#endif
-        h = fmin(fmin(100.0 * h0, h1), tend);
-        if (a.h0 > 0.0) h = fmin(a.h0, tend);
-        nrhs += 2;
-    }
-    float facold = 1e-4f;
-    bool last_rejected = false, k1_stale = false, poison = false;
 
-    for (int kt = kt0; kt < kt1; ++kt) {
-        const double tk = a.tout[kt];
-        while (status == SBM_OK && t < tk) {
-            const double hprop = h;
-            bool clipped = false;
-            if (t + 1.01 * h >= tk) { h = tk - t; clipped = true; }
-            if (nstep >= (unsigned)a.max_steps) { status = SBM_ERR_MAXSTEPS; break; }
-            if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) { status = SBM_ERR_UNDERFLOW; break; }
+    // A persistent grid: a lane that finishes its trajectory takes the next one from a global queue (one warp-aggregated
+    // atomic), so the lanes of a warp stay busy although their step counts differ (a one-trajectory-per-thread launch ran at
+    // 26.6 of 32 lanes on C5, profiles/r02_dp5_push.txt).  One loop: [fetch + start-up of the lanes that need it] + [one step
+    // attempt of every lane that has a trajectory, its output rows when the step lands on an output time].
+    long long traj = -1, b = 0;
+    int e = 0, kt = 0, kt1 = 0, status = SBM_OK;
+    double t = 0.0, h = 0.0, tk = 0.0;
+    float facold = 1e-4f;
+    bool last_rejected = false, k1_stale = false, exhausted = false;
+    unsigned nstep = 0;                            // of the trajectory in flight (step budget)
+    unsigned long long c_step = 0, c_rej = 0, c_rhs = 0, c_traj = 0;
+
+    for (;;) {
+        // ---- fetch ----
+        const bool need = (traj < 0) && !exhausted;
+        const unsigned want = __ballot_sync(FULL, need);
+        if (want) {
+            const int leader = __ffs(want) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(want));
+            base = __shfl_sync(FULL, base, leader);
+            if (need) {
+                const long long nt = (long long)base + __popc(want & ((1u << lane) - 1u));
+                if (nt >= ntraj) {
+                    exhausted = true;
+                } else {
+                    traj = nt;
+                    e = (int)(traj % a.E);
+                    b = traj / a.E;
+                    for (int m = 0; m < SBM_NP; ++m) {
+                        const int c = a.pmap[e * SBM_NP + m];
+                        p[m] = (c >= 0) ? exp(a.theta[b * a.theta_sb + c * a.theta_sp]) : a.pfix[e * SBM_NP + m];
+                    }
+#pragma unroll
+                    for (int i = 0; i < N; ++i) { SBM_PY(i) = a.y0[e * N + i]; w[i] = a.y0[e * N + i]; }
+                    kt = a.tout_off[e];
+                    kt1 = a.tout_off[e + 1];
+                    status = SBM_OK;
+                    t = 0.0;
+                    nstep = 0;
+                    facold = 1e-4f;
+                    last_rejected = false;
+                    k1_stale = false;
+                    if (kt >= kt1) {                          // no output times: nothing to integrate
+                        a.status[traj] = SBM_OK;
+                        c_traj++;
+                        traj = -1;
+                    } else {
+                        tk = a.tout[kt];
+                        const double tend = a.tout[kt1 - 1];
+                        // ---- k1 and the initial step size (Hairer, Norsett, Wanner II.4) ----
+                        sbm_f(t, w, p, out);
+                        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            SBM_PV(0, i) = out[i];
+                            const double isk = sbm_rcp(atol + rtol * fabs(w[i]));
+                            d0 = fma(w[i] * isk, w[i] * isk, d0);
+                            d1 = fma(out[i] * isk, out[i] * isk, d1);
+                        }
+                        d0 = sqrt(d0 * (1.0 / N)); d1 = sqrt(d1 * (1.0 / N));
+                        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+                        h0 = fmin(h0, tend);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) w[i] = fma(h0, out[i], w[i]);
+                        sbm_f(t + h0, w, p, out);
+                        double d2 = 0.0;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            const double q = (out[i] - SBM_PV(0, i)) * sbm_rcp(atol + rtol * fabs(SBM_PY(i)));
+                            d2 = fma(q, q, d2);
+                        }
+                        d2 = sqrt(d2 * (1.0 / N)) / h0;
+                        const double dm = fmax(d1, d2);
+                        const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
+                        h = fmin(fmin(100.0 * h0, h1), tend);
+                        if (a.h0 > 0.0) h = fmin(a.h0, tend);
+                        c_rhs += 2;
+                    }
+                }
+            }
+        }
+        if (__all_sync(FULL, traj < 0 && exhausted)) break;
+        if (traj < 0) continue;
+
+        // ---- one step attempt ----
+        const double hprop = h;
+        bool clipped = false;
+        if (t + 1.01 * h >= tk) { h = tk - t; clipped = true; }
+        if (nstep >= (unsigned)a.max_steps) status = SBM_ERR_MAXSTEPS;
+        else if (!clipped && !(h > 1e-15 * fmax(t, 1e-300))) status = SBM_ERR_UNDERFLOW;
+        bool landed = false;
+        if (status == SBM_OK) {
             nstep++;
-#ifndef SBM_PUSH_X3
+            c_step++;
             if (k1_stale) {                                   // after a rejection: V1 holds k7 of the rejected trial
 #pragma unroll
                 for (int i = 0; i < N; ++i) w[i] = SBM_PY(i);
                 sbm_f(t, w, p, out);
 #pragma unroll
                 for (int i = 0; i < N; ++i) SBM_PV(0, i) = out[i];
-                nrhs++;
+                c_rhs++;
                 k1_stale = false;
             }
-#endif
             double sq = 0.0;
-#ifdef SBM_PUSH_X2
-#pragma unroll
-#else
 #pragma unroll 1
-#endif
             for (int S = 2; S <= 7; ++S) {
                 // ---- stage input ----
                 if (S == 2) {
@@ -724,7 +758,7 @@ __device__ __forceinline__ void sbm_dp5_push_impl(const SbmSolveArgs& a)
                     }
                 }
             }
-            nrhs += 6;
+            c_rhs += 6;
             const double err = sqrt(sq * (1.0 / N));
             if (err <= 1.0) {
                 // accept; PI controller (DOPRI5: beta = 0.04, safe = 0.9, fac in [0.2, 10])
@@ -733,6 +767,7 @@ __device__ __forceinline__ void sbm_dp5_push_impl(const SbmSolveArgs& a)
                 fac = fmaxf(0.1f, fminf(5.0f, fac / 0.9f));
                 facold = fmaxf(ferr, 1e-4f);
                 t = clipped ? tk : t + h;
+                landed = clipped;
 #pragma unroll
                 for (int i = 0; i < N; ++i) SBM_PY(i) = w[i];
                 double hnew = h / (double)fac;
@@ -741,7 +776,7 @@ __device__ __forceinline__ void sbm_dp5_push_impl(const SbmSolveArgs& a)
                 h = hnew;
                 last_rejected = false;
             } else {
-                nrej++;
+                c_rej++;
                 last_rejected = true;
                 k1_stale = true;
                 if (err == err && err < 1e300) {
@@ -749,25 +784,44 @@ __device__ __forceinline__ void sbm_dp5_push_impl(const SbmSolveArgs& a)
                     h = h / (double)fminf(5.0f, __powf(ferr, 0.2f - 0.04f * 0.75f) / 0.9f);
                 } else {
                     h *= 0.1;                                // NaN/Inf in the trial state: retreat hard
-                    if (h < 1e-300) { status = SBM_ERR_NONFINITE; break; }
+                    if (h < 1e-300) status = SBM_ERR_NONFINITE;
                 }
             }
         }
-        if (status != SBM_OK) poison = true;
-        {
+        // ---- output rows: the step landed on an output time, or the trajectory failed (the remaining rows become NaN) ----
+        if (landed || status != SBM_OK) {
             double y[1][N];
 #pragma unroll
             for (int i = 0; i < N; ++i) y[0][i] = SBM_PY(i);
-            sbm_emit_rows<1, 1, 0>(a, b, kt, y, cid, pcol, pscale, poison);
+            do {
+                sbm_emit_rows<1, 1, 0>(a, b, kt, y, cid, pcol, pscale, status != SBM_OK);
+                kt++;
+            } while (status != SBM_OK && kt < kt1);
+            if (kt >= kt1) {
+                a.status[traj] = status;
+                c_traj++;
+                traj = -1;
+            } else {
+                tk = a.tout[kt];
+            }
         }
     }
 #undef SBM_PV
 #undef SBM_PY
-    a.status[traj] = status;
-    atomicAdd(a.counters + SBM_CNT_STEPS, (unsigned long long)nstep);
-    atomicAdd(a.counters + SBM_CNT_REJECT, (unsigned long long)nrej);
-    atomicAdd(a.counters + SBM_CNT_RHS, (unsigned long long)nrhs);
-    atomicAdd(a.counters + SBM_CNT_TRAJ, 1ull);
+    // ---- counters: one atomic per warp ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c_step += __shfl_xor_sync(FULL, c_step, o);
+        c_rej += __shfl_xor_sync(FULL, c_rej, o);
+        c_rhs += __shfl_xor_sync(FULL, c_rhs, o);
+        c_traj += __shfl_xor_sync(FULL, c_traj, o);
+    }
+    if (lane == 0) {
+        atomicAdd(a.counters + SBM_CNT_STEPS, c_step);
+        atomicAdd(a.counters + SBM_CNT_REJECT, c_rej);
+        atomicAdd(a.counters + SBM_CNT_RHS, c_rhs);
+        atomicAdd(a.counters + SBM_CNT_TRAJ, c_traj);
+    }
 }
 
 #define SBM_DEFINE_DP5_PUSH(NAME, BLOCK)                                                    \

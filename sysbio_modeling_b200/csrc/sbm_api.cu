@@ -204,7 +204,11 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     const int npp8 = (desc->n_params | 1) * 8;
     m->block = pick_block(6 * m->C * desc->n_vars * 8 + (npp8 + m->G - 1) / m->G);
     m->block_plain = pick_block(6 * desc->n_vars * 8 + npp8);
-    const int push_nv = desc->n_vars <= 25 ? 4 : 5;    // the push-form kernel keeps the state in registers up to 25 states
+    // the push-form kernel keeps the state in registers up to SBM_PUSH_YREG_MAX states (sbm_ode_kernels.cuh), beyond that in a
+    // fifth shared-memory vector
+    int push_yreg_max = 25;
+    if (const char* e = getenv("SBM_PUSH_YREG_MAX")) push_yreg_max = atoi(e);
+    const int push_nv = desc->n_vars <= push_yreg_max ? 4 : 5;
     m->block_push = pick_block(push_nv * desc->n_vars * 8 + npp8);
     if (desc->block_threads > 0) m->block = desc->block_threads;
     if (m->G < 1 || m->G > 32 || (m->G & (m->G - 1)) || m->G * m->C < desc->n_free + 1 || (m->block % 32) || m->block > 1024) {
@@ -274,8 +278,9 @@ extern "C" int sbm_model_compile(const char* model_src, const sbm_model_desc_t* 
     m->source = src.str();
 
     const std::string archopt = "--gpu-architecture=" + m->arch;
+    const std::string yregopt = "-DSBM_PUSH_YREG_MAX=" + std::to_string(push_yreg_max);
     std::vector<const char*> opts = {archopt.c_str(), "--std=c++17", "-lineinfo", "--fmad=true",
-                                     "--ptxas-options=-v", "-DSBM_NVRTC=1"};
+                                     "--ptxas-options=-v", "-DSBM_NVRTC=1", yregopt.c_str()};
     // extra -D options for experiments (e.g. SBM_KERNEL_DEFINES="-DSBM_CT_PROF=1 -DSBM_CT_Y_SMEM=1")
     std::vector<std::string> extra_defs;
     if (const char* ed = getenv("SBM_KERNEL_DEFINES")) {
@@ -618,7 +623,17 @@ extern "C" int sbm_solve(sbm_plan* p, const sbm_solver_opts_t* o, long long B,
         // 1.65 ms).  SBM_PLAIN_PUSH=0 selects the flat loop (experiments, cross-checks)
         bool push = true;
         if (const char* e = getenv("SBM_PLAIN_PUSH")) push = atoi(e) != 0;
-        if (push) { ks = &m->dp5_push; threads = ntraj; block = m->block_push; dyn = m->dyn_smem_push; }
+        if (push) {
+            // persistent grid, trajectories handed out through the queue counter (as for the CTA-transposed kernel)
+            ks = &m->dp5_push; threads = ntraj; block = m->block_push; dyn = m->dyn_smem_push;
+            int per_sm = 0;
+            DRV(driver().cuOccupancy_(&per_sm, ks->fn, block, (size_t)dyn));
+            if (per_sm < 1) per_sm = 1;
+            blocks = (ntraj + block - 1) / block;
+            const long long resident = (long long)m->sm_count * per_sm;
+            if (blocks > resident) blocks = resident;
+            RT(cudaMemsetAsync(counters + SBM_CNT_QUEUE, 0, sizeof(unsigned long long), st));
+        }
         else { ks = &m->dp5_plain; threads = ntraj; dyn = m->dyn_smem_plain; }
     }
     if (blocks < 0) blocks = (threads + block - 1) / block;
