@@ -1501,8 +1501,10 @@ __device__ __forceinline__ void sbm_ctl_warp(const SbmSolveArgs& a, const SbmCtS
 }
 
 // ---- model warp ---------------------------------------------------------------------------------------------------
-// stage value Y_S = y + h sum_j a_Sj f_j of the state column into sh.Pb (one value per state and lane), S = 3..7
-__device__ __forceinline__ void sbm_ctl_form_y(const SbmCtShared& sh, const int lane, const int S, const double h)
+// stage value Y_S = y + h sum_j a_Sj f_j of the state column, S = 3..7, in registers: the model reads it from there (through
+// shared memory the hand-over cost a store, a load and their latency at the head of the critical chain of every evaluation)
+__device__ __forceinline__ void sbm_ctl_form_y(const SbmCtShared& sh, const int lane, const int S, const double h,
+                                               double (&Y)[SBM_N])
 {
     double cf[6];
 #pragma unroll
@@ -1512,17 +1514,18 @@ __device__ __forceinline__ void sbm_ctl_form_y(const SbmCtShared& sh, const int 
         double v = 0.0;
 #pragma unroll
         for (int j = 0; j < 6; ++j) v = fma(cf[j], sh.fh[(j * SBM_N + i) * 32 + lane], v);
-        sh.Pb[i * 32 + lane] = fma(h, v, sh.yb[i * 32 + lane]);
+        Y[i] = fma(h, v, sh.yb[i * 32 + lane]);
     }
 }
 
-// the model at the stage value in sh.Pb -> J, G of stage S (buffer S & 1), f_S
-__device__ __forceinline__ void sbm_ctl_model(const SbmCtShared& sh, const int share, const int lane, const int S, const double ts)
+// the model at the stage value Y -> J, G of stage S (buffer S & 1), f_S
+__device__ __forceinline__ void sbm_ctl_model(const SbmCtShared& sh, const int share, const int lane, const int S, const double ts,
+                                              const double (&Y)[SBM_N])
 {
     const int b = S & 1;
     SBM_CT_JIT(16u + S);
-    sbm_primal_share<32>(share, ts, sh.Pb + lane, sh.Pb + lane, 0.0, sh.pb + lane, sh.Jb + b * SBM_NJS * 32 + lane,
-                         sh.Gd + b * SBM_NF * (SBM_N + (SBM_N & 1)) * 32 + 2 * lane, sh.fh + (S - 1) * SBM_N * 32 + lane);
+    sbm_primal_share<32, 1>(share, ts, Y, Y, 0.0, sh.pb + lane, sh.Jb + b * SBM_NJS * 32 + lane,
+                            sh.Gd + b * SBM_NF * (SBM_N + (SBM_N & 1)) * 32 + 2 * lane, sh.fh + (S - 1) * SBM_N * 32 + lane);
 }
 
 struct SbmCtlRegs {
@@ -1810,9 +1813,7 @@ __device__ __forceinline__ void sbm_ctl_model_warp(const SbmSolveArgs& a, const 
     // prologue: every lane is idle; fetch trajectories, publish the first step, model at the input of its stage 2
     sbm_ctl_setup<W>(a, sh, lane, r);
     __syncwarp();
-#pragma unroll
-    for (int i = 0; i < N; ++i) sh.Pb[i * 32 + lane] = r.ynew[i];
-    sbm_ctl_model(sh, warp, lane, 2, sh.cd[SBM_CTL_D_TS * 32 + lane]);
+    sbm_ctl_model(sh, warp, lane, 2, sh.cd[SBM_CTL_D_TS * 32 + lane], r.ynew);
     SBM_CT_BAR(NT);
 #ifdef SBM_CT_PROF
     tprev = sbm_ct_clock_after_barrier(sh.cta);
@@ -1828,12 +1829,13 @@ __device__ __forceinline__ void sbm_ctl_model_warp(const SbmSolveArgs& a, const 
 #endif
 #pragma unroll 1
         for (int S = 3; S <= 7; ++S) {
-            sbm_ctl_form_y(sh, lane, S, h);
+            double Y[N];
+            sbm_ctl_form_y(sh, lane, S, h, Y);
             if (S == 7) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) r.ynew[i] = sh.Pb[i * 32 + lane];
+                for (int i = 0; i < N; ++i) r.ynew[i] = Y[i];
             }
-            sbm_ctl_model(sh, warp, lane, S, fma(sbm_dp_c[S], h, t));
+            sbm_ctl_model(sh, warp, lane, S, fma(sbm_dp_c[S], h, t), Y);
             // interval 4 is bound by the column warps (the conversion of k1..k4): the set-up of the next step fits here -
             // column warp 0 finished the bookkeeping of the previous step in interval 3
             if (S == 5) sbm_ctl_setup<W>(a, sh, lane, r);
@@ -1859,9 +1861,10 @@ __device__ __forceinline__ void sbm_ctl_model_warp(const SbmSolveArgs& a, const 
         {
             const double hs = sh.hb[lane];
             // (a lane that has just fetched starts from y0: its committed state, which the stage value of stage 7 repeats)
+            double Y[N];
 #pragma unroll
-            for (int i = 0; i < N; ++i) sh.Pb[i * 32 + lane] = fma(hs * DP_A21, r.f7[i], r.ynew[i]);
-            sbm_ctl_model(sh, warp, lane, 2, fma(DP_C2, hs, sh.cd[SBM_CTL_D_TS * 32 + lane]));
+            for (int i = 0; i < N; ++i) Y[i] = fma(hs * DP_A21, r.f7[i], r.ynew[i]);
+            sbm_ctl_model(sh, warp, lane, 2, fma(DP_C2, hs, sh.cd[SBM_CTL_D_TS * 32 + lane]), Y);
         }
 #ifdef SBM_CT_PROF
         busy[7] += clock64() - tprev;

@@ -688,7 +688,7 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0, f
         assign(w, [it])
     L.append('// primal shares of the CTA-transposed kernel: estimated instructions per warp = %s'
              % ', '.join('%d' % int(v) for v in loads))
-    L.append('template <int PS>')
+    L.append('template <int PS, int YS = 32>   // YS: stride of Pp / fl (32: [state][lane] in shared memory, 1: a register array)')
     L.append('// Pp: partial stage value y + h sum_{j<s} a_{s+1,j} f_j (prepared one iteration earlier), fl: f_s, cl = h a_{s+1,s}')
     L.append('__device__ __forceinline__ void %s(const int share, const double t,' % fname)
     L.append('        const double* __restrict__ Pp, const double* __restrict__ fl, const double cl,')
@@ -707,7 +707,7 @@ def _emit_primal_shares(L, pr, N, f_x, J_x, G_x, gkeys, W, C, NF, ysyms, XW=0, f
         need = sorted(ypat[str(x)] for x in need_syms if str(x) in ypat)
         for i in need:
             # stage value of state i = prepared partial sum + the newest stage derivative
-            L.append('        const double Y%d = fma(cl, fl[%d * 32], Pp[%d * 32]);' % (i, i, i))
+            L.append('        const double Y%d = fma(cl, fl[%d * YS], Pp[%d * YS]);' % (i, i, i))
         body = []
         for k in rsym:
             if k in have[w]:
