@@ -567,13 +567,14 @@ class Project(object):
     def _warn_failed(self, status):
         """Numerical failure is not an exception in the reference - it is inf residuals / Jacobian - but
         a silent inf hides WHY: surface the integrator's per-trajectory status (max_steps: typically a stiff region the
-        explicit sensitivity integrator cannot cross - the stiff kernel integrates states only)."""
+        explicit integrator cannot cross - solver='rodas4' / 'auto' select the Rosenbrock kernels)."""
         status = np.asarray(status)
         if status.size and np.any(status != 0):
             bad = status[status != 0]
             names = sorted(set(_lib.STATUS_NAMES.get(int(x), str(int(x))) for x in bad))
             warnings.warn('%d of %d trajectories failed in the integrator (%s): their parameter sets get inf residuals; '
-                          'the sensitivity path is explicit (DP5) - a stiff model needs solver="rodas4" (states only)'
+                          'with the explicit integrator (solver="dp5") a stiff model exhausts its step budget - use '
+                          'solver="rodas4" or "auto" (sensitivities: autonomous models of at most 12 states)'
                           % (bad.size, status.size, ', '.join(names)), RuntimeWarning, stacklevel=3)
 
     def _store_last(self, theta, out, with_jac):
